@@ -1,0 +1,315 @@
+/*
+ * fmcmc_b200.h — C ABI of libfmcmcb200.so, the B200-native drop-in for the
+ * multi-chain Metropolis-Hastings hot path of the R package fmcmc (v0.6-0).
+ *
+ * Everything here is plain C: pointers, sizes, PODs.  No torch / CUDA types
+ * cross this boundary.  The reference-side binding (R `.Call` shim, or the
+ * Python ctypes mirror shipped in fmcmc_b200/) is shown in INTEGRATION.md.
+ *
+ * Reference interfaces replaced (file:line in USCbiostats/fmcmc):
+ *   fmcmc_run            R/mcmc.R:485-838 (MCMC_without_conv_checker: chain
+ *                        fan-out 643-673, MH loop 726-783, burnin/thin 786-813)
+ *   fmcmc_kernel_spec    R/kernel.R:283-317 (kernel_new env), hyper-parameters of
+ *                        R/kernel_normal.R:26-31,96-103  R/kernel_unif.R:15-20,74-81
+ *                        R/kernel_adapt.R:54-66  R/kernel_ram.R:65-79
+ *                        R/kernel_mirror.R:54-64,177-187
+ *   per-chain state      the mutable fields of those environments (abs_iter,
+ *                        Sigma, Mean_t_prev, mu, scale, obs_arate, nerrors) that
+ *                        R/mcmc.R:629-631 ships back from PSOCK workers
+ *   fmcmc_model_*        the user closure `fun` (README.md:128-139,356-360;
+ *                        vignettes/workflow-with-fmcmc.Rmd:35-41;
+ *                        vignettes/advanced-features.Rmd:46-53;
+ *                        playground/hierarchical-bayes.Rmd:45-51)
+ *   fmcmc_store_* / fmcmc_gelman*   R/mcmc.R:947-968 (append_chains + checker
+ *                        call) and R/convergence.R:191-246 -> coda::gelman.diag
+ *   fmcmc_cov_recursive / fmcmc_mean_recursive / fmcmc_reflect
+ *                        R/recursive.R:63-139, R/kernel.R:450-493 (exported R fns)
+ *
+ * Conventions
+ *   - every entry point returns an int status (0 = FMCMC_OK) and, where it takes
+ *     `err`/`errlen`, writes a NUL-terminated message on failure;
+ *   - the caller owns every host buffer it passes; the library never frees it;
+ *   - device memory is owned by the opaque handles;
+ *   - all calls for one handle must come from one host thread (the R main thread).
+ */
+#ifndef FMCMC_B200_H
+#define FMCMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMCMC_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------- */
+enum {
+  FMCMC_OK        = 0,
+  FMCMC_EINVAL    = 1,  /* bad argument (message says which; same substrings as the R errors) */
+  FMCMC_ENAN      = 2,  /* fun(par) undefined at some step (R/mcmc.R:758-765)  */
+  FMCMC_ECUDA     = 3,  /* CUDA runtime error                                  */
+  FMCMC_ENOMEM    = 4,
+  FMCMC_ENOTPD    = 5,  /* kernel_adapt: Sigma not positive definite (MASS::mvrnorm stop) */
+  FMCMC_EUNSUP    = 6,  /* configuration the reference itself mishandles or not built */
+  FMCMC_ENANRATIO = 7   /* f1 - f0 is NaN, R: "missing value where TRUE/FALSE needed" (D10) */
+};
+
+/* ---- log-posterior families (the device-side replacement of `fun`) ------- */
+enum {
+  FMCMC_FAMILY_GAUSSIAN_LM = 1, /* sum dnorm(y - (b0 + X b), sd = theta[k-1], log=TRUE)   */
+  FMCMC_FAMILY_LOGISTIC    = 2, /* Bernoulli-logit log-lik  - sum(beta^2)/(2 prior_sd^2)  */
+  FMCMC_FAMILY_HIER_NORMAL = 3  /* y_i~N(th_g(i),s), th_g~N(gamma,tau), gamma~U(lo,hi)    */
+};
+
+/* model flags */
+#define FMCMC_MODEL_INTERCEPT 1u /* GAUSSIAN_LM: theta[0] is an intercept that has no column in X */
+#define FMCMC_MODEL_GUARD     2u /* GAUSSIAN_LM: non-finite sum -> -Inf (README.md:135-136)        */
+#define FMCMC_MODEL_SCALES    4u /* HIER_NORMAL: theta also carries (sigma, tau) after gamma       */
+
+typedef struct fmcmc_model_desc {
+  int32_t  family;
+  uint32_t flags;
+  int64_t  n;         /* observations                                   */
+  int32_t  p_x;       /* columns of X (0 for HIER_NORMAL)               */
+  int32_t  n_groups;  /* HIER_NORMAL only                               */
+  const double*  X;   /* n x p_x, column-major (R layout); host pointer */
+  const double*  y;   /* n                                              */
+  const int32_t* group; /* n, 0-based group of each observation (HIER_NORMAL) */
+  double   hyper[4];  /* LOGISTIC: [0]=prior sd (2 in the vignette);
+                         HIER_NORMAL: [0]=gamma lower, [1]=gamma upper       */
+} fmcmc_model_desc;
+
+/* Number of parameters k the family expects (theta length).  <0 on bad desc. */
+int32_t fmcmc_model_nparams(const fmcmc_model_desc* desc);
+
+/* ---- transition kernels -------------------------------------------------- */
+enum {
+  FMCMC_KERNEL_NORMAL            = 1, /* R/kernel_normal.R:26-82   */
+  FMCMC_KERNEL_NORMAL_REFLECTIVE = 2, /* R/kernel_normal.R:96-177  */
+  FMCMC_KERNEL_UNIF              = 3, /* R/kernel_unif.R:15-66     */
+  FMCMC_KERNEL_UNIF_REFLECTIVE   = 4, /* R/kernel_unif.R:74-147    */
+  FMCMC_KERNEL_ADAPT             = 5, /* R/kernel_adapt.R:54-208   */
+  FMCMC_KERNEL_RAM               = 6, /* R/kernel_ram.R:65-181     */
+  FMCMC_KERNEL_NMIRROR           = 7, /* R/kernel_mirror.R:54-173  */
+  FMCMC_KERNEL_UMIRROR           = 8  /* R/kernel_mirror.R:177-301 */
+};
+
+/* update schemes of plan_update_sequence (R/kernel.R:66-133) */
+enum {
+  FMCMC_SCHEME_JOINT    = 0,
+  FMCMC_SCHEME_ORDERED  = 1,
+  FMCMC_SCHEME_RANDOM   = 2,
+  FMCMC_SCHEME_EXPLICIT = 3
+};
+
+/* how kernel_adapt turns Sigma into a draw */
+enum {
+  FMCMC_MVN_CHOLESKY = 0, /* mu + L z           (device production path)                 */
+  FMCMC_MVN_EIGEN    = 1  /* mu + V sqrt(max(ev,0)) z, MASS::mvrnorm's published form;
+                             oracle only (eigenvector signs are LAPACK-specific)          */
+};
+
+typedef struct fmcmc_kernel_spec {
+  int32_t type;
+  int32_t k;            /* length of theta                                        */
+  int32_t scheme;       /* NORMAL/UNIF/MIRROR families only                       */
+  int32_t order_len;    /* EXPLICIT scheme: length of `order` (== #free params)   */
+  const int32_t* order; /* EXPLICIT scheme: 1-based parameter indices             */
+  const int32_t* seq;   /* RANDOM scheme, fed mode: [nchains][seq_len] 1-based active
+                           coordinate of each row (R/kernel.R:109-112); NULL => Philox */
+  int64_t seq_len;      /* rows planned (the first run's nsteps, quirk D7)        */
+  /* All vectors below have length k and are already recycled
+     (check_dimensions, R/kernel.R:1-15) and NA-processed (process_bounds 25-41). */
+  const double*  mu;    /* NORMAL*: proposal mean; ADAPT: mu (indexed by free params
+                           inside); MIRROR: initial centre (used when state is fresh)    */
+  const double*  scale; /* NORMAL*: sd; MIRROR: initial scale                      */
+  const double*  min_;  /* UNIF*                                                   */
+  const double*  max_;  /* UNIF*                                                   */
+  const double*  lb;    /* reflective / adaptive / mirror kernels; +-DBL_MAX = none */
+  const double*  ub;
+  const uint8_t* fixed; /* 1 = parameter never moves                               */
+  /* adaptive hyper-parameters */
+  int64_t warmup;       /* ADAPT 500, RAM 0, MIRROR 500                            */
+  int64_t freq;         /* ADAPT/RAM 1                                             */
+  int64_t bw;           /* ADAPT windowed covariance (0 = recursive)               */
+  double  until;        /* ADAPT/RAM: stop adapting at this abs_iter (Inf = never) */
+  double  eps;          /* ADAPT/RAM 1e-4                                          */
+  double  Sd;           /* ADAPT: 5.76/k_free when <= 0 (only used when bw > 0)    */
+  double  arate;        /* RAM .234, MIRROR .4                                     */
+  const int64_t* nadapt;/* MIRROR: checkpoint schedule (R/kernel_mirror.R:165)     */
+  int32_t nadapt_len;
+  int32_t mvn_method;   /* ADAPT: FMCMC_MVN_*                                      */
+  const double* constr; /* RAM: k x k column-major mask or NULL (R/kernel_ram.R:149-150) */
+} fmcmc_kernel_spec;
+
+/*
+ * Per-chain mutable kernel state, round-tripped on every fmcmc_run so that a
+ * kernel object can be reused across bulks / calls exactly like the R env
+ * (SURVEY §5 "resume by value").  Flat layout, per chain c:
+ *   istate[c*FMCMC_ISTATE_LEN + 0] abs_iter
+ *   istate[c*FMCMC_ISTATE_LEN + 1] flags  (bit0: ADAPT Mean_t_prev is set;
+ *                                          bit1: state initialised (k known);
+ *                                          bits 2-3: MIRROR obs_arate 0=NULL 1=scalar 2=vector)
+ *   istate[c*FMCMC_ISTATE_LEN + 2] nerrors (RAM)
+ *   istate[c*FMCMC_ISTATE_LEN + 3] n_changed: rows of the current run whose state differs
+ *                                  from the previous row (scratch, reset every run)
+ *   dstate[c*dlen ...]  ADAPT : Sigma[kf*kf] (col-major), Mean_t_prev[kf]
+ *                       RAM   : Sigma[kf*kf] (used as the factor S)
+ *                       MIRROR: mu[k], scale[k], obs_arate[k]
+ *                       others: empty (dlen = 0)
+ * where kf = number of non-fixed parameters, dlen = fmcmc_kernel_state_len().
+ * A fresh state is all zeros (flags bit1 clear): the run initialises it the way
+ * the R closures do on their first proposal call.
+ */
+#define FMCMC_ISTATE_LEN 4
+#define FMCMC_STATE_HAS_MEAN   1
+#define FMCMC_STATE_INIT       2
+#define FMCMC_STATE_OBS_SHIFT  2
+
+int64_t fmcmc_kernel_state_len(int32_t type, int32_t k, int32_t k_free);
+
+typedef struct fmcmc_kernel_state {
+  int64_t* istate;  /* [nchains][FMCMC_ISTATE_LEN] */
+  double*  dstate;  /* [nchains][dlen]             */
+} fmcmc_kernel_state;
+
+/* ---- random streams ------------------------------------------------------ */
+enum {
+  FMCMC_STREAM_PHILOX = 0, /* production: Philox4x32-10 keyed by (seed, global chain id),
+                              counter (run_index, row, slot): independent of #GPUs       */
+  FMCMC_STREAM_FED    = 1  /* verification: host uploads R's own draws   */
+};
+
+typedef struct fmcmc_stream_spec {
+  int32_t  mode;
+  int32_t  kdraw;      /* FED: slots per row in `z` (k_free for joint, 1 otherwise)     */
+  uint64_t seed;       /* PHILOX                                                        */
+  uint64_t run_index;  /* PHILOX: bulk counter, so consecutive bulks use fresh counters */
+  const double* logu;  /* FED: [nchains][nsteps]   log(runif(nsteps)); [.,0] is unused  */
+  const double* z;     /* FED: [nchains][nsteps][kdraw]; row 0 unused.  Standard normals
+                          (NORMAL*, ADAPT, NMIRROR), U(0,1) (UNIF*, UMIRROR) or U=qfun(k)
+                          (RAM).  The device applies mu + scale*z / a + (b-a)*u unfused. */
+} fmcmc_stream_spec;
+
+/* ---- one call of MCMC_without_conv_checker ------------------------------- */
+#define FMCMC_RUN_NO_DRAWS   1u /* do not copy `draws` back (pointer may be NULL)       */
+#define FMCMC_RUN_COLMAJOR   2u /* outputs as R matrices: [chain][param][row]           */
+#define FMCMC_RUN_APPEND     4u /* append the kept rows to the handle's sample store
+                                   (append_chains, R/mcmc.R:947) for fmcmc_gelman       */
+#define FMCMC_RUN_NO_OUTPUT  8u /* keep results on the device only (store / last state) */
+
+typedef struct fmcmc_run_spec {
+  int64_t nsteps;        /* rows, including the initial state (R semantics)  */
+  int64_t burnin;
+  int64_t thin;
+  int32_t nchains;       /* chains handled by THIS call / GPU                */
+  uint32_t flags;
+  int64_t chain_offset;  /* global id of local chain 0 (Philox keying)       */
+  const double* initial; /* [nchains][k] row-major; NULL => continue from the
+                            last state kept on the device (next bulk)        */
+} fmcmc_run_spec;
+
+typedef struct fmcmc_run_report {
+  int64_t rows_kept;     /* T' = rows after burnin/thin                      */
+  int64_t first_iter;    /* iteration number of the first kept row (mcpar)   */
+  int64_t last_iter;
+  int64_t nan_chain;     /* FMCMC_ENAN: local chain / row (1-based, R's i)   */
+  int64_t nan_step;
+  int64_t n_accept;      /* accepted proposals over all chains               */
+  int64_t n_launches;    /* CUDA kernels launched by this call               */
+  double  device_ms;     /* CUDA-event time of the stepping kernels          */
+  int32_t path;          /* 1 = chain-resident fused kernel, 2 = observation-tiled */
+  int32_t reserved;
+} fmcmc_run_report;
+
+typedef struct fmcmc_model fmcmc_model;   /* opaque: device-resident X, y, buffers */
+
+int fmcmc_version(void);
+int fmcmc_device_count(void);
+
+/* Upload X/y once (the reference re-ships them to PSOCK workers every bulk,
+ * R/mcmc.R:550-577).  `device` is the CUDA ordinal (LOCAL_RANK). */
+int fmcmc_model_create(const fmcmc_model_desc* desc, int device,
+                       fmcmc_model** out, char* err, size_t errlen);
+/* Same, but X/y/group are DEVICE pointers already resident in HBM (borrowed,
+ * must outlive the model).  Used by the bench's HBM-resident leg. */
+int fmcmc_model_create_device(const fmcmc_model_desc* desc_with_device_ptrs, int device,
+                              fmcmc_model** out, char* err, size_t errlen);
+void fmcmc_model_free(fmcmc_model* m);
+
+/*
+ * Run `nsteps` rows for `nchains` chains.  Outputs (host, caller-allocated, may
+ * be NULL with FMCMC_RUN_NO_OUTPUT):
+ *   ans     [nchains][rows_kept][k]  accepted states   (R/mcmc.R:778)
+ *   draws   [nchains][rows_kept][k]  proposals         (R/mcmc.R:752)
+ *   logpost [nchains][rows_kept]     f(proposal), quirk D1 (R/mcmc.R:754)
+ * rows_kept = fmcmc_rows_kept(nsteps, burnin, thin).
+ */
+int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec* kernel,
+              fmcmc_kernel_state* state, const fmcmc_stream_spec* stream,
+              double* ans, double* draws, double* logpost,
+              fmcmc_run_report* report, char* err, size_t errlen);
+
+int64_t fmcmc_rows_kept(int64_t nsteps, int64_t burnin, int64_t thin);
+
+/* Force a stepping path (0 = auto, 1 = chain-resident, 2 = observation-tiled). */
+int fmcmc_set_path(fmcmc_model* m, int path);
+
+/* Evaluate the family's log-posterior for `nchains` parameter vectors
+ * ([nchains][k] row-major) on the device: the `f(theta)` of R/mcmc.R:742. */
+int fmcmc_logpost(fmcmc_model* m, int32_t nchains, const double* theta, double* out,
+                  char* err, size_t errlen);
+
+/* ---- sample store + Gelman-Rubin (R/convergence.R:191-246) -------------- */
+/* Reserve room for `capacity_rows` appended rows of nchains x k. */
+int fmcmc_store_reset(fmcmc_model* m, int32_t nchains, int32_t k, int64_t capacity_rows,
+                      char* err, size_t errlen);
+int64_t fmcmc_store_rows(const fmcmc_model* m);
+
+/*
+ * Per-GPU partial statistics of rows [row_begin,row_end) of the store, free
+ * parameters only (free_mask[k], 1 = keep):
+ *   xbar   [nchains][kf]   per-chain means
+ *   s2     [nchains][kf]   per-chain variances (divisor N-1)
+ *   wsum   [kf*kf]         sum over local chains of the chain covariance matrices
+ * Outputs are DEVICE pointers when dev_out != 0 (so torch.distributed can
+ * all_gather / all_reduce them over NCCL), host pointers otherwise.
+ */
+int fmcmc_gelman_partials(fmcmc_model* m, int64_t row_begin, int64_t row_end,
+                          const uint8_t* free_mask, double* xbar, double* s2, double* wsum,
+                          int dev_out, char* err, size_t errlen);
+
+/*
+ * Finish coda::gelman.diag from (gathered) statistics of `nchains_total`
+ * chains and `niter` rows: psrf point estimates [kf] and mpsrf (NaN if kf==1).
+ * Returns FMCMC_ENOTPD when chol(W) fails (the R wrapper turns that into a
+ * warning + FALSE, R/convergence.R:207-217).  Inputs are DEVICE pointers when
+ * dev_in != 0.
+ */
+int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, int32_t kf,
+                        const double* xbar, const double* s2, const double* wsum, int dev_in,
+                        double* psrf, double* mpsrf, char* err, size_t errlen);
+
+/* Single-GPU convenience: autoburnin window (second half) + partials + finish
+ * on everything in the store; `start_iter`/`end_iter`/`thin` describe mcpar. */
+int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double* mpsrf,
+                 int64_t* niter_used, char* err, size_t errlen);
+
+/* ---- exported helpers of the reference, device implementations ---------- */
+/* R/recursive.R:124-139 / 63-120 applied to `rows` consecutive rows of X
+ * ([rows][k] row-major), starting from (mean_prev, cov_prev, t).  Outputs the
+ * last mean [k] and covariance [k*k]. */
+int fmcmc_cov_recursive(int device, int32_t k, int64_t rows, const double* X,
+                        const double* mean_prev, const double* cov_prev, double t,
+                        double eps, double Sd, const double* Ik,
+                        double* mean_out, double* cov_out, char* err, size_t errlen);
+/* R/kernel.R:450-493 on `count` vectors of length k ([count][k]). */
+int fmcmc_reflect(int device, int32_t k, int64_t count, double* x, const double* lb,
+                  const double* ub, const uint8_t* which, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMCMC_B200_H */
