@@ -1,0 +1,233 @@
+"""MCMC(): the reference's entry point (R/mcmc.R:325-479) over the CUDA C ABI.
+
+Signature, argument meaning, return types (coda-like mcmc / mcmc.list), error messages and the
+bulk / convergence loop (R/mcmc.R:841-1019) follow the reference; the per-step work runs in
+libfmcmcb200.so.  `fun` must be a DeviceFamily: closures are a TypeError, never a CPU fallback."""
+from __future__ import annotations
+
+import sys
+import warnings
+
+import numpy as np
+
+from . import _abi as A
+from . import mcmc_info as info
+from .coda import Mcmc, McmcList, append_chains
+from .convergence import (GelmanChecker, convergence_data_flush, convergence_msg_get, convergence_msg_set)
+from .device import DeviceModel
+from .dist import current_sharding
+from .families import DeviceFamily
+from .kernels import FmcmcKernel, kernel_normal
+
+
+def _message(*parts):
+    print("".join(str(p) for p in parts), file=sys.stderr)
+
+
+def check_initial(initial, nchains):
+    """R/checks.R:22-58"""
+    if isinstance(initial, McmcList):
+        return np.stack([m.data[-1] for m in initial]), initial.varnames
+    names = None
+    if isinstance(initial, Mcmc):
+        names = initial.varnames
+        initial = initial.data[-1]
+    if isinstance(initial, dict):
+        names, initial = list(initial.keys()), list(initial.values())
+    a = np.asarray(initial, dtype=np.float64) if not isinstance(initial, str) else None
+    if a is None or a.dtype == object:
+        raise TypeError("When `initial` is not a numeric vector, it should be a matrix. Right now it is an "
+                        f"object of class `{type(initial).__name__}`.")
+    if a.ndim <= 1:
+        a = a.reshape(-1)
+        if nchains > 1:
+            warnings.warn("While using multiple chains, a single initial point has been passed via `initial`: c("
+                          + ", ".join(f"{v:g}" for v in a) + "). The values will be recycled. Ideally you would "
+                          "want to start each chain from different locations.")
+        if a.size == 0:
+            raise ValueError("The `initial` vector is of length zero.")
+        a = np.tile(a, (nchains, 1))
+    elif a.ndim == 2:
+        if a.shape[0] != nchains:
+            raise ValueError(f"The number of rows of `initial` ({a.shape[0]}) must coincide with the number of "
+                             f"chains ({nchains}).")
+    else:
+        raise TypeError("When `initial` is not a numeric vector, it should be a matrix.")
+    if names is None:
+        names = [f"par{i + 1}" for i in range(a.shape[1])]
+    return np.ascontiguousarray(a), names
+
+
+class FedStream:
+    """Verification mode: the host's own draws (R's runif / rnorm in the serial path's order,
+    SURVEY App. B).  logu: [nchains][nsteps], z: [nchains][nsteps][kdraw]; one per bulk."""
+
+    def __init__(self, logu, z):
+        self.logu, self.z = np.asarray(logu, dtype=np.float64), np.asarray(z, dtype=np.float64)
+
+
+def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_index, fed, names,
+              sharding, append, want_draws=True):
+    """MCMC_without_conv_checker, R/mcmc.R:485-838 (chains fan out on the device, not in a loop)."""
+    if nchains < 1:
+        raise ValueError("`nchains` must be an integer greater than 1.")
+    if burnin >= nsteps:
+        raise ValueError(f"-burnin- ({burnin}) cannot be >= than -nsteps- ({nsteps}).")
+    if thin >= nsteps:
+        raise ValueError(f"-thin- ({thin}) cannot be > than -nsteps- ({nsteps}).")
+    if thin < 1:
+        raise ValueError("-thin- should be >= 1.")
+    total_chains = sharding.total if sharding else nchains
+    if total_chains > 1 and not kernel.is_list:                 # R/mcmc.R:526-527 rep_kernel
+        kernel._replicate(nchains)
+    elif total_chains == 1 and kernel.is_list:
+        raise ValueError("The passed kernel is for MCMC with more than one chain. Right now, -kernel- is of "
+                         f"length {len(kernel)}")
+    k = model.k
+    if initial is not None and initial.shape[1] != k:
+        raise ValueError(f"Incorrect length of -initial-: the family has {k} parameters, got {initial.shape[1]}.")
+    spec = kernel.to_spec(k)
+    istate, dstate = kernel.state_arrays(nchains, k)
+    if fed is not None:
+        stream = A.marshal_stream(A.STREAM_FED, logu=fed.logu, z=fed.z)
+    else:
+        stream = A.marshal_stream(A.STREAM_PHILOX, seed=seed, run_index=run_index)
+    out = model.run(spec, nsteps, nchains, initial=initial, burnin=burnin, thin=thin, stream=stream,
+                    istate=istate, dstate=dstate if dstate.size and A.state_len(spec["type"], k, kernel._kf) else None,
+                    flags=A.RUN_APPEND if append else 0, chain_offset=sharding.offset if sharding else 0,
+                    want_draws=want_draws)
+    kernel.absorb_state(k)
+    rep = out["report"]
+    first, last = rep.first_iter, rep.last_iter
+    chains = [Mcmc(out["ans"][c], start=first, end=last, thin=thin, varnames=names) for c in range(nchains)]
+    info.MCMC_OUTPUT.report = rep
+    return chains, out
+
+
+def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel=None, multicore=False,
+         conv_checker=None, cl=None, progress=False, chain_id=1, device=None, fed=None, path=0, **dots):
+    """Drop-in for fmcmc::MCMC (R/mcmc.R:325-479).
+
+    initial   vector (recycled), nchains x k matrix, or a previous Mcmc / McmcList (restart)
+    fun       a DeviceFamily (ll_gaussian_lm / ll_logistic / ll_hier_normal)
+    nsteps    rows per chain, including the initial state
+    seed      Philox seed (the reference's set.seed(seed)); results do not depend on #GPUs
+    kernel    kernel_normal() by default; state is written back into the object
+    multicore / cl   accepted for signature compatibility; chains always run concurrently on the
+              GPU(s).  Under torchrun (torch.distributed initialised) chains are sharded over ranks
+              and each rank returns its own chains.
+    fed       FedStream or a list of FedStream (one per bulk): verification mode
+    """
+    if dots:
+        raise TypeError("The following arguments passed via -...- are not present in -fun-:\n - "
+                        + ",\n - ".join(dots) + ".\nDevice families carry their data (X, y) themselves.")
+    if not isinstance(fun, DeviceFamily):
+        raise TypeError("`fun` must be one of the built-in device log-posterior families "
+                        "(ll_gaussian_lm, ll_logistic, ll_hier_normal): an arbitrary closure cannot run on "
+                        "the GPU and fmcmc_b200 has no CPU fallback.")
+    if isinstance(initial, McmcList) and nchains != len(initial):
+        raise ValueError("The parameter `nchains` must equal the number of chains passed by `initial`.")
+    if multicore and nchains == 1:
+        raise ValueError("When `multicore = TRUE`, `nchains` should be greater than 1.")
+    if kernel is None:
+        kernel = kernel_normal()
+    if not isinstance(kernel, FmcmcKernel):
+        raise TypeError("`kernel` must be an fmcmc_kernel built by one of the kernel_*() constructors.")
+    nsteps, burnin, thin, nchains = int(nsteps), int(burnin), int(thin), int(nchains)
+
+    sharding = current_sharding(nchains)
+    nlocal = sharding.local if sharding else nchains
+    init_all, names = check_initial(initial, nchains)
+    init_local = init_all[sharding.offset:sharding.offset + nlocal] if sharding else init_all
+    if device is None:
+        device = sharding.device.index if (sharding and sharding.on_cuda) else 0
+    if seed is None:
+        seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 1 << 32], dtype=np.uint64))
+
+    info.MCMC_OUTPUT.clear(nlocal)
+    info.MCMC_init(initial=init_all, nsteps=nsteps, seed=seed, nchains=nchains, burnin=burnin, thin=thin,
+                   kernel=kernel, conv_checker=conv_checker)
+    info.MCMC_OUTPUT.kernel = kernel
+    model = DeviceModel(fun, device=device)
+    if path:
+        model.set_path(path)
+    feds = fed if isinstance(fed, (list, tuple)) else ([fed] if fed is not None else None)
+    try:
+        if conv_checker is None:
+            chains, out = _run_bulk(model, init_local, nsteps, nlocal, burnin, thin, kernel, seed, 0,
+                                    feds[0] if feds else None, names, sharding, append=False)
+            for c in range(nlocal):
+                info.MCMC_OUTPUT.logpost[c] = out["logpost"][c]
+                info.MCMC_OUTPUT.draws[c] = out["draws"][c]
+            ans = chains[0] if nchains == 1 else McmcList(chains)
+        else:
+            ans = _with_conv_checker(model, init_local, nsteps, nlocal, nchains, burnin, thin, kernel, seed, feds,
+                                     names, sharding, conv_checker)
+    finally:
+        model.close()
+    info.MCMC_finalize()
+    return ans
+
+
+def _with_conv_checker(model, initial, nsteps, nlocal, nchains, burnin, thin, kernel, seed, feds, names,
+                       sharding, conv_checker):
+    """MCMC_with_conv_checker, R/mcmc.R:841-1019."""
+    freq = getattr(conv_checker, "freq", None)
+    if freq is None:
+        freq = nsteps // 2
+        warnings.warn(f"The -conv_checker- function has no freq attribute. Default value set to be {freq}")
+    if freq * 2 > nsteps:
+        freq = 0
+    if freq > 0:
+        bulks = [freq] * ((nsteps - burnin) // freq)
+        if (nsteps - burnin) % freq:
+            bulks.append((nsteps - burnin) - sum(bulks))
+    else:
+        bulks = [nsteps]
+    bulks[0] += burnin
+    convergence_data_flush()
+    device_checker = isinstance(conv_checker, GelmanChecker)
+    total_keep = sum(A.rows_kept(b, burnin if i == 0 else 0, thin) for i, b in enumerate(bulks))
+    if device_checker:
+        model.store_reset(nlocal, total_keep)
+    fixed = np.broadcast_to(np.asarray(getattr(kernel, "fixed", False), dtype=bool), (model.k,))
+    free_mask = (~fixed).astype(np.uint8)
+    ans, converged, i = None, False, 0
+    lp_acc = [[] for _ in range(nlocal)]
+    dr_acc = [[] for _ in range(nlocal)]
+    for i, nst in enumerate(bulks, start=1):
+        if i > 1:
+            burnin = 0
+            initial = None                                       # continue from the device state (:909-911)
+        chains, out = _run_bulk(model, initial, nst, nlocal, burnin, thin, kernel, seed, i - 1,
+                                feds[i - 1] if feds else None, names, sharding, append=device_checker)
+        tmp = chains[0] if nchains == 1 else McmcList(chains)
+        ans = append_chains(ans, tmp) if ans is not None else tmp  # :947
+        for c in range(nlocal):
+            lp_acc[c].append(out["logpost"][c])
+            dr_acc[c].append(out["draws"][c])
+        convergence_msg_set()
+        if device_checker:
+            conv_checker._device_ctx = (model, nlocal, free_mask, sharding)
+            x = ans if isinstance(ans, McmcList) else McmcList([ans])
+            converged = conv_checker(x.select(np.where(free_mask)[0]) if nchains > 1 else ans)
+            conv_checker._device_ctx = None
+        else:                                                    # arbitrary checker: host path on the samples
+            free = np.where(free_mask)[0]
+            converged = conv_checker(ans.select(free) if isinstance(ans, McmcList) else ans[:, free])
+        msg = convergence_msg_get()
+        steps = sum(bulks[:i])
+        nsamp = ans.niter()
+        if converged:
+            _message("Convergence has been reached with ", steps, " steps. ", "" if msg is None else msg + " ",
+                     "(", nsamp, " final count of samples).")
+            break
+        _message("No convergence yet (steps count: ", steps, "). ", "" if msg is None else msg + " ",
+                 "Trying with the next bulk.")
+    if i == len(bulks) and not converged:
+        _message("No convergence reached after ", sum(bulks[:i]), " steps (", ans.niter(),
+                 " final count of samples).")
+    for c in range(nlocal):
+        info.MCMC_OUTPUT.logpost[c] = np.concatenate(lp_acc[c])
+        info.MCMC_OUTPUT.draws[c] = np.concatenate(dr_acc[c])
+    return ans

@@ -1,0 +1,130 @@
+"""Minimal stand-ins for coda's `mcmc` / `mcmc.list` containers (R/mcmc.R:829-836, 641, 671):
+a numeric matrix with iteration row names, parameter column names and mcpar = (start, end, thin)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Mcmc:
+    def __init__(self, data, start=1, end=None, thin=1, varnames=None):
+        self.data = np.asarray(data, dtype=np.float64)
+        if self.data.ndim == 1:
+            self.data = self.data.reshape(-1, 1)
+        n = self.data.shape[0]
+        self.start = int(start)
+        self.thin = int(thin)
+        self.end = int(end) if end is not None else self.start + (n - 1) * self.thin
+        self.varnames = list(varnames) if varnames is not None else [f"par{i + 1}" for i in range(self.data.shape[1])]
+
+    # coda accessors
+    @property
+    def mcpar(self):
+        return (self.start, self.end, self.thin)
+
+    def niter(self):
+        return self.data.shape[0]
+
+    def nvar(self):
+        return self.data.shape[1]
+
+    def nchain(self):
+        return 1
+
+    def iterations(self):
+        return self.start + self.thin * np.arange(self.niter())
+
+    def __getitem__(self, idx):
+        sub = self.data[idx]
+        if isinstance(idx, tuple) and len(idx) == 2 and not np.isscalar(idx[1]) and sub.ndim == 2 \
+                and sub.shape[0] == self.niter():
+            cols = np.arange(self.nvar())[idx[1]]
+            return Mcmc(sub, self.start, self.end, self.thin, [self.varnames[c] for c in np.atleast_1d(cols)])
+        return sub
+
+    def __array__(self, dtype=None, copy=None):
+        return self.data if dtype is None else self.data.astype(dtype)
+
+    def mean(self, axis=0):
+        return self.data.mean(axis=axis)
+
+    def __repr__(self):
+        return f"Mcmc(niter={self.niter()}, nvar={self.nvar()}, mcpar={self.mcpar})"
+
+
+class McmcList(list):
+    def nchain(self):
+        return len(self)
+
+    def niter(self):
+        return self[0].niter()
+
+    def nvar(self):
+        return self[0].nvar()
+
+    @property
+    def mcpar(self):
+        return self[0].mcpar
+
+    @property
+    def varnames(self):
+        return self[0].varnames
+
+    def as_array(self):
+        """[nchains][niter][nvar]"""
+        return np.stack([m.data for m in self])
+
+    def select(self, cols):
+        return McmcList([m[:, cols] for m in self])
+
+    def __repr__(self):
+        return f"McmcList(nchain={len(self)}, niter={self.niter()}, nvar={self.nvar()}, mcpar={self.mcpar})"
+
+
+def append_chains(*objs):
+    """R/append_chains.R:44-145: rbind consecutive runs, renumber iterations, rebuild mcpar."""
+    objs = [o for o in objs if o is not None and len(o) > 0]
+    if not objs:
+        raise ValueError("No method available to append these chains.")
+    if len(objs) == 1:
+        return objs[0]
+    if isinstance(objs[0], McmcList):
+        nch = {o.nchain() for o in objs}
+        if len(nch) != 1:
+            raise ValueError("All mcmc.list objects must have the same number of chains. The passed objects have "
+                             + ", ".join(str(o.nchain()) for o in objs) + " respectively.")
+        return McmcList([append_chains(*[o[i] for o in objs]) for i in range(objs[0].nchain())])
+    thin = [o.thin for o in objs]
+    if len(set(thin)) != 1:
+        raise ValueError("All `mcmc` objects have to have the same `thin` parameter.Observed: "
+                         + ", ".join(map(str, thin)) + " respectively.")
+    nvar = [o.nvar() for o in objs]
+    if len(set(nvar)) != 1:
+        raise ValueError("All `mcmc` objects have to have the same number of parameters.Observed: "
+                         + ", ".join(map(str, nvar)) + " respectively.")
+    start = [o.start for o in objs]
+    end = [o.end for o in objs]
+    for i in range(1, len(objs)):                     # R/append_chains.R:128
+        end[i] = end[i] + thin[i] - start[i]
+    data = np.concatenate([o.data for o in objs], axis=0)
+    return Mcmc(data, start=start[0], end=sum(end), thin=thin[0], varnames=objs[0].varnames)
+
+
+def __len_mcmc(self):
+    return self.niter()
+
+
+Mcmc.__len__ = __len_mcmc
+
+
+def window_first_row(start: int, end: int, thin: int, niter: int, new_start: float) -> int:
+    """0-based first row kept by coda's window.mcmc(x, start = new_start) (start snaps UP to
+    the next kept iteration; third-party coda, restated from its published source)."""
+    if new_start < start:
+        new_start = start
+    xtime = start + thin * np.arange(niter)
+    ts_eps = 1e-5
+    if np.all(np.abs(xtime - new_start) > abs(new_start) * ts_eps):
+        cand = xtime[(xtime > new_start) & ((new_start + thin) > xtime)]
+        new_start = cand[0]
+    first = int(np.trunc((new_start - start) / thin + 1.5))   # 1-based
+    return first - 1

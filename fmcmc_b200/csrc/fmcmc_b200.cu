@@ -1,0 +1,960 @@
+// fmcmc_b200.cu — C ABI (include/fmcmc_b200.h) + host orchestration.
+// Single translation unit; device code lives in the .cuh files next to it.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fmcmc_b200.h"
+#include "common.cuh"
+#include "families.cuh"
+#include "gelman.cuh"
+#include "propose.cuh"
+#include "resident.cuh"
+#include "tiled.cuh"
+
+// --------------------------------------------------------------------------------
+// small host utilities
+// --------------------------------------------------------------------------------
+static void set_err(char* err, size_t errlen, const char* fmt, ...) {
+  if (!err || !errlen) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, errlen, fmt, ap);
+  va_end(ap);
+}
+
+#define CU_CHECK(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      set_err(err, errlen, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,   \
+              __LINE__, #call);                                                               \
+      return FMCMC_ECUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static cudaError_t ensure(DevBuf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (bytes <= b.cap) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e == cudaSuccess) b.cap = bytes;
+  return e;
+}
+static void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+struct fmcmc_model {
+  int device = 0;
+  ModelParams mp{};
+  bool borrowed = false;
+  DevBuf X, y, group;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  int smem_optin = 0;
+  int forced_path = 0;
+  // run buffers (grow-only)
+  DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
+      errbuf, nacc, spec, fed_logu, fed_z, initial, partial, out_ans, out_draws, out_lp, tmp;
+  int state_nchains = 0, state_k = 0;  // shape of cur_theta (valid after a run)
+  // sample store (append_chains): [rows][C][k]
+  DevBuf store;
+  int store_C = 0, store_k = 0;
+  long long store_cap = 0, store_rows = 0;
+  // gelman scratch
+  DevBuf g_xbar, g_s2, g_wsum, g_wpart, g_mask;
+};
+
+static int count_free(const fmcmc_kernel_spec* ks, std::vector<int>& free_idx) {
+  free_idx.clear();
+  for (int j = 0; j < ks->k; j++)
+    if (!(ks->fixed && ks->fixed[j])) free_idx.push_back(j);
+  return (int)free_idx.size();
+}
+
+// --------------------------------------------------------------------------------
+// plain accessors
+// --------------------------------------------------------------------------------
+extern "C" int fmcmc_version(void) { return FMCMC_ABI_VERSION; }
+
+extern "C" int fmcmc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int32_t fmcmc_model_nparams(const fmcmc_model_desc* d) {
+  if (!d) return -1;
+  switch (d->family) {
+    case FMCMC_FAMILY_GAUSSIAN_LM: return d->p_x + ((d->flags & FMCMC_MODEL_INTERCEPT) ? 1 : 0) + 1;
+    case FMCMC_FAMILY_LOGISTIC: return d->p_x;
+    case FMCMC_FAMILY_HIER_NORMAL: return d->n_groups + 1 + ((d->flags & FMCMC_MODEL_SCALES) ? 2 : 0);
+  }
+  return -1;
+}
+
+extern "C" int64_t fmcmc_kernel_state_len(int32_t type, int32_t k, int32_t kf) {
+  switch (type) {
+    case FMCMC_KERNEL_ADAPT: return (int64_t)kf * kf + kf;
+    case FMCMC_KERNEL_RAM: return (int64_t)kf * kf;
+    case FMCMC_KERNEL_NMIRROR:
+    case FMCMC_KERNEL_UMIRROR: return 3 * (int64_t)k;
+  }
+  return 0;
+}
+
+extern "C" int64_t fmcmc_rows_kept(int64_t nsteps, int64_t burnin, int64_t thin) {
+  int64_t m = nsteps - burnin;
+  if (m < 0) return 0;
+  if (thin < 1) thin = 1;
+  return m / thin;
+}
+
+// --------------------------------------------------------------------------------
+// model
+// --------------------------------------------------------------------------------
+static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_ptrs, fmcmc_model** out, char* err,
+                             size_t errlen) {
+  if (!d || !out) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  const int k = fmcmc_model_nparams(d);
+  if (k < 1 || d->n < 1) { set_err(err, errlen, "bad model description (family %d, n %lld)", d->family, (long long)d->n); return FMCMC_EINVAL; }
+  if (d->family != FMCMC_FAMILY_HIER_NORMAL && (d->p_x < 1 || !d->X)) { set_err(err, errlen, "X is required"); return FMCMC_EINVAL; }
+  if (!d->y) { set_err(err, errlen, "y is required"); return FMCMC_EINVAL; }
+  if (d->family == FMCMC_FAMILY_HIER_NORMAL && (!d->group || d->n_groups < 1)) { set_err(err, errlen, "group is required"); return FMCMC_EINVAL; }
+  if (d->family == FMCMC_FAMILY_LOGISTIC && !(d->hyper[0] > 0)) { set_err(err, errlen, "logistic prior sd must be > 0"); return FMCMC_EINVAL; }
+  if (d->family == FMCMC_FAMILY_HIER_NORMAL && !(d->hyper[1] > d->hyper[0])) { set_err(err, errlen, "hier_normal needs gamma bounds lo < hi"); return FMCMC_EINVAL; }
+  int ndev = 0;
+  CU_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_err(err, errlen, "CUDA device %d not available (%d visible)", device, ndev); return FMCMC_ECUDA; }
+  CU_CHECK(cudaSetDevice(device));
+  fmcmc_model* m = new fmcmc_model();
+  m->device = device;
+  const long long n = d->n, ld = (n + 1) & ~1LL;  // even leading dimension: 16-byte aligned columns for TMA
+  ModelParams& mp = m->mp;
+  mp.family = d->family; mp.flags = d->flags; mp.n = n; mp.ld = ld; mp.p_x = d->p_x; mp.n_groups = d->n_groups;
+  mp.k = k; mp.h0 = d->hyper[0]; mp.h1 = d->hyper[1];
+  const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+#define MC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); fmcmc_model_free(m); return FMCMC_ECUDA; } } while (0)
+  MC(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  MC(cudaEventCreate(&m->ev0));
+  MC(cudaEventCreate(&m->ev1));
+  MC(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+  MC(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (device_ptrs && ld == n) {  // borrow
+    m->borrowed = true;
+    mp.X = d->X; mp.y = d->y; mp.group = d->group;
+  } else {
+    if (d->p_x > 0) {
+      MC(ensure(m->X, (size_t)d->p_x * ld * 8));
+      MC(cudaMemset(m->X.p, 0, (size_t)d->p_x * ld * 8));
+      MC(cudaMemcpy2D(m->X.p, ld * 8, d->X, n * 8, n * 8, d->p_x, kind));
+      mp.X = m->X.as<double>();
+    }
+    MC(ensure(m->y, (size_t)ld * 8));
+    MC(cudaMemset(m->y.p, 0, (size_t)ld * 8));
+    MC(cudaMemcpy(m->y.p, d->y, n * 8, kind));
+    mp.y = m->y.as<double>();
+    if (d->group) {
+      MC(ensure(m->group, (size_t)ld * 4));
+      MC(cudaMemset(m->group.p, 0, (size_t)ld * 4));
+      MC(cudaMemcpy(m->group.p, d->group, n * 4, kind));
+      mp.group = m->group.as<int>();
+    }
+  }
+  if (d->family == FMCMC_FAMILY_HIER_NORMAL && !device_ptrs) {
+    for (long long i = 0; i < n; i++)
+      if (d->group[i] < 0 || d->group[i] >= d->n_groups) {
+        set_err(err, errlen, "group[%lld] = %d out of range", i, d->group[i]);
+        fmcmc_model_free(m);
+        return FMCMC_EINVAL;
+      }
+  }
+  MC(ensure(m->errbuf, 4 * sizeof(int)));
+  MC(ensure(m->nacc, sizeof(unsigned long long)));
+#undef MC
+  *out = m;
+  return FMCMC_OK;
+}
+
+extern "C" int fmcmc_model_create(const fmcmc_model_desc* d, int device, fmcmc_model** out, char* err, size_t errlen) {
+  return model_create_impl(d, device, false, out, err, errlen);
+}
+extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, fmcmc_model** out, char* err,
+                                         size_t errlen) {
+  return model_create_impl(d, device, true, out, err, errlen);
+}
+
+extern "C" void fmcmc_model_free(fmcmc_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+                    &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
+                    &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
+                    &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
+                    &m->g_mask};
+  for (DevBuf* b : bufs) release(*b);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int fmcmc_set_path(fmcmc_model* m, int path) {
+  if (!m || path < 0 || path > 2) return FMCMC_EINVAL;
+  m->forced_path = path;
+  return FMCMC_OK;
+}
+
+// --------------------------------------------------------------------------------
+// validation: same conditions / message substrings as the R code
+// --------------------------------------------------------------------------------
+static int validate_run(const fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec* ks, int kf,
+                        char* err, size_t errlen) {
+  const int k = m->mp.k;
+  if (run->nchains < 1) { set_err(err, errlen, "`nchains` must be an integer greater than 1."); return FMCMC_EINVAL; }
+  if (run->burnin >= run->nsteps) {  // R/mcmc.R:512-513
+    set_err(err, errlen, "-burnin- (%lld) cannot be >= than -nsteps- (%lld).", (long long)run->burnin, (long long)run->nsteps);
+    return FMCMC_EINVAL;
+  }
+  if (run->thin >= run->nsteps) {  // R/mcmc.R:516-517
+    set_err(err, errlen, "-thin- (%lld) cannot be > than -nsteps- (%lld).", (long long)run->thin, (long long)run->nsteps);
+    return FMCMC_EINVAL;
+  }
+  if (run->thin < 1) { set_err(err, errlen, "-thin- should be >= 1."); return FMCMC_EINVAL; }  // :519-520
+  if (run->burnin < 0) { set_err(err, errlen, "-burnin- cannot be negative."); return FMCMC_EINVAL; }
+  if (ks->k != k) { set_err(err, errlen, "Incorrect length of -initial-: the kernel has k = %d, the family needs %d parameters.", ks->k, k); return FMCMC_EINVAL; }
+  if (ks->type < FMCMC_KERNEL_NORMAL || ks->type > FMCMC_KERNEL_UMIRROR) { set_err(err, errlen, "unknown kernel type %d", ks->type); return FMCMC_EINVAL; }
+  if (kf == 0) {  // R/kernel.R:125-128
+    set_err(err, errlen, "The number of parameters to update, i.e. not fixed, cannot be zero. Check the value -fixed- in the kernel initialization.");
+    return FMCMC_EINVAL;
+  }
+  const bool bounded = !(ks->type == FMCMC_KERNEL_NORMAL || ks->type == FMCMC_KERNEL_UNIF);
+  if (bounded)
+    for (int j = 0; j < k; j++)
+      if (ks->ub[j] <= ks->lb[j]) { set_err(err, errlen, "-ub- cannot be <= than -lb-."); return FMCMC_EINVAL; }  // R/kernel_normal.R:134-135
+  if (ks->type == FMCMC_KERNEL_UNIF || ks->type == FMCMC_KERNEL_UNIF_REFLECTIVE)
+    for (int j = 0; j < k; j++)
+      if (ks->max_[j] <= ks->min_[j]) { set_err(err, errlen, "-max.- cannot be <= than -min.-."); return FMCMC_EINVAL; }
+  if (ks->type == FMCMC_KERNEL_UMIRROR && (kf != k || ks->scheme != FMCMC_SCHEME_JOINT)) {
+    set_err(err, errlen, "kernel_umirror with fixed parameters or a non-joint scheme is ill-defined in the reference (quirk D11)");
+    return FMCMC_EUNSUP;
+  }
+  if (ks->type == FMCMC_KERNEL_ADAPT) {
+    if (ks->bw > 0 && ks->bw > ks->warmup) { set_err(err, errlen, "The `warmup` parameter must be greater than `bw`."); return FMCMC_EINVAL; }
+    if (ks->bw > 0) { set_err(err, errlen, "kernel_adapt(bw > 0) (windowed covariance) is not built on the device yet"); return FMCMC_EUNSUP; }
+    if (ks->mvn_method != FMCMC_MVN_CHOLESKY) { set_err(err, errlen, "the device draws mvrnorm through the Cholesky factor (FMCMC_MVN_CHOLESKY) only"); return FMCMC_EUNSUP; }
+    if (ks->freq < 1) { set_err(err, errlen, "-freq- must be >= 1."); return FMCMC_EINVAL; }
+  }
+  if (ks->type == FMCMC_KERNEL_RAM && ks->freq < 1) { set_err(err, errlen, "-freq- must be >= 1."); return FMCMC_EINVAL; }
+  const bool has_scheme = ks->type == FMCMC_KERNEL_NORMAL || ks->type == FMCMC_KERNEL_NORMAL_REFLECTIVE ||
+                          ks->type == FMCMC_KERNEL_UNIF || ks->type == FMCMC_KERNEL_UNIF_REFLECTIVE ||
+                          ks->type == FMCMC_KERNEL_NMIRROR || ks->type == FMCMC_KERNEL_UMIRROR;
+  if (has_scheme) {
+    if (ks->scheme < FMCMC_SCHEME_JOINT || ks->scheme > FMCMC_SCHEME_EXPLICIT) {
+      set_err(err, errlen, "-scheme- update must be either an integer sequence, 'joint', 'ordered', or 'random'.");
+      return FMCMC_EINVAL;
+    }
+    if (ks->scheme == FMCMC_SCHEME_EXPLICIT) {  // R/kernel.R:69-91
+      if (ks->order_len != kf || !ks->order) {
+        set_err(err, errlen, "When setting the update scheme, it should have the same length as the number of variables that will not be fixed. Right now length(scheme) = %d while sum(!fixed) = %d.", ks->order_len, kf);
+        return FMCMC_EINVAL;
+      }
+      for (int j = 0; j < k; j++) {
+        if (ks->fixed && ks->fixed[j]) continue;
+        bool found = false;
+        for (int q = 0; q < ks->order_len; q++) found |= (ks->order[q] == j + 1);
+        if (!found) {
+          set_err(err, errlen, "One or more variables was not included in the ordering sequence. Only variables that are not fixed can be included in this list.");
+          return FMCMC_EINVAL;
+        }
+      }
+    }
+    if (ks->scheme == FMCMC_SCHEME_RANDOM && ks->seq && ks->seq_len < run->nsteps) {
+      set_err(err, errlen, "the planned random update sequence (%lld rows) is shorter than nsteps (%lld) (quirk D7: subscript out of bounds in the reference)", (long long)ks->seq_len, (long long)run->nsteps);
+      return FMCMC_EUNSUP;
+    }
+  }
+  return FMCMC_OK;
+}
+
+// --------------------------------------------------------------------------------
+// output gather (burnin / thin, R/mcmc.R:786-813) and store append
+// --------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int C, int k,
+                                   long long keep, long long burnin, long long thin, int colmajor) {
+  const long long total = (long long)C * keep * k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long c, r;
+    int j;
+    if (colmajor) { r = e % keep; j = (int)((e / keep) % k); c = e / (keep * k); }
+    else { j = (int)(e % k); r = (e / k) % keep; c = e / ((long long)k * keep); }
+    const long long srow = burnin + (r + 1) * thin - 1;
+    dst[e] = src[((size_t)srow * C + c) * k + j];
+  }
+}
+__global__ void append_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rowlen,
+                                   long long keep, long long burnin, long long thin) {
+  const long long total = keep * rowlen;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / rowlen, o = e % rowlen;
+    dst[e] = src[(size_t)(burnin + (r + 1) * thin - 1) * rowlen + o];
+  }
+}
+
+// --------------------------------------------------------------------------------
+// fmcmc_run
+// --------------------------------------------------------------------------------
+struct Blob {  // host staging of the small kernel-spec arrays -> one H2D copy
+  std::vector<unsigned char> h;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (h.size() + 15) & ~(size_t)15;
+    h.resize(off + bytes);
+    if (p) memcpy(h.data() + off, p, bytes);
+    return off;
+  }
+};
+
+template <int FAMILY>
+static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
+  const size_t smem = tiled_smem_bytes(PB);
+#define TL_CASE(P)                                                                                               \
+  case P: {                                                                                                      \
+    static bool attr_done[64] = {};                                                                              \
+    if (!attr_done[m->device]) {                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_kernel<FAMILY, P>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      if (e != cudaSuccess) return e;                                                                            \
+      attr_done[m->device] = true;                                                                               \
+    }                                                                                                            \
+    tiled_loglik_kernel<FAMILY, P><<<grid, TL_THREADS, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, rb.nchains, \
+                                                                           tb, rb.err);                          \
+    break;                                                                                                       \
+  }
+  switch (PB) {
+    TL_CASE(8)
+    TL_CASE(16)
+    TL_CASE(32)
+    default: return cudaErrorInvalidValue;
+  }
+#undef TL_CASE
+  return cudaGetLastError();
+}
+
+extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec* ks,
+                         fmcmc_kernel_state* state, const fmcmc_stream_spec* stream, double* ans_out,
+                         double* draws_out, double* logpost_out, fmcmc_run_report* report, char* err,
+                         size_t errlen) {
+  if (!m || !run || !ks || !stream) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  std::vector<int> free_idx;
+  const int kf = count_free(ks, free_idx);
+  int rc = validate_run(m, run, ks, kf, err, errlen);
+  if (rc) return rc;
+  const int k = m->mp.k, C = run->nchains;
+  const long long T = run->nsteps;
+  const long long keep = fmcmc_rows_kept(T, run->burnin, run->thin);
+  const long long dlen = fmcmc_kernel_state_len(ks->type, k, kf);
+  if (!run->initial && (m->state_nchains != C || m->state_k != k)) {
+    set_err(err, errlen, "initial is NULL but the model holds no state for %d chains", C);
+    return FMCMC_EINVAL;
+  }
+  if (stream->mode == FMCMC_STREAM_FED && (!stream->logu || !stream->z || stream->kdraw < 1)) {
+    set_err(err, errlen, "fed stream needs logu, z and kdraw");
+    return FMCMC_EINVAL;
+  }
+  {
+    const int need = (ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM) ? kf
+                     : (ks->scheme == FMCMC_SCHEME_JOINT ? kf : 1);
+    if (stream->mode == FMCMC_STREAM_FED && stream->kdraw < need) {
+      set_err(err, errlen, "fed stream has %d draws per row, the kernel needs %d", stream->kdraw, need);
+      return FMCMC_EINVAL;
+    }
+  }
+  if (report) {
+    memset(report, 0, sizeof(*report));
+    report->rows_kept = keep;
+    report->first_iter = run->burnin + run->thin;
+    report->last_iter = run->burnin + keep * run->thin;
+  }
+
+  // ---- kernel spec -> device ----------------------------------------------------------
+  Blob blob;
+  KParams kp{};
+  kp.type = ks->type; kp.k = k; kp.kf = kf; kp.scheme = ks->scheme; kp.order_len = ks->order_len;
+  kp.nadapt_len = ks->nadapt_len; kp.seq_len = ks->seq_len;
+  kp.warmup = ks->warmup; kp.freq = ks->freq < 1 ? 1 : ks->freq; kp.bw = ks->bw;
+  kp.until = ks->until; kp.eps = ks->eps; kp.Sd = ks->Sd; kp.arate = ks->arate; kp.dlen = dlen;
+  std::vector<double> dflt0(k, 0.0), dflt1(k, 1.0), dfltlo(k, -1.79769313486231570815e308), dflthi(k, 1.79769313486231570815e308);
+  std::vector<unsigned char> fixed0(k, 0);
+  const size_t o_mu = blob.add(ks->mu ? ks->mu : dflt0.data(), k * 8);
+  const size_t o_scale = blob.add(ks->scale ? ks->scale : dflt1.data(), k * 8);
+  const size_t o_min = blob.add(ks->min_ ? ks->min_ : dflt0.data(), k * 8);
+  const size_t o_max = blob.add(ks->max_ ? ks->max_ : dflt1.data(), k * 8);
+  const size_t o_lb = blob.add(ks->lb ? ks->lb : dfltlo.data(), k * 8);
+  const size_t o_ub = blob.add(ks->ub ? ks->ub : dflthi.data(), k * 8);
+  const size_t o_fixed = blob.add(ks->fixed ? ks->fixed : fixed0.data(), k);
+  const size_t o_free = blob.add(free_idx.data(), kf * sizeof(int));
+  const size_t o_order = (ks->scheme == FMCMC_SCHEME_EXPLICIT) ? blob.add(ks->order, ks->order_len * sizeof(int)) : 0;
+  const size_t o_nadapt = ks->nadapt_len > 0 ? blob.add(ks->nadapt, ks->nadapt_len * sizeof(long long)) : 0;
+  const size_t o_constr = ks->constr ? blob.add(ks->constr, (size_t)k * k * 8) : 0;
+  const bool fed_seq = ks->scheme == FMCMC_SCHEME_RANDOM && ks->seq;
+  const size_t o_seq = fed_seq ? blob.add(ks->seq, (size_t)C * ks->seq_len * sizeof(int)) : 0;
+  CU_CHECK(ensure(m->spec, blob.h.size()));
+  CU_CHECK(cudaMemcpyAsync(m->spec.p, blob.h.data(), blob.h.size(), cudaMemcpyHostToDevice, m->stream));
+  unsigned char* sb = m->spec.as<unsigned char>();
+  kp.mu = (const double*)(sb + o_mu); kp.scale = (const double*)(sb + o_scale);
+  kp.min_ = (const double*)(sb + o_min); kp.max_ = (const double*)(sb + o_max);
+  kp.lb = (const double*)(sb + o_lb); kp.ub = (const double*)(sb + o_ub);
+  kp.fixed = sb + o_fixed; kp.free_idx = (const int*)(sb + o_free);
+  kp.order = (ks->scheme == FMCMC_SCHEME_EXPLICIT) ? (const int*)(sb + o_order) : nullptr;
+  kp.nadapt = ks->nadapt_len > 0 ? (const long long*)(sb + o_nadapt) : nullptr;
+  kp.constr = ks->constr ? (const double*)(sb + o_constr) : nullptr;
+  kp.seq = fed_seq ? (const int*)(sb + o_seq) : nullptr;
+
+  // ---- stream ----------------------------------------------------------------------------
+  StreamParams sp{};
+  sp.mode = stream->mode; sp.kdraw = stream->kdraw; sp.seed = stream->seed; sp.run = (unsigned int)stream->run_index;
+  if (stream->mode == FMCMC_STREAM_FED) {
+    CU_CHECK(ensure(m->fed_logu, (size_t)C * T * 8));
+    CU_CHECK(ensure(m->fed_z, (size_t)C * T * stream->kdraw * 8));
+    CU_CHECK(cudaMemcpyAsync(m->fed_logu.p, stream->logu, (size_t)C * T * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_CHECK(cudaMemcpyAsync(m->fed_z.p, stream->z, (size_t)C * T * stream->kdraw * 8, cudaMemcpyHostToDevice, m->stream));
+    sp.logu = m->fed_logu.as<double>();
+    sp.z = m->fed_z.as<double>();
+  }
+
+  // ---- run buffers ---------------------------------------------------------------------
+  const bool is_ram = ks->type == FMCMC_KERNEL_RAM;
+  const long long worklen = is_ram ? 4LL * kf * kf : (ks->type == FMCMC_KERNEL_ADAPT ? (long long)kf * kf : 0);
+  CU_CHECK(ensure(m->ans, (size_t)T * C * k * 8));
+  CU_CHECK(ensure(m->draws, (size_t)T * C * k * 8));
+  CU_CHECK(ensure(m->logpost, (size_t)T * C * 8));
+  if (m->state_nchains != C || m->state_k != k) {
+    // shape change: state buffers are reallocated (grow-only helper keeps old data otherwise)
+    m->state_nchains = 0;
+  }
+  CU_CHECK(ensure(m->cur_theta, (size_t)C * k * 8));
+  CU_CHECK(ensure(m->cur_f, (size_t)C * 8));
+  CU_CHECK(ensure(m->prop, (size_t)C * k * 8));
+  CU_CHECK(ensure(m->prop_u, (size_t)C * k * 8));
+  CU_CHECK(ensure(m->istate, (size_t)C * FMCMC_ISTATE_LEN * 8));
+  CU_CHECK(ensure(m->dstate, (size_t)C * (dlen ? dlen : 1) * 8));
+  CU_CHECK(ensure(m->colsum, (size_t)C * kf * 8));
+  CU_CHECK(ensure(m->ubuf, (size_t)C * kf * 8));
+  CU_CHECK(ensure(m->work, (size_t)C * (worklen ? worklen : 1) * 8));
+  CU_CHECK(ensure(m->cflags, (size_t)C * sizeof(int)));
+  CU_CHECK(cudaMemsetAsync(m->errbuf.p, 0, 4 * sizeof(int), m->stream));
+  CU_CHECK(cudaMemsetAsync(m->nacc.p, 0, sizeof(unsigned long long), m->stream));
+  CU_CHECK(cudaMemsetAsync(m->cflags.p, 0, (size_t)C * sizeof(int), m->stream));
+  if (state && state->istate) {
+    CU_CHECK(cudaMemcpyAsync(m->istate.p, state->istate, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyHostToDevice, m->stream));
+  } else {
+    CU_CHECK(cudaMemsetAsync(m->istate.p, 0, (size_t)C * FMCMC_ISTATE_LEN * 8, m->stream));
+  }
+  if (dlen) {
+    if (state && state->dstate) {
+      CU_CHECK(cudaMemcpyAsync(m->dstate.p, state->dstate, (size_t)C * dlen * 8, cudaMemcpyHostToDevice, m->stream));
+    } else {
+      CU_CHECK(cudaMemsetAsync(m->dstate.p, 0, (size_t)C * dlen * 8, m->stream));
+    }
+  }
+  const double* d_initial = nullptr;
+  if (run->initial) {
+    CU_CHECK(ensure(m->initial, (size_t)C * k * 8));
+    CU_CHECK(cudaMemcpyAsync(m->initial.p, run->initial, (size_t)C * k * 8, cudaMemcpyHostToDevice, m->stream));
+    d_initial = m->initial.as<double>();
+  }
+  RunBuffers rb{};
+  rb.nchains = C; rb.chain_offset = run->chain_offset; rb.T = T;
+  rb.ans = m->ans.as<double>(); rb.draws = m->draws.as<double>(); rb.logpost = m->logpost.as<double>();
+  rb.cur_theta = m->cur_theta.as<double>(); rb.cur_f = m->cur_f.as<double>();
+  rb.prop = m->prop.as<double>(); rb.prop_u = m->prop_u.as<double>();
+  rb.istate = m->istate.as<long long>(); rb.dstate = m->dstate.as<double>();
+  rb.colsum = m->colsum.as<double>(); rb.ubuf = m->ubuf.as<double>();
+  rb.work = m->work.as<double>(); rb.worklen = worklen;
+  rb.chain_flags = m->cflags.as<int>(); rb.err = m->errbuf.as<int>();
+  rb.n_accept = m->nacc.as<unsigned long long>();
+
+  // ---- choose the stepping path --------------------------------------------------------
+  const ModelParams& mp = m->mp;
+  const size_t data_bytes = (size_t)mp.p_x * mp.ld * 8 + (size_t)mp.ld * 8 + (mp.group ? (size_t)mp.ld * 4 + 16 : 0);
+  const bool tiled_ok = (mp.family == FMCMC_FAMILY_GAUSSIAN_LM || mp.family == FMCMC_FAMILY_LOGISTIC) && mp.p_x <= 32;
+  int path = m->forced_path;
+  if (path == 0) path = (tiled_ok && data_bytes > 96 * 1024) ? 2 : 1;
+  if (path == 2 && !tiled_ok) {
+    set_err(err, errlen, "the observation-tiled path supports gaussian_lm / logistic with p_x <= 32 (got family %d, p_x %d)", mp.family, mp.p_x);
+    return FMCMC_EUNSUP;
+  }
+  long long launches = 0;
+  CU_CHECK(cudaEventRecord(m->ev0, m->stream));
+  if (path == 1) {
+    // ---- path 1: chain-resident fused kernel, one launch per bulk -------------------------
+    const bool wpc = C >= 2 * m->sm_count;
+    const int chain_smem_doubles = 7 * k;
+    int threads, chains_per_block;
+    if (wpc) { threads = 256; chains_per_block = threads / 32; }
+    else {
+      long long want = (mp.n + 3) / 4;
+      threads = (int)std::min<long long>(256, std::max<long long>(32, ((want + 31) / 32) * 32));
+      chains_per_block = 1;
+    }
+    const size_t chain_bytes = (size_t)chains_per_block * chain_smem_doubles * 8 + 2 * RES_MAX_WARPS * 8 + 128;
+    const bool in_smem = data_bytes + chain_bytes + 64 <= (size_t)m->smem_optin;
+    const size_t smem = chain_bytes + (in_smem ? data_bytes + 16 : 0);
+    if (smem > (size_t)m->smem_optin) {
+      set_err(err, errlen, "k = %d needs %zu bytes of shared memory per CTA (limit %d)", k, smem, m->smem_optin);
+      return FMCMC_EUNSUP;
+    }
+    const int blocks = (C + chains_per_block - 1) / chains_per_block;
+    if (wpc) {
+      CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mh_resident_kernel<true><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles);
+    } else {
+      CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mh_resident_kernel<false><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles);
+    }
+    CU_CHECK(cudaGetLastError());
+    launches += 1;
+  } else {
+    // ---- path 2: observation-tiled, two launches per row ------------------------------------
+    const int PB = mp.p_x <= 8 ? 8 : (mp.p_x <= 16 ? 16 : 32);
+    TiledBuffers tb{};
+    tb.ncols = is_ram ? 2 * C : C;
+    const int chain_blocks = (tb.ncols + TL_CHAINS - 1) / TL_CHAINS;
+    const long long ntiles = (mp.ld + TL_TILE - 1) / TL_TILE;
+    int gx = std::max(1, m->sm_count / chain_blocks);
+    if (gx > ntiles) gx = (int)ntiles;
+    tb.gx = gx;
+    CU_CHECK(ensure(m->partial, (size_t)gx * tb.ncols * 8));
+    tb.partial = m->partial.as<double>();
+    const dim3 lgrid(gx, chain_blocks);
+    const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
+    const size_t hsmem = (size_t)TL_HEAD_WARPS * 4 * k * 8;
+    for (long long row = 1; row <= T + 1; row++) {
+      tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row);
+      launches += 1;
+      if (row <= T) {
+        cudaError_t e = (mp.family == FMCMC_FAMILY_LOGISTIC)
+                            ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC>(m, PB, lgrid, rb, tb)
+                            : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM>(m, PB, lgrid, rb, tb);
+        if (e != cudaSuccess) { set_err(err, errlen, "CUDA launch error %s (tiled_loglik)", cudaGetErrorString(e)); return FMCMC_ECUDA; }
+        launches += 1;
+      }
+    }
+    CU_CHECK(cudaGetLastError());
+  }
+  CU_CHECK(cudaEventRecord(m->ev1, m->stream));
+
+  // ---- error check, outputs -----------------------------------------------------------------
+  int herr[4] = {0, 0, 0, 0};
+  unsigned long long hacc = 0;
+  CU_CHECK(cudaMemcpyAsync(herr, m->errbuf.p, sizeof(herr), cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaMemcpyAsync(&hacc, m->nacc.p, sizeof(hacc), cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  if (report) {
+    report->device_ms = ms;
+    report->n_accept = (int64_t)hacc;
+    report->path = path;
+    report->n_launches = launches;
+  }
+  if (herr[0] != 0) {
+    m->state_nchains = 0;
+    if (report) { report->nan_chain = herr[1]; report->nan_step = herr[2]; }
+    switch (herr[0]) {
+      case FMCMC_ENAN:
+        set_err(err, errlen, "fun(par) is undefined (NaN). Check either -fun- or the -lb- and -ub- parameters. This error ocurred during step i = %d (chain %d).", herr[2], herr[1]);
+        break;
+      case FMCMC_ENANRATIO:
+        set_err(err, errlen, "missing value where TRUE/FALSE needed (f1 - f0 is NaN) at step i = %d (chain %d).", herr[2], herr[1]);
+        break;
+      case FMCMC_ENOTPD:
+        set_err(err, errlen, "'Sigma' is not positive definite (step i = %d, chain %d).", herr[2], herr[1]);
+        break;
+      case FMCMC_EUNSUP:
+        set_err(err, errlen, "the kernel reached a state the reference itself mishandles at step i = %d, chain %d (SURVEY App. D: mirror quirk D8 / adapt update range / t. = 0)", herr[2], herr[1]);
+        break;
+      default:
+        set_err(err, errlen, "device error %d at step i = %d (chain %d).", herr[0], herr[2], herr[1]);
+    }
+    return herr[0];
+  }
+  m->state_nchains = C;
+  m->state_k = k;
+
+  const int gblocks = m->sm_count * 4;
+  if (run->flags & FMCMC_RUN_APPEND) {
+    if (m->store_C != C || m->store_k != k || m->store_rows + keep > m->store_cap) {
+      set_err(err, errlen, "sample store not reserved for %d chains x %d params x %lld more rows (call fmcmc_store_reset)", C, k, (long long)keep);
+      return FMCMC_EINVAL;
+    }
+    if (keep > 0) {
+      append_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.ans, m->store.as<double>() + (size_t)m->store_rows * C * k,
+                                                         (long long)C * k, keep, run->burnin, run->thin);
+      launches += 1;
+    }
+    m->store_rows += keep;
+  }
+  if (!(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0) {
+    const int colmajor = (run->flags & FMCMC_RUN_COLMAJOR) ? 1 : 0;
+    if (ans_out) {
+      CU_CHECK(ensure(m->out_ans, (size_t)C * keep * k * 8));
+      gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
+      CU_CHECK(cudaMemcpyAsync(ans_out, m->out_ans.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      launches += 1;
+    }
+    if (draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) {
+      CU_CHECK(ensure(m->out_draws, (size_t)C * keep * k * 8));
+      gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
+      CU_CHECK(cudaMemcpyAsync(draws_out, m->out_draws.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      launches += 1;
+    }
+    if (logpost_out) {
+      CU_CHECK(ensure(m->out_lp, (size_t)C * keep * 8));
+      gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, run->burnin, run->thin, 0);
+      CU_CHECK(cudaMemcpyAsync(logpost_out, m->out_lp.p, (size_t)C * keep * 8, cudaMemcpyDeviceToHost, m->stream));
+      launches += 1;
+    }
+  }
+  if (state && state->istate)
+    CU_CHECK(cudaMemcpyAsync(state->istate, m->istate.p, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (state && state->dstate && dlen)
+    CU_CHECK(cudaMemcpyAsync(state->dstate, m->dstate.p, (size_t)C * dlen * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  CU_CHECK(cudaGetLastError());
+  if (report) report->n_launches = launches;
+  return FMCMC_OK;
+}
+
+// --------------------------------------------------------------------------------
+// f(theta) on the device
+// --------------------------------------------------------------------------------
+extern "C" int fmcmc_logpost(fmcmc_model* m, int32_t nchains, const double* theta, double* out, char* err,
+                             size_t errlen) {
+  if (!m || !theta || !out || nchains < 1) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  const int k = m->mp.k;
+  CU_CHECK(ensure(m->initial, (size_t)nchains * k * 8));
+  CU_CHECK(ensure(m->tmp, (size_t)nchains * 8));
+  CU_CHECK(cudaMemcpyAsync(m->initial.p, theta, (size_t)nchains * k * 8, cudaMemcpyHostToDevice, m->stream));
+  logpost_kernel<<<nchains, 256, 0, m->stream>>>(m->mp, m->initial.as<double>(), m->tmp.as<double>(), nchains);
+  CU_CHECK(cudaGetLastError());
+  CU_CHECK(cudaMemcpyAsync(out, m->tmp.p, (size_t)nchains * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  return FMCMC_OK;
+}
+
+// --------------------------------------------------------------------------------
+// sample store + Gelman-Rubin
+// --------------------------------------------------------------------------------
+extern "C" int fmcmc_store_reset(fmcmc_model* m, int32_t nchains, int32_t k, int64_t capacity_rows, char* err,
+                                 size_t errlen) {
+  if (!m || nchains < 1 || k < 1 || capacity_rows < 0) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  CU_CHECK(ensure(m->store, (size_t)capacity_rows * nchains * k * 8));
+  m->store_C = nchains; m->store_k = k; m->store_cap = capacity_rows; m->store_rows = 0;
+  return FMCMC_OK;
+}
+extern "C" int64_t fmcmc_store_rows(const fmcmc_model* m) { return m ? m->store_rows : -1; }
+
+extern "C" int fmcmc_gelman_partials(fmcmc_model* m, int64_t row_begin, int64_t row_end, const uint8_t* free_mask,
+                                     double* xbar, double* s2, double* wsum, int dev_out, char* err, size_t errlen) {
+  if (!m || !xbar || !s2 || !wsum) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  const int C = m->store_C, k = m->store_k;
+  if (row_begin < 0 || row_end > m->store_rows || row_end - row_begin < 2) {
+    set_err(err, errlen, "bad window [%lld, %lld) of %lld stored rows", (long long)row_begin, (long long)row_end, (long long)m->store_rows);
+    return FMCMC_EINVAL;
+  }
+  std::vector<int> fidx;
+  for (int j = 0; j < k; j++)
+    if (!free_mask || free_mask[j]) fidx.push_back(j);
+  const int kf = (int)fidx.size();
+  if (kf < 1) { set_err(err, errlen, "no free parameters"); return FMCMC_EINVAL; }
+  CU_CHECK(ensure(m->g_mask, kf * sizeof(int)));
+  CU_CHECK(cudaMemcpyAsync(m->g_mask.p, fidx.data(), kf * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  const int nblocks = std::min(C, 4 * m->sm_count);
+  CU_CHECK(ensure(m->g_wpart, (size_t)nblocks * kf * kf * 8));
+  double *dx = xbar, *ds = s2, *dw = wsum;
+  if (!dev_out) {
+    CU_CHECK(ensure(m->g_xbar, (size_t)C * kf * 8));
+    CU_CHECK(ensure(m->g_s2, (size_t)C * kf * 8));
+    CU_CHECK(ensure(m->g_wsum, (size_t)kf * kf * 8));
+    dx = m->g_xbar.as<double>(); ds = m->g_s2.as<double>(); dw = m->g_wsum.as<double>();
+  }
+  const size_t smem = (size_t)kf * 8;
+  gelman_chain_stats_kernel<<<nblocks, 256, smem, m->stream>>>(m->store.as<double>(), C, k, row_begin, row_end,
+                                                               m->g_mask.as<int>(), kf, dx, ds, m->g_wpart.as<double>());
+  gelman_wsum_kernel<<<(kf * kf + 255) / 256, 256, 0, m->stream>>>(m->g_wpart.as<double>(), nblocks, kf * kf, dw);
+  CU_CHECK(cudaGetLastError());
+  if (!dev_out) {
+    CU_CHECK(cudaMemcpyAsync(xbar, dx, (size_t)C * kf * 8, cudaMemcpyDeviceToHost, m->stream));
+    CU_CHECK(cudaMemcpyAsync(s2, ds, (size_t)C * kf * 8, cudaMemcpyDeviceToHost, m->stream));
+    CU_CHECK(cudaMemcpyAsync(wsum, dw, (size_t)kf * kf * 8, cudaMemcpyDeviceToHost, m->stream));
+  }
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  return FMCMC_OK;
+}
+
+// Host finish of coda::gelman.diag's multivariate part: largest eigenvalue of
+// L^-1 B L^-T with W = L L' (== backsolve(CW, t(backsolve(CW, B, transpose=TRUE)), transpose=TRUE)).
+static int host_gelman_emax(int p, const std::vector<double>& W, const std::vector<double>& B, double* emax) {
+  std::vector<double> L((size_t)p * p, 0.0), Y((size_t)p * p), Mx((size_t)p * p);
+  for (int j = 0; j < p; j++) {
+    double s = W[j + (size_t)j * p];
+    for (int q = 0; q < j; q++) s -= L[j + (size_t)q * p] * L[j + (size_t)q * p];
+    if (!(s > 0.0)) return 1;
+    const double ljj = sqrt(s);
+    L[j + (size_t)j * p] = ljj;
+    for (int i = j + 1; i < p; i++) {
+      double v = W[i + (size_t)j * p];
+      for (int q = 0; q < j; q++) v -= L[i + (size_t)q * p] * L[j + (size_t)q * p];
+      L[i + (size_t)j * p] = v / ljj;
+    }
+  }
+  for (int c = 0; c < p; c++)
+    for (int a = 0; a < p; a++) {
+      double s = B[a + (size_t)c * p];
+      for (int q = 0; q < a; q++) s -= L[a + (size_t)q * p] * Y[q + (size_t)c * p];
+      Y[a + (size_t)c * p] = s / L[a + (size_t)a * p];
+    }
+  for (int c = 0; c < p; c++)
+    for (int a = 0; a < p; a++) {
+      double s = Y[c + (size_t)a * p];
+      for (int q = 0; q < a; q++) s -= L[a + (size_t)q * p] * Mx[q + (size_t)c * p];
+      Mx[a + (size_t)c * p] = s / L[a + (size_t)a * p];
+    }
+  for (int a = 0; a < p; a++)
+    for (int b = 0; b < a; b++) {
+      const double v = 0.5 * (Mx[a + (size_t)b * p] + Mx[b + (size_t)a * p]);
+      Mx[a + (size_t)b * p] = Mx[b + (size_t)a * p] = v;
+    }
+  // cyclic Jacobi, eigenvalues only
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0, diag = 0.0;
+    for (int q = 0; q < p; q++)
+      for (int r = 0; r < p; r++) {
+        const double v = Mx[r + (size_t)q * p] * Mx[r + (size_t)q * p];
+        if (r != q) off += v; else diag += v;
+      }
+    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+    for (int a = 0; a < p - 1; a++)
+      for (int b = a + 1; b < p; b++) {
+        const double apq = Mx[a + (size_t)b * p];
+        if (apq == 0.0) continue;
+        const double theta = (Mx[b + (size_t)b * p] - Mx[a + (size_t)a * p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int r = 0; r < p; r++) {
+          const double x = Mx[r + (size_t)a * p], y = Mx[r + (size_t)b * p];
+          Mx[r + (size_t)a * p] = c * x - s * y;
+          Mx[r + (size_t)b * p] = s * x + c * y;
+        }
+        for (int r = 0; r < p; r++) {
+          const double x = Mx[a + (size_t)r * p], y = Mx[b + (size_t)r * p];
+          Mx[a + (size_t)r * p] = c * x - s * y;
+          Mx[b + (size_t)r * p] = s * x + c * y;
+        }
+      }
+  }
+  double e = Mx[0];
+  for (int a = 1; a < p; a++) e = std::max(e, Mx[a + (size_t)a * p]);
+  *emax = e;
+  return 0;
+}
+
+extern "C" int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, int32_t kf,
+                                   const double* xbar, const double* s2, const double* wsum, int dev_in,
+                                   double* psrf, double* mpsrf, char* err, size_t errlen) {
+  if (!m || !xbar || !s2 || !wsum || !psrf || !mpsrf || kf < 1) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  if (nchains_total < 2) {  // R/convergence.R:239
+    set_err(err, errlen, "Convergence test with the Gelman is only available when `nchains` > 1L.");
+    return FMCMC_EINVAL;
+  }
+  CU_CHECK(cudaSetDevice(m->device));
+  const double *dx = xbar, *ds = s2, *dw = wsum;
+  if (!dev_in) {
+    CU_CHECK(ensure(m->g_xbar, (size_t)nchains_total * kf * 8));
+    CU_CHECK(ensure(m->g_s2, (size_t)nchains_total * kf * 8));
+    CU_CHECK(ensure(m->g_wsum, (size_t)kf * kf * 8));
+    CU_CHECK(cudaMemcpyAsync(m->g_xbar.p, xbar, (size_t)nchains_total * kf * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_CHECK(cudaMemcpyAsync(m->g_s2.p, s2, (size_t)nchains_total * kf * 8, cudaMemcpyHostToDevice, m->stream));
+    CU_CHECK(cudaMemcpyAsync(m->g_wsum.p, wsum, (size_t)kf * kf * 8, cudaMemcpyHostToDevice, m->stream));
+    dx = m->g_xbar.as<double>(); ds = m->g_s2.as<double>(); dw = m->g_wsum.as<double>();
+  }
+  // device: cross-chain moments + between-chain scatter (fixed order); host: O(kf^3) finish
+  const int nb = (int)std::min<long long>(nchains_total, 2LL * m->sm_count);
+  const size_t nK = (size_t)kf * kf;
+  CU_CHECK(ensure(m->tmp, ((size_t)kf * 8 + (size_t)nb * nK + nK) * 8));
+  double* d_mom = m->tmp.as<double>();
+  double* d_bpart = d_mom + (size_t)kf * 8;
+  double* d_b = d_bpart + (size_t)nb * nK;
+  gelman_moments_kernel<<<kf, 256, 0, m->stream>>>(dx, ds, (long long)nchains_total, kf, d_mom);
+  gelman_between_kernel<<<nb, 256, 0, m->stream>>>(dx, (long long)nchains_total, kf, d_mom, d_bpart);
+  gelman_wsum_kernel<<<(int)((nK + 255) / 256), 256, 0, m->stream>>>(d_bpart, nb, (int)nK, d_b);
+  CU_CHECK(cudaGetLastError());
+  std::vector<double> mom((size_t)kf * 8), B(nK), W(nK);
+  CU_CHECK(cudaMemcpyAsync(mom.data(), d_mom, mom.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaMemcpyAsync(B.data(), d_b, nK * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaMemcpyAsync(W.data(), dw, nK * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  const double N = (double)niter, M = (double)nchains_total;
+  for (size_t e = 0; e < nK; e++) { W[e] /= M; B[e] = N * (B[e] / (M - 1.0)); }
+  int status = FMCMC_OK;
+  *mpsrf = NAN;
+  if (kf > 1) {
+    double emax = 0.0;
+    if (host_gelman_emax(kf, W, B, &emax)) {
+      set_err(err, errlen, "chol(W) failed: the within-chain covariance is not positive definite");
+      status = FMCMC_ENOTPD;
+    } else {
+      *mpsrf = sqrt((1.0 - 1.0 / N) + (1.0 + 1.0 / (double)kf) * emax / N);
+    }
+  }
+  for (int a = 0; a < kf; a++) {  // univariate point estimates (coda::gelman.diag)
+    const double w = W[a + (size_t)a * kf], b = B[a + (size_t)a * kf];
+    const double muhat = mom[(size_t)a * 8], var_s2 = mom[(size_t)a * 8 + 2];
+    const double c1 = mom[(size_t)a * 8 + 3], c2 = mom[(size_t)a * 8 + 4];
+    const double var_w = var_s2 / M;
+    const double var_b = (2.0 * b * b) / (M - 1.0);
+    const double cov_wb = (N / M) * (c1 - 2.0 * muhat * c2);
+    const double V = (N - 1.0) * w / N + (1.0 + 1.0 / M) * b / N;
+    const double var_V = ((N - 1.0) * (N - 1.0) * var_w + (1.0 + 1.0 / M) * (1.0 + 1.0 / M) * var_b +
+                          2.0 * (N - 1.0) * (1.0 + 1.0 / M) * cov_wb) / (N * N);
+    const double df_V = (2.0 * V * V) / var_V;
+    const double df_adj = (df_V + 3.0) / (df_V + 1.0);
+    psrf[a] = sqrt(df_adj * ((N - 1.0) / N + (1.0 + 1.0 / M) * (1.0 / N) * (b / w)));
+  }
+  return status;
+}
+
+extern "C" int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double* mpsrf,
+                            int64_t* niter_used, char* err, size_t errlen) {
+  if (!m) { set_err(err, errlen, "null model"); return FMCMC_EINVAL; }
+  const long long rows = m->store_rows;
+  // coda: if (autoburnin && start(x) < end(x)/2) x <- window(x, start = end(x)/2 + 1); on the
+  // store's own 1..rows grid this keeps rows (floor(rows/2)+1 .. rows) (0-based: rows/2 ..).
+  const long long begin = rows / 2;
+  int kf = 0;
+  for (int j = 0; j < m->store_k; j++) kf += (!free_mask || free_mask[j]) ? 1 : 0;
+  if (m->store_C < 2) {
+    set_err(err, errlen, "Convergence test with the Gelman is only available when `nchains` > 1L.");
+    return FMCMC_EINVAL;
+  }
+  CU_CHECK(cudaSetDevice(m->device));
+  CU_CHECK(ensure(m->g_xbar, (size_t)m->store_C * kf * 8));
+  CU_CHECK(ensure(m->g_s2, (size_t)m->store_C * kf * 8));
+  CU_CHECK(ensure(m->g_wsum, (size_t)kf * kf * 8));
+  int rc = fmcmc_gelman_partials(m, begin, rows, free_mask, m->g_xbar.as<double>(), m->g_s2.as<double>(),
+                                 m->g_wsum.as<double>(), 1, err, errlen);
+  if (rc) return rc;
+  if (niter_used) *niter_used = rows - begin;
+  return fmcmc_gelman_finish(m, rows - begin, m->store_C, kf, m->g_xbar.as<double>(), m->g_s2.as<double>(),
+                             m->g_wsum.as<double>(), 1, psrf, mpsrf, err, errlen);
+}
+
+// --------------------------------------------------------------------------------
+// exported reference helpers on the device
+// --------------------------------------------------------------------------------
+__global__ void cov_recursive_kernel(int k, long long rows, const double* X, const double* mean_prev,
+                                     const double* cov_prev, double t, double eps, double Sd, const double* Ik,
+                                     double* mean_out, double* cov_out, double* scr) {
+  const int lane = threadIdx.x;
+  double* m = scr;
+  double* mp = scr + k;
+  for (int a = lane; a < k; a += FM_WARP) mp[a] = mean_prev[a];
+  for (int e = lane; e < k * k; e += FM_WARP) cov_out[e] = cov_prev[e];
+  __syncwarp();
+  for (long long i = 0; i < rows; i++) {
+    const double ti = t + (double)i;
+    const double* x = X + i * k;
+    for (int a = lane; a < k; a += FM_WARP) m[a] = xdiv(xadd(xmul(mp[a], ti), x[a]), ti + 1.0);
+    __syncwarp();
+    const double c1 = xdiv(ti - 1.0, ti), c2 = xdiv(Sd, ti);
+    for (int e = lane; e < k * k; e += FM_WARP) {
+      const int a = e % k, b = e / k;
+      double inner = xsub(xmul(ti, xmul(mp[a], mp[b])), xmul(ti + 1.0, xmul(m[a], m[b])));
+      inner = xadd(inner, xmul(x[a], x[b]));
+      inner = xadd(inner, xmul(eps, Ik ? Ik[e] : (a == b ? 1.0 : 0.0)));
+      cov_out[e] = xadd(xmul(c1, cov_out[e]), xmul(c2, inner));
+    }
+    __syncwarp();
+    for (int a = lane; a < k; a += FM_WARP) mp[a] = m[a];
+    __syncwarp();
+  }
+  for (int a = lane; a < k; a += FM_WARP) mean_out[a] = mp[a];
+}
+
+extern "C" int fmcmc_cov_recursive(int device, int32_t k, int64_t rows, const double* X, const double* mean_prev,
+                                   const double* cov_prev, double t, double eps, double Sd, const double* Ik,
+                                   double* mean_out, double* cov_out, char* err, size_t errlen) {
+  if (k < 1 || rows < 1 || !X || !mean_prev || !cov_prev || !mean_out || !cov_out) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(device));
+  const size_t nX = (size_t)rows * k, nK = (size_t)k * k;
+  double* d = nullptr;
+  const size_t total = nX + k + nK + nK + k + nK + 2 * (size_t)k;
+  CU_CHECK(cudaMalloc(&d, total * 8));
+  double *dX = d, *dm = dX + nX, *dc = dm + k, *dI = dc + nK, *dmo = dI + nK, *dco = dmo + k, *dscr = dco + nK;
+  cudaMemcpy(dX, X, nX * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dm, mean_prev, k * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dc, cov_prev, nK * 8, cudaMemcpyHostToDevice);
+  if (Ik) cudaMemcpy(dI, Ik, nK * 8, cudaMemcpyHostToDevice);
+  cov_recursive_kernel<<<1, 32>>>(k, rows, dX, dm, dc, t, eps, Sd, Ik ? dI : nullptr, dmo, dco, dscr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(mean_out, dmo, k * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(cov_out, dco, nK * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU_CHECK(e);
+  return FMCMC_OK;
+}
+
+__global__ void reflect_kernel(int k, long long count, double* x, const double* lb, const double* ub,
+                               const unsigned char* which) {
+  const long long total = count * k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % k);
+    if (which && !which[j]) continue;
+    x[e] = reflect1(x[e], lb[j], ub[j]);
+  }
+}
+
+extern "C" int fmcmc_reflect(int device, int32_t k, int64_t count, double* x, const double* lb, const double* ub,
+                             const uint8_t* which, char* err, size_t errlen) {
+  if (k < 1 || count < 1 || !x || !lb || !ub) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(device));
+  double* d = nullptr;
+  unsigned char* dw = nullptr;
+  const size_t n = (size_t)count * k;
+  CU_CHECK(cudaMalloc(&d, (n + 2 * (size_t)k) * 8));
+  CU_CHECK(cudaMalloc(&dw, k));
+  cudaMemcpy(d, x, n * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n, lb, k * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d + n + k, ub, k * 8, cudaMemcpyHostToDevice);
+  if (which) cudaMemcpy(dw, which, k, cudaMemcpyHostToDevice);
+  reflect_kernel<<<148, 256>>>(k, count, d, d + n, d + n + k, which ? dw : nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(x, d, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaFree(dw);
+  CU_CHECK(e);
+  return FMCMC_OK;
+}

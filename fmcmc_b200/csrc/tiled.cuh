@@ -1,0 +1,257 @@
+// tiled.cuh — observation-tiled stepping path (path 2) for large n.
+//
+// Per MH row two kernels run back to back on one stream (optionally replayed from a
+// CUDA graph):
+//   tiled_head    one warp per chain: finishes row i-1 (fixed-order reduction of the
+//                 per-CTA partial sums -> f(theta1) -> RAM phase B -> accept/reject ->
+//                 ans/draws/logpost rows) and proposes row i (propose_warp).
+//   tiled_loglik  the hot kernel.  Grid = (observation slices) x (chain blocks of 512).
+//                 Each CTA streams its slice of X / y through a 4-stage TMA pipeline
+//                 (cp.async.bulk + mbarrier full/empty ring).  Lane <-> chain: every
+//                 thread keeps the parameter vectors of 2 chains in registers, reads
+//                 the X tile by shared-memory BROADCAST (one LDS.128 feeds 4 DFMAs per
+//                 lane), applies the family's per-observation epilogue and accumulates
+//                 the chain's partial log-likelihood privately -> no cross-lane
+//                 reduction, no atomics, deterministic.  X is read from HBM once per
+//                 row per chain block and shared by all 512 chains of the CTA.
+#pragma once
+#include "families.cuh"
+#include "propose.cuh"
+
+#define TL_THREADS 256
+#define TL_RC 2
+#define TL_CHAINS (TL_THREADS * TL_RC)
+#define TL_TILE 128
+#define TL_STAGES 4
+#define TL_HEAD_WARPS 4
+
+struct TiledBuffers {
+  double* partial;  // [gx][ncols]
+  int gx;           // observation slices (gridDim.x of tiled_loglik)
+  int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
+};
+
+__host__ __device__ inline size_t tiled_smem_bytes(int PB) {
+  return 128 + (size_t)TL_STAGES * ((size_t)PB * TL_TILE + TL_TILE) * sizeof(double);
+}
+
+template <int FAMILY>
+__device__ __forceinline__ void tile_epilogue(double e00, double e01, double e10, double e11, double y0, double y1,
+                                              double& acc0, double& acc1) {
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
+    acc0 += logistic_term(e00, y0);
+    acc1 += logistic_term(e01, y0);
+    acc0 += logistic_term(e10, y1);
+    acc1 += logistic_term(e11, y1);
+  } else {  // Gaussian LM: e already holds the linear predictor incl. intercept
+    const double r00 = y0 - e00, r01 = y0 - e01, r10 = y1 - e10, r11 = y1 - e11;
+    acc0 = fma(r00, r00, acc0);
+    acc1 = fma(r01, r01, acc1);
+    acc0 = fma(r10, r10, acc0);
+    acc1 = fma(r11, r11, acc1);
+  }
+}
+
+template <int FAMILY, int PB>
+__global__ void __launch_bounds__(TL_THREADS, 1)
+tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
+                    TiledBuffers tb, const int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + TL_STAGES;
+  double* stage0 = reinterpret_cast<double*>(smem_raw + 128);
+  constexpr int STAGE_DOUBLES = PB * TL_TILE + TL_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (err[0] != 0) return;
+
+  const long long ntiles = (mp.ld + TL_TILE - 1) / TL_TILE;
+  const int p_x = mp.p_x;
+
+  if (tid == 0) {
+    for (int s = 0; s < TL_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TL_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  // columns >= p_x of every stage are never written by TMA: zero them once
+  for (int s = 0; s < TL_STAGES; s++)
+    for (int e = p_x * TL_TILE + tid; e < PB * TL_TILE; e += TL_THREADS) stage0[(size_t)s * STAGE_DOUBLES + e] = 0.0;
+  // make the generic-proxy zero fill visible before async-proxy traffic is consumed
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  auto issue = [&](long long tile, int s) {  // executed by thread 0 only
+    const long long row0 = tile * TL_TILE;
+    const long long rows = min((long long)TL_TILE, mp.ld - row0);
+    const uint32_t bytes = (uint32_t)(rows * 8);
+    double* dst = stage0 + (size_t)s * STAGE_DOUBLES;
+    mbar_expect_tx(&full[s], bytes * (uint32_t)(p_x + 1));
+    for (int j = 0; j < p_x; j++) bulk_g2s(dst + (size_t)j * TL_TILE, mp.X + (size_t)j * mp.ld + row0, bytes, &full[s]);
+    bulk_g2s(dst + (size_t)PB * TL_TILE, mp.y + row0, bytes, &full[s]);
+  };
+
+  // ---- this thread's two chains: parameters into registers ----------------------
+  const int col0 = blockIdx.y * TL_CHAINS + tid, col1 = col0 + TL_THREADS;
+  const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
+  double th0[PB], th1[PB], b00 = 0.0, b01 = 0.0;
+  {
+    const double* s0 = (col0 < tb.ncols) ? (col0 < C ? prop + (size_t)col0 * mp.k : prop_u + (size_t)(col0 - C) * mp.k) : nullptr;
+    const double* s1 = (col1 < tb.ncols) ? (col1 < C ? prop + (size_t)col1 * mp.k : prop_u + (size_t)(col1 - C) * mp.k) : nullptr;
+#pragma unroll
+    for (int j = 0; j < PB; j++) {
+      th0[j] = (s0 && j < p_x) ? s0[icpt + j] : 0.0;
+      th1[j] = (s1 && j < p_x) ? s1[icpt + j] : 0.0;
+    }
+    if (icpt) { b00 = s0 ? s0[0] : 0.0; b01 = s1 ? s1[0] : 0.0; }
+  }
+
+  // ---- pipeline prologue -----------------------------------------------------------
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    long long t = first;
+    for (int s = 0; s < TL_STAGES && t < ntiles; s++, t += step) issue(t, s);
+  }
+
+  double acc0 = 0.0, acc1 = 0.0;
+  long long it = 0;
+  for (long long tile = first; tile < ntiles; tile += step, it++) {
+    const int s = (int)(it % TL_STAGES);
+    const uint32_t ph = (uint32_t)((it / TL_STAGES) & 1);
+    if (tid == 0 && it >= 1) {  // refill the stage consumed in the previous iteration
+      const long long pit = it - 1;
+      const int ps = (int)(pit % TL_STAGES);
+      const long long nt = tile - step + (long long)TL_STAGES * step;
+      if (nt < ntiles) {
+        mbar_wait(&empty[ps], (uint32_t)((pit / TL_STAGES) & 1));
+        issue(nt, ps);
+      }
+    }
+    mbar_wait(&full[s], ph);
+    const double* Xs = stage0 + (size_t)s * STAGE_DOUBLES;
+    const double* ys = Xs + (size_t)PB * TL_TILE;
+    const long long row0 = tile * TL_TILE;
+    const int valid = (int)min((long long)TL_TILE, mp.n - row0);  // < TL_TILE only for the last tile
+    if (valid == TL_TILE) {
+#pragma unroll 1
+      for (int o = 0; o < TL_TILE; o += 2) {
+        double e00 = b00, e01 = b01, e10 = b00, e11 = b01;
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+          const double2 x = *reinterpret_cast<const double2*>(Xs + j * TL_TILE + o);  // warp-wide broadcast
+          e00 = fma(x.x, th0[j], e00);
+          e01 = fma(x.x, th1[j], e01);
+          e10 = fma(x.y, th0[j], e10);
+          e11 = fma(x.y, th1[j], e11);
+        }
+        const double2 yy = *reinterpret_cast<const double2*>(ys + o);
+        tile_epilogue<FAMILY>(e00, e01, e10, e11, yy.x, yy.y, acc0, acc1);
+      }
+    } else {
+      for (int o = 0; o < valid; o++) {
+        double e0 = b00, e1 = b01;
+#pragma unroll
+        for (int j = 0; j < PB; j++) {
+          const double x = Xs[j * TL_TILE + o];
+          e0 = fma(x, th0[j], e0);
+          e1 = fma(x, th1[j], e1);
+        }
+        const double yv = ys[o];
+        if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
+          acc0 += logistic_term(e0, yv);
+          acc1 += logistic_term(e1, yv);
+        } else {
+          const double r0 = yv - e0, r1 = yv - e1;
+          acc0 = fma(r0, r0, acc0);
+          acc1 = fma(r1, r1, acc1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  (void)warp;
+  if (col0 < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col0] = acc0;
+  if (col1 < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col1] = acc1;
+}
+
+// Fixed-order reduction of one column of the partial sums by one warp.
+__device__ __forceinline__ double reduce_partials(const TiledBuffers& tb, long long col, int lane) {
+  double s = 0.0;
+  for (int g = lane; g < tb.gx; g += FM_WARP) s += tb.partial[(size_t)g * tb.ncols + col];
+  return warp_sum(s);
+}
+
+// Finishes row `row - 1` and proposes row `row` (1 <= row <= T + 1).
+__global__ void __launch_bounds__(TL_HEAD_WARPS * 32)
+tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, TiledBuffers tb,
+                  const double* initial, long long row) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long c = (long long)blockIdx.x * TL_HEAD_WARPS + warp;
+  if (c >= rb.nchains || rb.err[0] != 0) return;
+  const int k = kp.k;
+  double* scr = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 4 * k;
+  double* th0 = rb.cur_theta + (size_t)c * k;
+  double* th1 = rb.prop + (size_t)c * k;
+  double* th1u = rb.prop_u + (size_t)c * k;
+
+  if (row == 1) {  // R/mcmc.R:737-743: theta0 = theta1 = initial, f evaluated by the next loglik launch
+    const double* src = initial ? initial + (size_t)c * k : th0;
+    for (int j = lane; j < k; j += FM_WARP) {
+      const double v = src[j];
+      th0[j] = v; th1[j] = v; th1u[j] = v;
+    }
+    if (lane == 0) {
+      rb.istate[c * FMCMC_ISTATE_LEN + 3] = 0;
+      rb.chain_flags[c] = 0;
+    }
+    return;
+  }
+
+  ChainCtx cx;
+  cx.c = c; cx.theta0 = th0; cx.theta1 = th1; cx.theta1u = th1u; cx.scr = scr;
+  cx.ans = rb.ans; cx.ans_stride = (long long)rb.nchains * k;
+
+  // ---- finish row r = row - 1 -------------------------------------------------------
+  const long long r = row - 1;
+  const double s = reduce_partials(tb, c, lane);
+  const double f1 = family_finish(mp, th1, s);
+  if (r == 1) {
+    if (lane == 0) {
+      for (int j = 0; j < k; j++) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
+      rb.logpost[c] = f1;
+      rb.cur_f[c] = f1;
+      for (int a = 0; a < kp.kf; a++) rb.colsum[(size_t)c * kp.kf + a] = th0[kp.free_idx[a]];
+    }
+  } else {
+    double f0 = rb.cur_f[c];
+    cx.i = r; cx.f0 = f0;
+    if (kp.type == FMCMC_KERNEL_RAM && (rb.chain_flags[c] & 1)) {  // phase B, R/kernel_ram.R:129-150
+      const double su = reduce_partials(tb, (long long)rb.nchains + c, lane);
+      const double f1u = family_finish(mp, th1u, su);
+      const int rc = ram_adapt_warp(kp, rb, cx, f1u, lane);
+      if (rc) { if (lane == 0) set_error(rb.err, rc, c + 1, r); return; }
+    }
+    int failed_i = 0;
+    if (lane == 0) {
+      bool failed = false;
+      unsigned long long n_acc = 0;
+      f0 = accept_row(kp, sp, rb, c, r, th0, th1, f0, f1, n_acc, failed);
+      rb.cur_f[c] = f0;
+      if (n_acc) atomicAdd(rb.n_accept, n_acc);
+      failed_i = failed;
+    }
+    failed_i = __shfl_sync(FM_FULL, failed_i, 0);
+    if (failed_i) return;
+  }
+  __syncwarp();
+
+  // ---- propose row `row` ---------------------------------------------------------------
+  if (row <= rb.T) {
+    cx.i = row;
+    cx.f0 = rb.cur_f[c];
+    const int rc = propose_warp(kp, sp, rb, cx, lane);
+    if (rc && lane == 0) set_error(rb.err, rc, c + 1, row);
+  }
+}

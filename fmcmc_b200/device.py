@@ -1,0 +1,166 @@
+"""Thin object wrapper over the C ABI handles (what the R glue keeps as an external pointer)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from . import _lib
+
+
+class DeviceModel:
+    """X / y uploaded once to HBM (fmcmc_model_create) + the run / store / Gelman entry points."""
+
+    def __init__(self, family, device: int = 0, device_ptrs=None):
+        L = _lib.lib()
+        self.family = family
+        self.k = family.k
+        self._h = C.c_void_p()
+        err = _lib.errbuf()
+        if device_ptrs is None:
+            m = family.marshal()
+            rc = L.fmcmc_model_create(m.byref(), device, C.byref(self._h), err, len(err))
+        else:
+            m = A.marshal_model(family.family, family.n, family.p_x, family.n_groups, flags=family.flags,
+                                hyper=family.hyper, device_ptrs=device_ptrs)
+            rc = L.fmcmc_model_create_device(m.byref(), device, C.byref(self._h), err, len(err))
+        _lib.check(rc, err)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().fmcmc_model_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_path(self, path: int):
+        rc = _lib.lib().fmcmc_set_path(self._h, path)
+        if rc:
+            raise _lib.FmcmcError(rc, "bad path")
+
+    def logpost(self, theta):
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        out = np.empty(theta.shape[0])
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_logpost(self._h, theta.shape[0], A.ptr(theta), A.ptr(out), err, len(err)), err)
+        return out
+
+    def run(self, kernel_spec: dict, nsteps, nchains, initial=None, burnin=0, thin=1, stream=None,
+            istate=None, dstate=None, flags=0, chain_offset=0, want_draws=True, outputs=True):
+        """One MCMC_without_conv_checker call (R/mcmc.R:485-838) for `nchains` chains."""
+        L = _lib.lib()
+        k = self.k
+        ks = A.marshal_kernel(kernel_spec)
+        if istate is None:
+            istate = np.zeros((nchains, A.ISTATE_LEN), dtype=np.int64)
+        st = A.marshal_state(istate, dstate)
+        if initial is not None:
+            initial = np.ascontiguousarray(np.broadcast_to(np.asarray(initial, dtype=np.float64), (nchains, k)))
+        rs = A.marshal_run(nsteps, nchains, initial, burnin, thin, flags | (0 if outputs else A.RUN_NO_OUTPUT)
+                           | (0 if want_draws else A.RUN_NO_DRAWS), chain_offset)
+        if stream is None:
+            stream = A.marshal_stream()
+        keep = A.rows_kept(nsteps, burnin, thin)
+        ans = draws = lp = None
+        if outputs:
+            ans = np.empty((nchains, keep, k))
+            lp = np.empty((nchains, keep))
+            if want_draws:
+                draws = np.empty((nchains, keep, k))
+        rep = A.RunReport()
+        err = _lib.errbuf()
+        rc = L.fmcmc_run(self._h, rs.byref(), ks.byref(), st.byref(), stream.byref(),
+                         A.ptr(ans) if ans is not None else None,
+                         A.ptr(draws) if draws is not None else None,
+                         A.ptr(lp) if lp is not None else None, C.byref(rep), err, len(err))
+        if rc:
+            e = _lib.FmcmcError(rc, err.value.decode(errors="replace"))
+            e.report = rep
+            raise e
+        return dict(ans=ans, draws=draws, logpost=lp, report=rep, istate=istate, dstate=dstate)
+
+    # ---- sample store + Gelman -------------------------------------------------------------
+    def store_reset(self, nchains, capacity_rows):
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_store_reset(self._h, nchains, self.k, capacity_rows, err, len(err)), err)
+
+    def store_rows(self) -> int:
+        return _lib.lib().fmcmc_store_rows(self._h)
+
+    def gelman_partials(self, row_begin, row_end, free_mask, nchains, out=None):
+        """Host arrays by default; with `out=(xbar_ptr, s2_ptr, wsum_ptr)` raw device pointers."""
+        mask = np.ascontiguousarray(free_mask, dtype=np.uint8)
+        kf = int(mask.sum())
+        err = _lib.errbuf()
+        if out is None:
+            xbar, s2, ws = np.empty((nchains, kf)), np.empty((nchains, kf)), np.empty((kf, kf), order="F")
+            rc = _lib.lib().fmcmc_gelman_partials(self._h, row_begin, row_end, A.ptr(mask, C.POINTER(C.c_uint8)),
+                                                  xbar.ctypes.data, s2.ctypes.data, ws.ctypes.data, 0, err, len(err))
+            _lib.check(rc, err)
+            return xbar, s2, ws
+        rc = _lib.lib().fmcmc_gelman_partials(self._h, row_begin, row_end, A.ptr(mask, C.POINTER(C.c_uint8)),
+                                              out[0], out[1], out[2], 1, err, len(err))
+        _lib.check(rc, err)
+        return None
+
+    def gelman_finish(self, niter, nchains_total, kf, xbar, s2, wsum, dev_in=False):
+        psrf = np.empty(kf)
+        mpsrf = C.c_double()
+        err = _lib.errbuf()
+        if dev_in:
+            px, ps, pw = xbar, s2, wsum
+        else:
+            xbar = np.ascontiguousarray(xbar, dtype=np.float64)
+            s2 = np.ascontiguousarray(s2, dtype=np.float64)
+            wsum = np.asfortranarray(wsum, dtype=np.float64)
+            px, ps, pw = xbar.ctypes.data, s2.ctypes.data, wsum.ctypes.data
+        rc = _lib.lib().fmcmc_gelman_finish(self._h, niter, nchains_total, kf, px, ps, pw, 1 if dev_in else 0,
+                                            A.ptr(psrf), C.byref(mpsrf), err, len(err))
+        _lib.check(rc, err)
+        return psrf, mpsrf.value
+
+
+def cov_recursive(X_t, Cov_t, Mean_t_prev, t_, Mean_t=None, eps=0.0, Sd=1.0, Ik=None, device=0):
+    """R/recursive.R:63-120 on the device.  Returns (Mean_t, Cov_t) after the last row of X_t."""
+    X = np.ascontiguousarray(np.atleast_2d(X_t), dtype=np.float64)
+    rows, k = X.shape
+    mp = np.ascontiguousarray(Mean_t_prev, dtype=np.float64).reshape(k)
+    cp = np.asfortranarray(Cov_t, dtype=np.float64)
+    ik = np.asfortranarray(Ik, dtype=np.float64) if Ik is not None else None
+    mo, co = np.empty(k), np.empty((k, k), order="F")
+    err = _lib.errbuf()
+    rc = _lib.lib().fmcmc_cov_recursive(device, k, rows, A.ptr(X), A.ptr(mp), A.ptr(cp), float(t_), float(eps),
+                                        float(Sd), A.ptr(ik) if ik is not None else None, A.ptr(mo), A.ptr(co),
+                                        err, len(err))
+    _lib.check(rc, err)
+    return mo, co
+
+
+def mean_recursive(X_t, Mean_t_prev, t_, device=0):
+    """R/recursive.R:124-139 on the device."""
+    X = np.atleast_2d(X_t)
+    k = X.shape[1]
+    return cov_recursive(X, np.zeros((k, k)), Mean_t_prev, t_, device=device)[0]
+
+
+def reflect_on_boundaries(x, lb, ub, which=None, device=0):
+    """R/kernel.R:450-493 on the device; `which` is 1-based like in R (None = all)."""
+    x = np.array(np.atleast_2d(x), dtype=np.float64, order="C")
+    count, k = x.shape
+    lb = np.ascontiguousarray(np.broadcast_to(np.asarray(lb, dtype=np.float64), (k,)))
+    ub = np.ascontiguousarray(np.broadcast_to(np.asarray(ub, dtype=np.float64), (k,)))
+    mask = None
+    if which is not None:
+        mask = np.zeros(k, dtype=np.uint8)
+        mask[np.asarray(which, dtype=int) - 1] = 1
+    err = _lib.errbuf()
+    rc = _lib.lib().fmcmc_reflect(device, k, count, A.ptr(x), A.ptr(lb), A.ptr(ub),
+                                  A.ptr(mask, C.POINTER(C.c_uint8)) if mask is not None else None, err, len(err))
+    _lib.check(rc, err)
+    return x if count > 1 else x[0]

@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), chains sharded across ranks with no
+data-path collective; NCCL is used only at convergence checks to
+  - all_gather the per-chain means / variances  (psrf),
+  - all_reduce the k x k within-chain scatter sum (W, needed for mpsrf).
+torch is used for device memory and torch.distributed only — no compute."""
+from __future__ import annotations
+
+import os
+
+
+class ChainSharding:
+    def __init__(self, nchains_total: int):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.total = nchains_total
+        base, rem = divmod(nchains_total, self.world)
+        self.counts = [base + (1 if r < rem else 0) for r in range(self.world)]
+        self.offset = sum(self.counts[:self.rank])
+        self.local = self.counts[self.rank]
+        self.on_cuda = dist.get_backend() == "nccl"
+        self.device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if self.on_cuda \
+            else torch.device("cpu")
+
+    def gelman(self, model, row_begin, row_end, free_mask, nlocal, kf, niter):
+        """partials on every GPU -> all_gather(xbar, s2) + all_reduce(wsum) -> replicated finish."""
+        torch, dist = self.torch, self.dist
+        if self.on_cuda:
+            xbar = torch.empty((nlocal, kf), dtype=torch.float64, device=self.device)
+            s2 = torch.empty_like(xbar)
+            ws = torch.empty((kf * kf,), dtype=torch.float64, device=self.device)
+            model.gelman_partials(row_begin, row_end, free_mask, nlocal,
+                                  out=(xbar.data_ptr(), s2.data_ptr(), ws.data_ptr()))
+        else:   # gloo (CPU tests): statistics computed by the caller-supplied model on host arrays
+            xb, s, w = model.gelman_partials(row_begin, row_end, free_mask, nlocal)
+            xbar, s2, ws = torch.from_numpy(xb), torch.from_numpy(s), torch.from_numpy(w.reshape(-1, order="F").copy())
+        gx, gs = self.all_gather_rows(xbar), self.all_gather_rows(s2)
+        dist.all_reduce(ws, op=dist.ReduceOp.SUM)
+        if self.on_cuda:
+            torch.cuda.synchronize(self.device)
+            return model.gelman_finish(niter, self.total, kf, gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), dev_in=True)
+        return model.gelman_finish(niter, self.total, kf, gx.numpy(), gs.numpy(),
+                                   ws.numpy().reshape(kf, kf, order="F"))
+
+    def all_gather_rows(self, t):
+        """all_gather of [n_r][kf] blocks with (possibly) different n_r, in rank order."""
+        torch, dist = self.torch, self.dist
+        if len(set(self.counts)) == 1:
+            out = torch.empty((self.total, t.shape[1]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.contiguous())
+            return out
+        parts = [torch.empty((n, t.shape[1]), dtype=t.dtype, device=t.device) for n in self.counts]
+        dist.all_gather(parts, t.contiguous())
+        return torch.cat(parts, dim=0)
+
+
+def current_sharding(nchains_total: int):
+    """ChainSharding when torch.distributed is initialised with world_size > 1, else None."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    return ChainSharding(nchains_total)

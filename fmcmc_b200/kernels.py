@@ -1,0 +1,244 @@
+"""Transition-kernel constructors with the reference's names, arguments and defaults
+(R/kernel_normal.R, R/kernel_unif.R, R/kernel_adapt.R, R/kernel_ram.R, R/kernel_mirror.R).
+
+An `FmcmcKernel` plays the role of the R `fmcmc_kernel` environment (R/kernel.R:283-317):
+hyper-parameters and mutable per-chain state (`abs_iter`, `Sigma`, `Mean_t_prev`, `mu`,
+`scale`, `obs_arate`, `nerrors`) are attributes, readable after the run and reused when the
+object is passed to another MCMC() call.  With nchains > 1 the object turns into a kernel
+list (R/kernel.R:348-377 rep_kernel): `kernel[i]` is chain i's copy."""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+
+from . import _abi as A
+
+_SCHEMES = {"joint": A.SCHEME_JOINT, "ordered": A.SCHEME_ORDERED, "random": A.SCHEME_RANDOM}
+
+
+def _check_dimensions(x, k, name):
+    """R/kernel.R:1-15"""
+    x = np.atleast_1d(np.asarray(x))
+    if x.size > 1 and x.size != k:
+        raise ValueError(f"Incorrect length of -{name}-.")
+    if x.size == 1 and k > 1:
+        return np.repeat(x, k)
+    return x
+
+
+def _process_bounds(b, lower):
+    """R/kernel.R:25-41: NA -> -/+ .Machine$double.xmax"""
+    b = np.array(b, dtype=np.float64, copy=True)
+    b[np.isnan(b)] = -A.DBL_MAX if lower else A.DBL_MAX
+    return b
+
+
+class FmcmcKernel:
+    def __init__(self, ktype, **hyper):
+        self.type = ktype
+        self.__dict__.update(hyper)
+        self.k = None
+        self.abs_iter = 0
+        self.nerrors = 0
+        self._chains = None      # list of per-chain copies once replicated
+        self._istate = None      # [C][4] int64 / [C][dlen] float64 round-tripped through the ABI
+        self._dstate = None
+        self._kf = None
+
+    # -- kernel-list behaviour (R/kernel.R:330-434) --------------------------------------
+    @property
+    def is_list(self):
+        return self._chains is not None
+
+    def __len__(self):
+        return len(self._chains) if self._chains is not None else 1
+
+    def __getitem__(self, i):
+        if self._chains is None:
+            raise TypeError("not a kernel list")
+        return self._chains[i]
+
+    def _replicate(self, nchains):
+        proto = copy.copy(self)
+        proto._chains = None
+        self._chains = [copy.deepcopy(proto) for _ in range(nchains)]
+
+    # -- marshalling -------------------------------------------------------------------------
+    def to_spec(self, k: int) -> dict:
+        """Recycles / validates the hyper-parameters for a k-vector (the lazy init every R
+        proposal closure does on its first call) and returns the dict _abi.marshal_kernel eats."""
+        t = self.type
+        s = dict(type=t, k=k)
+        g = self.__dict__
+        fixed = _check_dimensions(g.get("fixed", False), k, "fixed").astype(bool)
+        s["fixed"] = fixed
+        if "lb" in g:
+            lb = _process_bounds(_check_dimensions(g["lb"], k, "lb"), True)
+            ub = _process_bounds(_check_dimensions(g["ub"], k, "ub"), False)
+            if np.any(ub <= lb):
+                raise ValueError("-ub- cannot be <= than -lb-.")
+            s["lb"], s["ub"] = lb, ub
+        if "mu" in g:
+            s["mu"] = _check_dimensions(g["mu"], k, "mu").astype(np.float64)
+        if "scale" in g:
+            s["scale"] = _check_dimensions(g["scale"], k, "scale").astype(np.float64)
+        if "min_" in g:
+            s["min_"] = _check_dimensions(g["min_"], k, "min.").astype(np.float64)
+            s["max_"] = _check_dimensions(g["max_"], k, "max.").astype(np.float64)
+            if np.any(s["max_"] <= s["min_"]):
+                raise ValueError("-max.- cannot be <= than -min.-.")
+        scheme = g.get("scheme", "joint")
+        if isinstance(scheme, str):
+            if scheme not in _SCHEMES:
+                raise ValueError("-scheme- update must be either an integer sequence, 'joint', 'ordered', "
+                                 "or 'random'.")
+            s["scheme"] = _SCHEMES[scheme]
+        else:                                          # explicit integer order, R/kernel.R:69-91
+            order = np.asarray(scheme, dtype=np.int32)
+            nfree = int((~fixed).sum())
+            if order.size != nfree:
+                raise ValueError("When setting the update scheme, it should have the same length as the "
+                                 f"number of variables that will not be fixed. Right now length(scheme) = "
+                                 f"{order.size} while sum(!fixed) = {nfree}.")
+            missing = [j + 1 for j in np.where(~fixed)[0] if (j + 1) not in order]
+            if missing:
+                raise ValueError("One or more variables was not included in the ordering sequence. The full "
+                                 f"list follows: {', '.join(map(str, missing))}. Only variables that are not "
+                                 "fixed can be included in this list.")
+            s["scheme"], s["order"] = A.SCHEME_EXPLICIT, order
+        if (~fixed).sum() == 0:
+            raise ValueError("The number of parameters to update, i.e. not fixed, cannot be zero. Check the "
+                             "value -fixed- in the kernel initialization.")
+        for name in ("warmup", "freq", "bw", "until", "eps", "Sd", "arate", "constr", "mvn_method"):
+            if name in g and g[name] is not None:
+                s[name] = g[name]
+        if "nadapt_schedule" in g:
+            s["nadapt"] = g["nadapt_schedule"]
+        self.k = int((~fixed).sum()) if t in (A.KERNEL_ADAPT, A.KERNEL_RAM) else \
+            (int((~fixed).sum()) if s["scheme"] == A.SCHEME_JOINT else 1)
+        self._kf = int((~fixed).sum())
+        self.which_ = np.where(~fixed)[0] + 1
+        return s
+
+    # -- state <-> flat ABI arrays -----------------------------------------------------------
+    def state_arrays(self, nchains, k):
+        kf = self._kf
+        dlen = A.state_len(self.type, k, kf)
+        if self._istate is not None and self._istate.shape[0] == nchains and \
+                (self._dstate is None or self._dstate.shape[1] == max(dlen, 1)):
+            return self._istate, self._dstate
+        ist = np.zeros((nchains, A.ISTATE_LEN), dtype=np.int64)
+        dst = np.zeros((nchains, max(dlen, 1)), dtype=np.float64)
+        user_sigma = getattr(self, "Sigma", None)
+        if user_sigma is not None and self.type in (A.KERNEL_ADAPT, A.KERNEL_RAM) and not self.is_list:
+            sig = np.asfortranarray(user_sigma, dtype=np.float64)
+            dst[:, :kf * kf] = sig.reshape(-1, order="F")[None, :]
+            ist[:, 1] |= A.STATE_INIT
+        self._istate, self._dstate = ist, dst
+        return ist, dst
+
+    def absorb_state(self, k):
+        """Write the device state back into user-visible attributes (R/mcmc.R:629-631)."""
+        ist, dst = self._istate, self._dstate
+        if ist is None:
+            return
+        kf = self._kf
+        targets = self._chains if self._chains is not None else [self]
+        for c, kc in enumerate(targets):
+            kc.abs_iter = int(ist[c, 0])
+            kc.nerrors = int(ist[c, 2])
+            if self.type == A.KERNEL_ADAPT:
+                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F").copy()
+                kc.Mean_t_prev = dst[c, kf * kf:kf * kf + kf].copy() if ist[c, 1] & A.STATE_HAS_MEAN else None
+            elif self.type == A.KERNEL_RAM:
+                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F").copy()
+            elif self.type in (A.KERNEL_NMIRROR, A.KERNEL_UMIRROR):
+                kc.mu = dst[c, :k].copy()
+                kc.scale = dst[c, k:2 * k].copy()
+                kind = (int(ist[c, 1]) >> A.STATE_OBS_SHIFT) & 3
+                kc.obs_arate = None if kind == 0 else (float(dst[c, 2 * k]) if kind == 1 else dst[c, 2 * k:3 * k].copy())
+
+    def __repr__(self):
+        if self.is_list:
+            return f"A list of {len(self)} fmcmc_kernels."
+        names = sorted(n for n in self.__dict__ if not n.startswith("_"))
+        return "An environment of class fmcmc_kernel: " + ", ".join(names)
+
+
+def kernel_normal(mu=0.0, scale=1.0, fixed=False, scheme="joint"):
+    """R/kernel_normal.R:26-82"""
+    return FmcmcKernel(A.KERNEL_NORMAL, mu=mu, scale=scale, fixed=fixed, scheme=scheme)
+
+
+def kernel_normal_reflective(mu=0.0, scale=1.0, lb=-A.DBL_MAX, ub=A.DBL_MAX, fixed=False, scheme="joint"):
+    """R/kernel_normal.R:96-177"""
+    return FmcmcKernel(A.KERNEL_NORMAL_REFLECTIVE, mu=mu, scale=scale, lb=lb, ub=ub, fixed=fixed, scheme=scheme)
+
+
+def kernel_unif(min_=-1.0, max_=1.0, fixed=False, scheme="joint"):
+    """R/kernel_unif.R:15-66 (R's `min.`/`max.` are spelled min_/max_)"""
+    return FmcmcKernel(A.KERNEL_UNIF, min_=min_, max_=max_, fixed=fixed, scheme=scheme)
+
+
+def kernel_unif_reflective(min_=-1.0, max_=1.0, lb=None, ub=None, fixed=False, scheme="joint"):
+    """R/kernel_unif.R:74-147 (lb = min., ub = max. by default)"""
+    return FmcmcKernel(A.KERNEL_UNIF_REFLECTIVE, min_=min_, max_=max_, lb=min_ if lb is None else lb,
+                       ub=max_ if ub is None else ub, fixed=fixed, scheme=scheme)
+
+
+def kernel_adapt(mu=0.0, bw=0, lb=-A.DBL_MAX, ub=A.DBL_MAX, freq=1, warmup=500, Sigma=None, Sd=None,
+                 eps=1e-4, fixed=False, until=math.inf):
+    """R/kernel_adapt.R:54-208 (Haario et al. 2001)."""
+    if bw > 0 and bw > warmup:
+        raise ValueError("The `warmup` parameter must be greater than `bw`.")
+    return FmcmcKernel(A.KERNEL_ADAPT, mu=mu, bw=bw, lb=lb, ub=ub, freq=freq, warmup=warmup, Sigma=Sigma, Sd=Sd,
+                       eps=eps, fixed=fixed, until=until, Mean_t_prev=None)
+
+
+kernel_am = kernel_adapt
+
+
+def kernel_ram(mu=0.0, eta=None, qfun=None, arate=0.234, freq=1, warmup=0, Sigma=None, eps=1e-4,
+               lb=-A.DBL_MAX, ub=A.DBL_MAX, fixed=False, until=math.inf, constr=None):
+    """R/kernel_ram.R:65-181 (Vihola 2012).  `eta` and `qfun` are R closures in the reference;
+    only their defaults (min(1, i^(-2/3) k) and rt(k, k)) exist on the device."""
+    if eta is not None or qfun is not None:
+        raise TypeError("kernel_ram: custom `eta` / `qfun` closures cannot run on the device; only the "
+                        "reference defaults are built in.")
+    return FmcmcKernel(A.KERNEL_RAM, mu=mu, arate=arate, freq=freq, warmup=warmup, Sigma=Sigma, eps=eps, lb=lb,
+                       ub=ub, fixed=fixed, until=until, constr=constr)
+
+
+def _nadapt_schedule(warmup, nadapt):
+    """floor(seq(1, warmup, length.out = nadapt + 1)[-1])  (R/kernel_mirror.R:165)"""
+    n = nadapt + 1
+    if n < 2:
+        return np.zeros(0, dtype=np.int64)
+    by = (warmup - 1) / (n - 1)
+    seq = [1.0] + [1.0 + i * by for i in range(1, n - 1)] + [float(warmup)]
+    return np.floor(np.array(seq[1:])).astype(np.int64)
+
+
+def kernel_nmirror(mu=0.0, scale=1.0, warmup=500, nadapt=4, arate=0.4, lb=-A.DBL_MAX, ub=A.DBL_MAX,
+                   fixed=False, scheme="joint"):
+    """R/kernel_mirror.R:54-173 (Thawornwattana et al. 2018)."""
+    return FmcmcKernel(A.KERNEL_NMIRROR, mu=mu, scale=scale, warmup=warmup, nadapt=nadapt, arate=arate, lb=lb,
+                       ub=ub, fixed=fixed, scheme=scheme, obs_arate=None,
+                       nadapt_schedule=_nadapt_schedule(warmup, nadapt))
+
+
+def kernel_umirror(mu=0.0, scale=1.0, warmup=500, nadapt=4, arate=0.4, lb=-A.DBL_MAX, ub=A.DBL_MAX,
+                   fixed=False, scheme="joint"):
+    """R/kernel_mirror.R:177-301"""
+    return FmcmcKernel(A.KERNEL_UMIRROR, mu=mu, scale=scale, warmup=warmup, nadapt=nadapt, arate=arate, lb=lb,
+                       ub=ub, fixed=fixed, scheme=scheme, obs_arate=None,
+                       nadapt_schedule=_nadapt_schedule(warmup, nadapt))
+
+
+def kernel_new(proposal=None, *args, **kwargs):
+    """R/kernel.R:283-317: user closures cannot run on the device (north_star)."""
+    raise TypeError("kernel_new(): a kernel made of R/Python closures cannot run on the device. Use one of "
+                    "kernel_normal, kernel_normal_reflective, kernel_unif, kernel_unif_reflective, "
+                    "kernel_adapt, kernel_ram, kernel_nmirror, kernel_umirror.")
