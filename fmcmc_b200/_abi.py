@@ -30,7 +30,7 @@ STATE_HAS_MEAN, STATE_INIT, STATE_OBS_SHIFT = 1, 2, 2
 
 STREAM_PHILOX, STREAM_FED = 0, 1
 
-RUN_NO_DRAWS, RUN_COLMAJOR, RUN_APPEND, RUN_NO_OUTPUT = 1, 2, 4, 8
+RUN_NO_DRAWS, RUN_COLMAJOR, RUN_APPEND, RUN_NO_OUTPUT, RUN_DEVICE_STATE = 1, 2, 4, 8, 16
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -86,7 +86,8 @@ class RunReport(C.Structure):
         ("rows_kept", C.c_int64), ("first_iter", C.c_int64), ("last_iter", C.c_int64),
         ("nan_chain", C.c_int64), ("nan_step", C.c_int64), ("n_accept", C.c_int64),
         ("n_launches", C.c_int64), ("device_ms", C.c_double), ("path", C.c_int32),
-        ("reserved", C.c_int32),
+        ("reserved", C.c_int32), ("hot_ms", C.c_double), ("hot_launches", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
     ]
 
 

@@ -61,7 +61,7 @@ struct RunBuffers {
   double* prop_u;          // [C][k]  RAM un-reflected proposal
   long long* istate;       // [C][4]
   double* dstate;          // [C][dlen]
-  double* colsum;          // [C][kf] running column sums of this run's ans rows (kernel_adapt)
+  double* colsum;          // [C][kf][2] compensated (hi, lo) running column sums of this run's ans rows (kernel_adapt)
   double* ubuf;            // [C][kf] RAM's U of the current row
   double* work;            // [C][worklen] scratch matrices (L cache, RAM temporaries)
   long long worklen;

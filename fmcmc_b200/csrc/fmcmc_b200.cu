@@ -39,6 +39,8 @@ static void set_err(char* err, size_t errlen, const char* fmt, ...) {
     }                                                                                         \
   } while (0)
 
+#define FM_HOT_EVENTS 64
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -74,7 +76,8 @@ struct fmcmc_model {
   // run buffers (grow-only)
   DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
       errbuf, nacc, spec, fed_logu, fed_z, initial, partial, out_ans, out_draws, out_lp, tmp;
-  int state_nchains = 0, state_k = 0;  // shape of cur_theta (valid after a run)
+  int state_nchains = 0, state_k = 0, state_type = 0;  // shape of cur_theta / kernel state (valid after a run)
+  std::vector<cudaEvent_t> hot_ev;
   // sample store (append_chains): [rows][C][k]
   DevBuf store;
   int store_C = 0, store_k = 0;
@@ -211,6 +214,7 @@ extern "C" void fmcmc_model_free(fmcmc_model* m) {
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
                     &m->g_mask};
   for (DevBuf* b : bufs) release(*b);
+  for (auto& e : m->hot_ev) cudaEventDestroy(e);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -395,6 +399,13 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     report->last_iter = run->burnin + keep * run->thin;
   }
 
+  long long h2d = 0, d2h = 0;
+  const bool dev_state = (run->flags & FMCMC_RUN_DEVICE_STATE) != 0;
+  if (dev_state && (m->state_nchains != C || m->state_k != k || m->state_type != ks->type)) {
+    set_err(err, errlen, "FMCMC_RUN_DEVICE_STATE: the model holds no kernel state of this shape");
+    return FMCMC_EINVAL;
+  }
+
   // ---- kernel spec -> device ----------------------------------------------------------
   Blob blob;
   KParams kp{};
@@ -419,6 +430,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   const size_t o_seq = fed_seq ? blob.add(ks->seq, (size_t)C * ks->seq_len * sizeof(int)) : 0;
   CU_CHECK(ensure(m->spec, blob.h.size()));
   CU_CHECK(cudaMemcpyAsync(m->spec.p, blob.h.data(), blob.h.size(), cudaMemcpyHostToDevice, m->stream));
+  h2d += (long long)blob.h.size();
   unsigned char* sb = m->spec.as<unsigned char>();
   kp.mu = (const double*)(sb + o_mu); kp.scale = (const double*)(sb + o_scale);
   kp.min_ = (const double*)(sb + o_min); kp.max_ = (const double*)(sb + o_max);
@@ -437,6 +449,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     CU_CHECK(ensure(m->fed_z, (size_t)C * T * stream->kdraw * 8));
     CU_CHECK(cudaMemcpyAsync(m->fed_logu.p, stream->logu, (size_t)C * T * 8, cudaMemcpyHostToDevice, m->stream));
     CU_CHECK(cudaMemcpyAsync(m->fed_z.p, stream->z, (size_t)C * T * stream->kdraw * 8, cudaMemcpyHostToDevice, m->stream));
+    h2d += (long long)C * T * 8 * (1 + stream->kdraw);
     sp.logu = m->fed_logu.as<double>();
     sp.z = m->fed_z.as<double>();
   }
@@ -457,21 +470,25 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   CU_CHECK(ensure(m->prop_u, (size_t)C * k * 8));
   CU_CHECK(ensure(m->istate, (size_t)C * FMCMC_ISTATE_LEN * 8));
   CU_CHECK(ensure(m->dstate, (size_t)C * (dlen ? dlen : 1) * 8));
-  CU_CHECK(ensure(m->colsum, (size_t)C * kf * 8));
+  CU_CHECK(ensure(m->colsum, (size_t)C * kf * 16));
   CU_CHECK(ensure(m->ubuf, (size_t)C * kf * 8));
   CU_CHECK(ensure(m->work, (size_t)C * (worklen ? worklen : 1) * 8));
   CU_CHECK(ensure(m->cflags, (size_t)C * sizeof(int)));
   CU_CHECK(cudaMemsetAsync(m->errbuf.p, 0, 4 * sizeof(int), m->stream));
   CU_CHECK(cudaMemsetAsync(m->nacc.p, 0, sizeof(unsigned long long), m->stream));
   CU_CHECK(cudaMemsetAsync(m->cflags.p, 0, (size_t)C * sizeof(int), m->stream));
-  if (state && state->istate) {
+  if (dev_state) {
+    // resident: nothing to move
+  } else if (state && state->istate) {
     CU_CHECK(cudaMemcpyAsync(m->istate.p, state->istate, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyHostToDevice, m->stream));
+    h2d += (long long)C * FMCMC_ISTATE_LEN * 8;
   } else {
     CU_CHECK(cudaMemsetAsync(m->istate.p, 0, (size_t)C * FMCMC_ISTATE_LEN * 8, m->stream));
   }
-  if (dlen) {
+  if (dlen && !dev_state) {
     if (state && state->dstate) {
       CU_CHECK(cudaMemcpyAsync(m->dstate.p, state->dstate, (size_t)C * dlen * 8, cudaMemcpyHostToDevice, m->stream));
+      h2d += (long long)C * dlen * 8;
     } else {
       CU_CHECK(cudaMemsetAsync(m->dstate.p, 0, (size_t)C * dlen * 8, m->stream));
     }
@@ -481,6 +498,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     CU_CHECK(ensure(m->initial, (size_t)C * k * 8));
     CU_CHECK(cudaMemcpyAsync(m->initial.p, run->initial, (size_t)C * k * 8, cudaMemcpyHostToDevice, m->stream));
     d_initial = m->initial.as<double>();
+    h2d += (long long)C * k * 8;
   }
   RunBuffers rb{};
   rb.nchains = C; rb.chain_offset = run->chain_offset; rb.T = T;
@@ -504,6 +522,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     return FMCMC_EUNSUP;
   }
   long long launches = 0;
+  int hot_timed = 0;
   CU_CHECK(cudaEventRecord(m->ev0, m->stream));
   if (path == 1) {
     // ---- path 1: chain-resident fused kernel, one launch per bulk -------------------------
@@ -548,14 +567,21 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const dim3 lgrid(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const size_t hsmem = (size_t)TL_HEAD_WARPS * 4 * k * 8;
+    if (m->hot_ev.empty()) {
+      m->hot_ev.resize(2 * FM_HOT_EVENTS);
+      for (auto& e : m->hot_ev) CU_CHECK(cudaEventCreate(&e));
+    }
     for (long long row = 1; row <= T + 1; row++) {
       tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row);
       launches += 1;
       if (row <= T) {
+        const bool timed = hot_timed < FM_HOT_EVENTS;
+        if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
         cudaError_t e = (mp.family == FMCMC_FAMILY_LOGISTIC)
                             ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC>(m, PB, lgrid, rb, tb)
                             : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM>(m, PB, lgrid, rb, tb);
         if (e != cudaSuccess) { set_err(err, errlen, "CUDA launch error %s (tiled_loglik)", cudaGetErrorString(e)); return FMCMC_ECUDA; }
+        if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed + 1], m->stream), hot_timed++;
         launches += 1;
       }
     }
@@ -571,7 +597,16 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   CU_CHECK(cudaStreamSynchronize(m->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, m->ev0, m->ev1);
+  double hot_ms = 0.0;
+  for (int q = 0; q < hot_timed; q++) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, m->hot_ev[2 * q], m->hot_ev[2 * q + 1]);
+    hot_ms += t;
+  }
+  d2h += (long long)sizeof(int) * 4 + 8;
   if (report) {
+    report->hot_ms = hot_ms;
+    report->hot_launches = hot_timed;
     report->device_ms = ms;
     report->n_accept = (int64_t)hacc;
     report->path = path;
@@ -600,6 +635,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   }
   m->state_nchains = C;
   m->state_k = k;
+  m->state_type = ks->type;
 
   const int gblocks = m->sm_count * 4;
   if (run->flags & FMCMC_RUN_APPEND) {
@@ -620,28 +656,35 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       CU_CHECK(ensure(m->out_ans, (size_t)C * keep * k * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
       CU_CHECK(cudaMemcpyAsync(ans_out, m->out_ans.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      d2h += (long long)C * keep * k * 8;
       launches += 1;
     }
     if (draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) {
       CU_CHECK(ensure(m->out_draws, (size_t)C * keep * k * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
       CU_CHECK(cudaMemcpyAsync(draws_out, m->out_draws.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      d2h += (long long)C * keep * k * 8;
       launches += 1;
     }
     if (logpost_out) {
       CU_CHECK(ensure(m->out_lp, (size_t)C * keep * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, run->burnin, run->thin, 0);
       CU_CHECK(cudaMemcpyAsync(logpost_out, m->out_lp.p, (size_t)C * keep * 8, cudaMemcpyDeviceToHost, m->stream));
+      d2h += (long long)C * keep * 8;
       launches += 1;
     }
   }
-  if (state && state->istate)
+  if (state && state->istate && !dev_state) {
     CU_CHECK(cudaMemcpyAsync(state->istate, m->istate.p, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyDeviceToHost, m->stream));
-  if (state && state->dstate && dlen)
+    d2h += (long long)C * FMCMC_ISTATE_LEN * 8;
+  }
+  if (state && state->dstate && dlen && !dev_state) {
     CU_CHECK(cudaMemcpyAsync(state->dstate, m->dstate.p, (size_t)C * dlen * 8, cudaMemcpyDeviceToHost, m->stream));
+    d2h += (long long)C * dlen * 8;
+  }
   CU_CHECK(cudaStreamSynchronize(m->stream));
   CU_CHECK(cudaGetLastError());
-  if (report) report->n_launches = launches;
+  if (report) { report->n_launches = launches; report->h2d_bytes = h2d; report->d2h_bytes = d2h; }
   return FMCMC_OK;
 }
 
@@ -956,5 +999,51 @@ extern "C" int fmcmc_reflect(int device, int32_t k, int64_t count, double* x, co
   cudaFree(d);
   cudaFree(dw);
   CU_CHECK(e);
+  return FMCMC_OK;
+}
+
+// --------------------------------------------------------------------------------
+// FP64 FMA peak (measurement helper for bench.py; SURVEY 8d: the binding roof)
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, double a, double b, int iters) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-9, x2 = x0 + 2e-9, x3 = x0 + 3e-9, x4 = x0 + 4e-9, x5 = x0 + 5e-9,
+         x6 = x0 + 6e-9, x7 = x0 + 7e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int fmcmc_measure_fp64_peak(int device, double* dfma_tflops, char* err, size_t errlen) {
+  if (!dfma_tflops) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(device));
+  int sms = 0;
+  CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double* d = nullptr;
+  CU_CHECK(cudaMalloc(&d, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  CU_CHECK(cudaEventCreate(&e0));
+  CU_CHECK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(d, 0.999999, 1e-7, iters);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(d); CU_CHECK(e); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *dfma_tflops = best;
   return FMCMC_OK;
 }

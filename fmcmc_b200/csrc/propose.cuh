@@ -247,8 +247,16 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
         double* m = cx.scr + kf;
         double* mp = cx.scr + 2 * kf;
         if (!(flags & FMCMC_STATE_HAS_MEAN)) {  // :130-131
-          const double* cs = rb.colsum + (size_t)cx.c * kf;
-          for (int a = lane; a < kf; a += FM_WARP) Mean_prev[a] = xdiv(cs[a], (double)(i - 1));
+          // colMeans(): R accumulates in long double; the running column sum is kept as a
+          // compensated (hi, lo) pair so the mean is the correctly rounded one as well
+          const double* cs = rb.colsum + (size_t)cx.c * 2 * kf;
+          const double nn = (double)(i - 1);
+          for (int a = lane; a < kf; a += FM_WARP) {
+            const double hi = cs[2 * a], lo = cs[2 * a + 1];
+            const double q = xdiv(hi, nn);
+            const double r = fma(-q, nn, hi);
+            Mean_prev[a] = xadd(q, xdiv(xadd(r, lo), nn));
+          }
           flags |= FMCMC_STATE_HAS_MEAN;
           __syncwarp();
         }
@@ -437,8 +445,15 @@ __device__ __forceinline__ double accept_row(const KParams& kp, const StreamPara
     f0 = f1;
     n_acc += 1;
   }
-  double* cs = rb.colsum + (size_t)c * kp.kf;
+  double* cs = rb.colsum + (size_t)c * 2 * kp.kf;
   for (int j = 0; j < k; j++) ans[j] = th0[j];
-  for (int a = 0; a < kp.kf; a++) cs[a] = xadd(cs[a], th0[kp.free_idx[a]]);
+  for (int a = 0; a < kp.kf; a++) {  // Neumaier two-sum: (hi, lo) += theta0
+    const double x = th0[kp.free_idx[a]], hi = cs[2 * a];
+    const double sum = xadd(hi, x);
+    const double bp = xsub(sum, hi);
+    const double e = xadd(xsub(hi, xsub(sum, bp)), xsub(x, bp));
+    cs[2 * a] = sum;
+    cs[2 * a + 1] = xadd(cs[2 * a + 1], e);
+  }
   return f0;
 }

@@ -115,7 +115,7 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
     const size_t off = (size_t)c;
     for (int j = 0; j < k; j++) { rb.ans[off * k + j] = th0[j]; rb.draws[off * k + j] = th0[j]; }
     rb.logpost[off] = f0;
-    for (int a = 0; a < kp.kf; a++) rb.colsum[(size_t)c * kp.kf + a] = th0[kp.free_idx[a]];
+    for (int a = 0; a < kp.kf; a++) { rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]]; rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0; }
     rb.istate[c * FMCMC_ISTATE_LEN + 3] = 0;
     rb.chain_flags[c] = 0;
   }

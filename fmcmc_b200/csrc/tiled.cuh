@@ -222,7 +222,7 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
       for (int j = 0; j < k; j++) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
       rb.logpost[c] = f1;
       rb.cur_f[c] = f1;
-      for (int a = 0; a < kp.kf; a++) rb.colsum[(size_t)c * kp.kf + a] = th0[kp.free_idx[a]];
+      for (int a = 0; a < kp.kf; a++) { rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]]; rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0; }
     }
   } else {
     double f0 = rb.cur_f[c];

@@ -199,6 +199,9 @@ typedef struct fmcmc_stream_spec {
 #define FMCMC_RUN_APPEND     4u /* append the kept rows to the handle's sample store
                                    (append_chains, R/mcmc.R:947) for fmcmc_gelman       */
 #define FMCMC_RUN_NO_OUTPUT  8u /* keep results on the device only (store / last state) */
+#define FMCMC_RUN_DEVICE_STATE 16u /* kernel state stays resident in HBM: `state` is neither
+                                   uploaded nor downloaded; the state the previous fmcmc_run left
+                                   on this model is used (bulk loop, R/mcmc.R:901-947)       */
 
 typedef struct fmcmc_run_spec {
   int64_t nsteps;        /* rows, including the initial state (R semantics)  */
@@ -222,6 +225,10 @@ typedef struct fmcmc_run_report {
   double  device_ms;     /* CUDA-event time of the stepping kernels          */
   int32_t path;          /* 1 = chain-resident fused kernel, 2 = observation-tiled */
   int32_t reserved;
+  double  hot_ms;        /* summed CUDA-event time of the dominant kernel's launches ... */
+  int64_t hot_launches;  /* ... and how many of them were timed (path 2: tiled_loglik)   */
+  int64_t h2d_bytes;     /* bytes this call copied host -> device                        */
+  int64_t d2h_bytes;     /* bytes this call copied device -> host                        */
 } fmcmc_run_report;
 
 typedef struct fmcmc_model fmcmc_model;   /* opaque: device-resident X, y, buffers */
@@ -308,6 +315,11 @@ int fmcmc_cov_recursive(int device, int32_t k, int64_t rows, const double* X,
 /* R/kernel.R:450-493 on `count` vectors of length k ([count][k]). */
 int fmcmc_reflect(int device, int32_t k, int64_t count, double* x, const double* lb,
                   const double* ub, const uint8_t* which, char* err, size_t errlen);
+
+/* ---- measurement helper (bench.py): FP64 FMA peak of the device ---------- */
+/* Times a register-resident DFMA loop on every SM; returns TFLOP/s (2 flop per FMA).
+ * MEASURED_PEAKS.json has no FP64 figure and the hot path is FP64-pipe bound. */
+int fmcmc_measure_fp64_peak(int device, double* dfma_tflops, char* err, size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -106,7 +106,7 @@ def test_errors(readme_data):
     with pytest.raises(ValueError, match="thin"):
         fm.MCMC([1, 1, 1], ll, 100, thin=100)
     with pytest.raises(fm.FmcmcError, match="undefined") as ei:      # sd < 0 -> dnorm NaN -> abort
-        fm.MCMC([1, 1, 0.05], ll, 200, seed=1, kernel=fm.kernel_normal(scale=1.0))
+        fm.MCMC([1, 1, 0.05], ll, 200, seed=1, kernel=fm.kernel_normal(mu=[0, 0, -1.0], scale=.01))
     assert ei.value.code == A.ENAN and "step i =" in str(ei.value)
     with pytest.raises(TypeError, match="closure"):
         fm.MCMC([1, 1, 1], lambda p: 0.0, 100)
@@ -130,7 +130,7 @@ def test_adaptive_kernels_reach_target(readme_data):
     for kern in (fm.kernel_adapt(lb=lb, warmup=300), fm.kernel_ram(lb=lb),
                  fm.kernel_nmirror(lb=lb, warmup=400, scale=.2), fm.kernel_umirror(lb=lb, warmup=400, scale=.2)):
         with pytest.warns(UserWarning):
-            ans = fm.MCMC([2, 1, 4.0], ll, 4000, nchains=8, burnin=2000, seed=11, kernel=kern)
+            ans = fm.MCMC([3, 2, 4.0], ll, 4000, nchains=8, burnin=2000, seed=11, kernel=kern)
         m = ans.as_array().mean(axis=(0, 1))
         assert np.linalg.norm(m[:2] - bhat) < 0.25, (kern.type, m)
         assert kern[0].abs_iter == 3999
