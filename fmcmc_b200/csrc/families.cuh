@@ -7,9 +7,10 @@
 // and a per-chain "finish" that turns the reduced sum(s) into f(theta).
 #pragma once
 #include "common.cuh"
+#include "softplus.h"
 
-// log(1 + exp(-a)), a >= 0
-__device__ __forceinline__ double softplus_neg(double a) { return log1p(exp(-a)); }
+// log(1 + exp(-a)), a >= 0: branch-free FP64 implementation (softplus.h), <= ~2 ulp
+__device__ __forceinline__ double softplus_neg(double a) { return fm_softplus_neg(a); }
 
 // Logistic term for one observation: y==1 -> logp, y==0 -> logq, else 0
 // (sum(logp[y == 1]) + sum(logq[y == 0]), workflow-with-fmcmc.Rmd:37-39).

@@ -574,7 +574,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     for (long long row = 1; row <= T + 1; row++) {
       tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row);
       launches += 1;
-      if (row <= T) {
+      if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
         cudaError_t e = (mp.family == FMCMC_FAMILY_LOGISTIC)
@@ -1045,5 +1045,23 @@ extern "C" int fmcmc_measure_fp64_peak(int device, double* dfma_tflops, char* er
   cudaEventDestroy(e1);
   cudaFree(d);
   *dfma_tflops = best;
+  return FMCMC_OK;
+}
+
+__global__ void softplus_test_kernel(const double* a, double* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = softplus_neg(a[i]);
+}
+extern "C" int fmcmc_test_softplus(int device, int64_t n, const double* a, double* out, char* err, size_t errlen) {
+  if (n < 1 || !a || !out) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(device));
+  double* d = nullptr;
+  CU_CHECK(cudaMalloc(&d, (size_t)n * 16));
+  cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice);
+  softplus_test_kernel<<<296, 256>>>(d, d + n, n);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU_CHECK(e);
   return FMCMC_OK;
 }

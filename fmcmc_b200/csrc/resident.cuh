@@ -109,7 +109,9 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
     for (int j = lane; j < k; j += FM_WARP) { th0[j] = src[j]; th1[j] = src[j]; th1u[j] = src[j]; }
   }
   group_sync<WPC>();
-  double f0 = loglik(th0);
+  // continuing from the device-resident state: f(theta0) is already known (same value the
+  // reference recomputes at R/mcmc.R:742), so the first likelihood pass is skipped
+  double f0 = initial ? loglik(th0) : rb.cur_f[c];
   unsigned long long n_acc = 0;
   if (leader_warp && lane == 0) {
     const size_t off = (size_t)c;

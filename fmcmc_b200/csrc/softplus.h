@@ -1,0 +1,116 @@
+// softplus.h — branch-free FP64 log(1 + exp(-a)), a >= 0, for the logistic family's epilogue.
+//
+// The logistic log-posterior (vignettes/workflow-with-fmcmc.Rmd:36-38) needs exactly one
+// exp and one log1p per chain-step x observation; with CUDA's libm versions (slow paths,
+// branches, ~110 non-FP64 instructions) they dominate the hot kernel (profiles/r01_v0_*).
+// This version is straight-line code so four evaluations interleave in the FP64 pipe:
+//   exp(-a) : n = rint(-a log2 e) (magic-number add), Cody-Waite reduction with fdlibm's
+//             ln2_hi/ln2_lo, degree-11 near-minimax polynomial (Chebyshev interpolant,
+//             rel. error 1.6e-17 on |r| <= ln2/2), scale by 2^n through the exponent bits;
+//   log1p(e): u = 1 + e with its exact rounding error c carried along, u folded into
+//             [sqrt(.5), sqrt(2)], s = f/(2+f) via reciprocal seed + one cubic Newton step,
+//             fdlibm e_log.c's degree-14 odd polynomial (Lg1..Lg7, error < 2^-58.45).
+// Host-compilable (plain C++) so tests/ can check it against mpmath on the CPU: max error
+// 1 ulp-ish (see tests/test_softplus_cpu.py); the device differs only in the reciprocal seed.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define FM_HD __host__ __device__ __forceinline__
+#else
+#define FM_HD static inline
+#endif
+
+FM_HD double fm_rcp_seed(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+#else
+  return (double)(1.0f / (float)x);
+#endif
+}
+
+FM_HD double fm_bits_to_double(int64_t b) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+FM_HD int64_t fm_double_to_bits(double d) {
+#ifdef __CUDA_ARCH__
+  return __double_as_longlong(d);
+#else
+  int64_t b;
+  memcpy(&b, &d, 8);
+  return b;
+#endif
+}
+
+// exp(-a) for a in [0, 708]
+FM_HD double fm_exp_neg(double a) {
+  const double x = -a;
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 1.4426950408889634074, MAGIC);
+  const double n = t - MAGIC;
+  double r = fma(n, -6.93147180369123816490e-01, x);
+  r = fma(n, -1.90821492927058770002e-10, r);
+  double p = 2.5110049204818658e-08;
+  p = fma(p, r, 2.763265472252779e-07);
+  p = fma(p, r, 2.755724088722987e-06);
+  p = fma(p, r, 2.4801485441561313e-05);
+  p = fma(p, r, 0.00019841269890076403);
+  p = fma(p, r, 0.0013888888952352863);
+  p = fma(p, r, 0.008333333333319589);
+  p = fma(p, r, 0.04166666666648795);
+  p = fma(p, r, 0.1666666666666668);
+  p = fma(p, r, 0.5000000000000019);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  // 2^n: the low word of t holds n (two's complement), n in [-1022, 0]
+  const int64_t ni = (int64_t)(int32_t)(uint32_t)fm_double_to_bits(t);
+  const double scale = fm_bits_to_double((ni + 1023) << 52);
+  return p * scale;
+}
+
+// log(1 + e) for e in [0, 1]
+FM_HD double fm_log1p_unit(double e) {
+  const double u = 1.0 + e;
+  const double c = e - (u - 1.0);  // exact: u + c == 1 + e
+  const bool big = u > 1.41421356237309504880;
+  const double m = big ? 0.5 * u : u;
+  const double kk = big ? 1.0 : 0.0;
+  const double f = m - 1.0;  // exact
+  const double d = 2.0 + f;
+  double rc = fm_rcp_seed(d);
+  double er = fma(-d, rc, 1.0);
+  rc = fma(rc, fma(er, er, er), rc);  // cubic step: rel. error ~ seed^3
+  er = fma(-d, rc, 1.0);
+  rc = fma(rc, er, rc);
+  const double s = f * rc;
+  const double z = s * s;
+  double R = 1.479819860511658591e-01;
+  R = fma(R, z, 1.531383769920937332e-01);
+  R = fma(R, z, 1.818357216161805012e-01);
+  R = fma(R, z, 2.222219843214978396e-01);
+  R = fma(R, z, 2.857142874366239149e-01);
+  R = fma(R, z, 3.999999999940941908e-01);
+  R = fma(R, z, 6.666666666666735130e-01);
+  R = R * z;
+  const double hfsq = 0.5 * f * f;
+  // log(m) = f - (hfsq - s (hfsq + R));  + kk ln2 (hi/lo) + c / u  (c/u ~= c: |c| <= 2^-53)
+  const double lo = fma(kk, 1.90821492927058770002e-10, c);
+  const double t = hfsq - fma(s, hfsq + R, lo);
+  return fma(kk, 6.93147180369123816490e-01, f - t);
+}
+
+// log(1 + exp(-a)), a >= 0
+FM_HD double fm_softplus_neg(double a) {
+  a = a < 708.0 ? a : 708.0;
+  return fm_log1p_unit(fm_exp_neg(a));
+}

@@ -215,8 +215,13 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
 
   // ---- finish row r = row - 1 -------------------------------------------------------
   const long long r = row - 1;
-  const double s = reduce_partials(tb, c, lane);
-  const double f1 = family_finish(mp, th1, s);
+  double f1;
+  if (r == 1 && !initial) {
+    f1 = rb.cur_f[c];  // continuing from the resident state: f(theta0) is known, no loglik launch was made
+  } else {
+    const double s = reduce_partials(tb, c, lane);
+    f1 = family_finish(mp, th1, s);
+  }
   if (r == 1) {
     if (lane == 0) {
       for (int j = 0; j < k; j++) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }

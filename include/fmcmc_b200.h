@@ -321,6 +321,10 @@ int fmcmc_reflect(int device, int32_t k, int64_t count, double* x, const double*
  * MEASURED_PEAKS.json has no FP64 figure and the hot path is FP64-pipe bound. */
 int fmcmc_measure_fp64_peak(int device, double* dfma_tflops, char* err, size_t errlen);
 
+/* Self-test hook: out[i] = log(1 + exp(-a[i])) evaluated by the device routine the logistic
+ * epilogue uses (csrc/softplus.h), so tests can bound its error against mpmath. */
+int fmcmc_test_softplus(int device, int64_t n, const double* a, double* out, char* err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,56 @@
+"""csrc/softplus.h (the logistic epilogue's branch-free log(1+exp(-a))) compiled for the HOST and checked
+against mpmath: the algorithm and its coefficients are validated without a GPU."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+mpmath = pytest.importorskip("mpmath")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ulp_err(got, a):
+    from mpmath import exp, log1p, mp, mpf
+    mp.dps = 60
+    out = []
+    for g, x in zip(got, a):
+        r = log1p(exp(-mpf(float(x))))
+        u = np.spacing(abs(float(r)))
+        out.append(abs(float((mpf(float(g)) - r) / mpf(float(u)))))
+    return np.array(out)
+
+
+def sample_points(rng):
+    return np.concatenate([rng.uniform(0, 40, 4000), rng.uniform(0, 2, 4000), 10 ** rng.uniform(-300, 2.8, 1500),
+                           [0.0, 708.0, 1e-17, 36.7, 37.0, 0.34657, 0.34658, 745.0, 1e300]])
+
+
+def test_softplus_host_build_vs_mpmath():
+    src = '#include "%s/fmcmc_b200/csrc/softplus.h"\n' % ROOT + \
+          'extern "C" void sp_eval(const double* a, double* o, long n) { for (long i = 0; i < n; i++) o[i] = fm_softplus_neg(a[i]); }\n'
+    with tempfile.TemporaryDirectory() as td:
+        cpp, so = os.path.join(td, "sp.cpp"), os.path.join(td, "libsp.so")
+        open(cpp, "w").write(src)
+        subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
+        L = C.CDLL(so)
+        a = sample_points(np.random.default_rng(0))
+        o = np.empty_like(a)
+        L.sp_eval(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_long(a.size))
+    e = ulp_err(o, np.minimum(a, 708.0))
+    assert e.max() < 2.5 and e.mean() < 0.6, (e.max(), e.mean())
+
+
+@pytest.mark.gpu
+def test_softplus_device_vs_mpmath():
+    import fmcmc_b200 as fm
+    a = sample_points(np.random.default_rng(1))
+    o = np.empty_like(a)
+    err = C.create_string_buffer(256)
+    dp = C.POINTER(C.c_double)
+    rc = fm.lib().fmcmc_test_softplus(0, a.size, a.ctypes.data_as(dp), o.ctypes.data_as(dp), err, 256)
+    assert rc == 0, err.value
+    e = ulp_err(o, np.minimum(a, 708.0))
+    assert e.max() < 2.5 and e.mean() < 0.6, (e.max(), e.mean())
