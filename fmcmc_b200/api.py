@@ -134,10 +134,23 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
     if not isinstance(kernel, FmcmcKernel):
         raise TypeError("`kernel` must be an fmcmc_kernel built by one of the kernel_*() constructors.")
     nsteps, burnin, thin, nchains = int(nsteps), int(burnin), int(thin), int(nchains)
+    if nchains < 1:                                             # R/mcmc.R:508-520
+        raise ValueError("`nchains` must be an integer greater than 1.")
+    if burnin >= nsteps:
+        raise ValueError(f"-burnin- ({burnin}) cannot be >= than -nsteps- ({nsteps}).")
+    if thin >= nsteps:
+        raise ValueError(f"-thin- ({thin}) cannot be > than -nsteps- ({nsteps}).")
+    if thin < 1:
+        raise ValueError("-thin- should be >= 1.")
+    if conv_checker is not None and isinstance(conv_checker, GelmanChecker) and nchains < 2:
+        raise ValueError("Convergence test with the Gelman is only available when `nchains` > 1L.")
 
     sharding = current_sharding(nchains)
     nlocal = sharding.local if sharding else nchains
     init_all, names = check_initial(initial, nchains)
+    if init_all.shape[1] != fun.k:
+        raise ValueError(f"Incorrect length of -initial-: the family has {fun.k} parameters, got {init_all.shape[1]}.")
+    kernel.to_spec(fun.k) if not kernel.is_list else None       # validates the kernel before touching the GPU
     init_local = init_all[sharding.offset:sharding.offset + nlocal] if sharding else init_all
     if device is None:
         device = sharding.device.index if (sharding and sharding.on_cuda) else 0

@@ -41,6 +41,7 @@ struct ModelParams {
   long long n;     // observations
   long long ld;    // leading dimension of X (>= n, even)
   int p_x, n_groups, k;
+  int y_binary;    // logistic: every y is exactly +0.0 or 1.0 (fast epilogue)
   const double* X;  // [p_x][ld]
   const double* y;  // [ld]
   const int* group; // [ld]

@@ -21,6 +21,17 @@ __device__ __forceinline__ double logistic_term(double eta, double y) {
   return (y == 1.0) ? v1 : ((y == 0.0) ? v0 : 0.0);
 }
 
+// Same term when y is known to be exactly +0.0 or 1.0 (ModelParams::y_binary): with z = +-eta,
+// term = min(z, 0) - log(1 + exp(-|z|)).  Sign flip, min and the y test are integer operations on the
+// high word (ALU pipe); the FP64 pipe only runs the softplus and one subtraction.
+__device__ __forceinline__ double logistic_term_binary(double eta, double y) {
+  const long long flip = (fm_hi_word(y) == 0) ? (long long)0x8000000000000000ULL : 0LL;  // y == 0 -> z = -eta
+  const double z = fm_bits_to_double(fm_double_to_bits(eta) ^ flip);
+  const double t = softplus_neg(fabs(eta));
+  const double zmin = (fm_hi_word(z) < 0) ? z : 0.0;
+  return zmin - t;
+}
+
 // sum_i dnorm(r_i, 0, sd, log=TRUE) from ss = sum r_i^2 with R's dnorm edge cases
 // (nmath/dnorm.c): sd<0 -> NaN, sd==0 -> +-Inf, !finite(sd) -> -Inf.
 __device__ __forceinline__ double gauss_sum_from_ss(double ss, double n, double sd) {
@@ -56,6 +67,7 @@ __device__ __forceinline__ double family_finish(const ModelParams& mp, const dou
     case FMCMC_FAMILY_LOGISTIC: {
       double b2 = 0.0;
       for (int j = 0; j < mp.k; j++) b2 = fma(th[j], th[j], b2);
+      if (isnan(b2)) return NAN;  // a NaN parameter makes x %*% beta NaN for every observation
       return s - b2 / (2.0 * mp.h0 * mp.h0);  // - sum(beta^2)/8 for prior sd 2
     }
     case FMCMC_FAMILY_HIER_NORMAL: {

@@ -190,6 +190,22 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
         return FMCMC_EINVAL;
       }
   }
+  if (d->family == FMCMC_FAMILY_LOGISTIC) {  // enables the integer-select epilogue (logistic_term_binary)
+    std::vector<double> hy;
+    const double* yh = d->y;
+    if (device_ptrs) {
+      hy.resize((size_t)n);
+      MC(cudaMemcpy(hy.data(), d->y, (size_t)n * 8, cudaMemcpyDeviceToHost));
+      yh = hy.data();
+    }
+    int bin = 1;
+    for (long long i = 0; i < n && bin; i++) {
+      int64_t bits;
+      memcpy(&bits, &yh[i], 8);
+      bin = (bits == 0 || bits == 0x3FF0000000000000LL);
+    }
+    mp.y_binary = bin;
+  }
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
 #undef MC
@@ -336,20 +352,20 @@ struct Blob {  // host staging of the small kernel-spec arrays -> one H2D copy
   }
 };
 
-template <int FAMILY>
+template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
   const size_t smem = tiled_smem_bytes(PB);
 #define TL_CASE(P)                                                                                               \
   case P: {                                                                                                      \
     static bool attr_done[64] = {};                                                                              \
     if (!attr_done[m->device]) {                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_kernel<FAMILY, P>,                                        \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_kernel<FAMILY, P, YBIN>,                                     \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
       attr_done[m->device] = true;                                                                               \
     }                                                                                                            \
-    tiled_loglik_kernel<FAMILY, P><<<grid, TL_THREADS, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, rb.nchains, \
-                                                                           tb, rb.err);                          \
+    tiled_loglik_kernel<FAMILY, P, YBIN><<<grid, TL_THREADS, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u,       \
+                                                                                 rb.nchains, tb, rb.err);        \
     break;                                                                                                       \
   }
   switch (PB) {
@@ -578,8 +594,9 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         const bool timed = hot_timed < FM_HOT_EVENTS;
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
         cudaError_t e = (mp.family == FMCMC_FAMILY_LOGISTIC)
-                            ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC>(m, PB, lgrid, rb, tb)
-                            : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM>(m, PB, lgrid, rb, tb);
+                            ? (mp.y_binary ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, true>(m, PB, lgrid, rb, tb)
+                                           : launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, false>(m, PB, lgrid, rb, tb))
+                            : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, PB, lgrid, rb, tb);
         if (e != cudaSuccess) { set_err(err, errlen, "CUDA launch error %s (tiled_loglik)", cudaGetErrorString(e)); return FMCMC_ECUDA; }
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed + 1], m->stream), hot_timed++;
         launches += 1;

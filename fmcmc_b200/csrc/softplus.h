@@ -73,25 +73,37 @@ FM_HD double fm_exp_neg(double a) {
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   // 2^n: the low word of t holds n (two's complement), n in [-1022, 0]
-  const int64_t ni = (int64_t)(int32_t)(uint32_t)fm_double_to_bits(t);
+  const int64_t ni = (int64_t)(int32_t)(uint32_t)fm_double_to_bits(t);  // NaN in -> garbage scale, but p is NaN
   const double scale = fm_bits_to_double((ni + 1023) << 52);
   return p * scale;
 }
 
-// log(1 + e) for e in [0, 1]
+FM_HD int32_t fm_hi_word(double d) { return (int32_t)(fm_double_to_bits(d) >> 32); }
+FM_HD double fm_add_hi_word(double d, int32_t delta) {
+  return fm_bits_to_double(fm_double_to_bits(d) + ((int64_t)delta << 32));
+}
+
+#ifndef FM_RCP_EXTRA_STEP
+#define FM_RCP_EXTRA_STEP 0  // the reciprocal seed (>= 2^-20 accurate) + one cubic step is already < 2^-58
+#endif
+
+// log(1 + e) for e in [0, 1].  All selections are integer tests on the high word (ALU pipe), so the
+// FP64 pipe only sees the arithmetic: 25 FP64 instructions.
 FM_HD double fm_log1p_unit(double e) {
   const double u = 1.0 + e;
   const double c = e - (u - 1.0);  // exact: u + c == 1 + e
-  const bool big = u > 1.41421356237309504880;
-  const double m = big ? 0.5 * u : u;
-  const double kk = big ? 1.0 : 0.0;
+  // fold u in [1,2] into m in [sqrt(.5), sqrt(2)) like fdlibm e_log.c: test the high word against sqrt(2)
+  const bool big = fm_hi_word(u) > 0x3FF6A09E;
+  const double m = fm_add_hi_word(u, big ? -0x00100000 : 0);  // m = big ? u/2 : u (exact)
   const double f = m - 1.0;  // exact
   const double d = 2.0 + f;
   double rc = fm_rcp_seed(d);
   double er = fma(-d, rc, 1.0);
   rc = fma(rc, fma(er, er, er), rc);  // cubic step: rel. error ~ seed^3
+#if FM_RCP_EXTRA_STEP
   er = fma(-d, rc, 1.0);
   rc = fma(rc, er, rc);
+#endif
   const double s = f * rc;
   const double z = s * s;
   double R = 1.479819860511658591e-01;
@@ -102,15 +114,19 @@ FM_HD double fm_log1p_unit(double e) {
   R = fma(R, z, 3.999999999940941908e-01);
   R = fma(R, z, 6.666666666666735130e-01);
   R = R * z;
-  const double hfsq = 0.5 * f * f;
-  // log(m) = f - (hfsq - s (hfsq + R));  + kk ln2 (hi/lo) + c / u  (c/u ~= c: |c| <= 2^-53)
-  const double lo = fma(kk, 1.90821492927058770002e-10, c);
-  const double t = hfsq - fma(s, hfsq + R, lo);
-  return fma(kk, 6.93147180369123816490e-01, f - t);
+  // log(m) = f - (hfsq - s (hfsq + R)), hfsq = f^2 / 2;  + [big] ln2 (hi/lo) + c / u  (c/u ~= c: |c| <= 2^-53)
+  const double q = f * f;
+  const double A = fma(0.5, q, R);
+  const double lo = c + (big ? 1.90821492927058770002e-10 : 0.0);
+  const double B = fma(s, A, lo);
+  const double t = fma(0.5, q, -B);
+  return (f - t) + (big ? 6.93147180369123816490e-01 : 0.0);
 }
 
-// log(1 + exp(-a)), a >= 0
+// log(1 + exp(-a)), a >= 0 (NaN is passed through: the clamp is an integer test that NaN fails)
 FM_HD double fm_softplus_neg(double a) {
-  a = a < 708.0 ? a : 708.0;
+  const bool over = fm_hi_word(a) >= 0x40862000 && fm_hi_word(a) < 0x7FF00000;  // a >= 708 and finite/inf
+  a = (fm_hi_word(a) >= 0x7FF00000 && !(a != a)) ? 708.0 : a;                  // +inf
+  a = over ? 708.0 : a;
   return fm_log1p_unit(fm_exp_neg(a));
 }

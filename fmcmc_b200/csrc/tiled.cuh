@@ -1,7 +1,6 @@
 // tiled.cuh — observation-tiled stepping path (path 2) for large n.
 //
-// Per MH row two kernels run back to back on one stream (optionally replayed from a
-// CUDA graph):
+// Per MH row two kernels run back to back on one stream:
 //   tiled_head    one warp per chain: finishes row i-1 (fixed-order reduction of the
 //                 per-CTA partial sums -> f(theta1) -> RAM phase B -> accept/reject ->
 //                 ans/draws/logpost rows) and proposes row i (propose_warp).
@@ -14,6 +13,8 @@
 //                 the chain's partial log-likelihood privately -> no cross-lane
 //                 reduction, no atomics, deterministic.  X is read from HBM once per
 //                 row per chain block and shared by all 512 chains of the CTA.
+//                 TL_RO observations x 2 chains = 2*TL_RO independent evaluations are in
+//                 flight per thread so the FP64 pipe (the binding roof) stays fed.
 #pragma once
 #include "families.cuh"
 #include "propose.cuh"
@@ -24,6 +25,9 @@
 #define TL_TILE 128
 #define TL_STAGES 4
 #define TL_HEAD_WARPS 4
+#ifndef TL_RO
+#define TL_RO 4
+#endif
 
 struct TiledBuffers {
   double* partial;  // [gx][ncols]
@@ -35,24 +39,16 @@ __host__ __device__ inline size_t tiled_smem_bytes(int PB) {
   return 128 + (size_t)TL_STAGES * ((size_t)PB * TL_TILE + TL_TILE) * sizeof(double);
 }
 
-template <int FAMILY>
-__device__ __forceinline__ void tile_epilogue(double e00, double e01, double e10, double e11, double y0, double y1,
-                                              double& acc0, double& acc1) {
-  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
-    acc0 += logistic_term(e00, y0);
-    acc1 += logistic_term(e01, y0);
-    acc0 += logistic_term(e10, y1);
-    acc1 += logistic_term(e11, y1);
-  } else {  // Gaussian LM: e already holds the linear predictor incl. intercept
-    const double r00 = y0 - e00, r01 = y0 - e01, r10 = y1 - e10, r11 = y1 - e11;
-    acc0 = fma(r00, r00, acc0);
-    acc1 = fma(r01, r01, acc1);
-    acc0 = fma(r10, r10, acc0);
-    acc1 = fma(r11, r11, acc1);
-  }
+// One observation, one chain: per-observation term of the family.
+//   FAMILY logistic, YBIN: y is known to be exactly 0.0 or 1.0 (checked at model creation)
+template <int FAMILY, bool YBIN>
+__device__ __forceinline__ double tile_term(double e, double y) {
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) return YBIN ? logistic_term_binary(e, y) : logistic_term(e, y);
+  const double r = y - e;  // Gaussian LM: e already holds the linear predictor incl. intercept
+  return r * r;
 }
 
-template <int FAMILY, int PB>
+template <int FAMILY, int PB, bool YBIN>
 __global__ void __launch_bounds__(TL_THREADS, 1)
 tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
                     TiledBuffers tb, const int* __restrict__ err) {
@@ -61,7 +57,7 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
   uint64_t* empty = full + TL_STAGES;
   double* stage0 = reinterpret_cast<double*>(smem_raw + 128);
   constexpr int STAGE_DOUBLES = PB * TL_TILE + TL_TILE;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (err[0] != 0) return;
 
   const long long ntiles = (mp.ld + TL_TILE - 1) / TL_TILE;
@@ -134,18 +130,29 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
     const int valid = (int)min((long long)TL_TILE, mp.n - row0);  // < TL_TILE only for the last tile
     if (valid == TL_TILE) {
 #pragma unroll 1
-      for (int o = 0; o < TL_TILE; o += 2) {
-        double e00 = b00, e01 = b01, e10 = b00, e11 = b01;
+      for (int o = 0; o < TL_TILE; o += TL_RO) {
+        double e0[TL_RO], e1[TL_RO];
+#pragma unroll
+        for (int q = 0; q < TL_RO; q++) { e0[q] = b00; e1[q] = b01; }
 #pragma unroll
         for (int j = 0; j < PB; j++) {
-          const double2 x = *reinterpret_cast<const double2*>(Xs + j * TL_TILE + o);  // warp-wide broadcast
-          e00 = fma(x.x, th0[j], e00);
-          e01 = fma(x.x, th1[j], e01);
-          e10 = fma(x.y, th0[j], e10);
-          e11 = fma(x.y, th1[j], e11);
+#pragma unroll
+          for (int q = 0; q < TL_RO; q += 2) {
+            const double2 x = *reinterpret_cast<const double2*>(Xs + j * TL_TILE + o + q);  // warp-wide broadcast
+            e0[q] = fma(x.x, th0[j], e0[q]);
+            e1[q] = fma(x.x, th1[j], e1[q]);
+            e0[q + 1] = fma(x.y, th0[j], e0[q + 1]);
+            e1[q + 1] = fma(x.y, th1[j], e1[q + 1]);
+          }
         }
-        const double2 yy = *reinterpret_cast<const double2*>(ys + o);
-        tile_epilogue<FAMILY>(e00, e01, e10, e11, yy.x, yy.y, acc0, acc1);
+#pragma unroll
+        for (int q = 0; q < TL_RO; q += 2) {
+          const double2 yy = *reinterpret_cast<const double2*>(ys + o + q);
+          acc0 += tile_term<FAMILY, YBIN>(e0[q], yy.x);
+          acc1 += tile_term<FAMILY, YBIN>(e1[q], yy.x);
+          acc0 += tile_term<FAMILY, YBIN>(e0[q + 1], yy.y);
+          acc1 += tile_term<FAMILY, YBIN>(e1[q + 1], yy.y);
+        }
       }
     } else {
       for (int o = 0; o < valid; o++) {
@@ -157,20 +164,13 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
           e1 = fma(x, th1[j], e1);
         }
         const double yv = ys[o];
-        if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
-          acc0 += logistic_term(e0, yv);
-          acc1 += logistic_term(e1, yv);
-        } else {
-          const double r0 = yv - e0, r1 = yv - e1;
-          acc0 = fma(r0, r0, acc0);
-          acc1 = fma(r1, r1, acc1);
-        }
+        acc0 += tile_term<FAMILY, false>(e0, yv);
+        acc1 += tile_term<FAMILY, false>(e1, yv);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
-  (void)warp;
   if (col0 < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col0] = acc0;
   if (col1 < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col1] = acc1;
 }
@@ -227,7 +227,10 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
       for (int j = 0; j < k; j++) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
       rb.logpost[c] = f1;
       rb.cur_f[c] = f1;
-      for (int a = 0; a < kp.kf; a++) { rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]]; rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0; }
+      for (int a = 0; a < kp.kf; a++) {
+        rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]];
+        rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0;
+      }
     }
   } else {
     double f0 = rb.cur_f[c];

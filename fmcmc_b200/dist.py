@@ -50,9 +50,13 @@ class ChainSharding:
             out = torch.empty((self.total, t.shape[1]), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t.contiguous())
             return out
-        parts = [torch.empty((n, t.shape[1]), dtype=t.dtype, device=t.device) for n in self.counts]
-        dist.all_gather(parts, t.contiguous())
-        return torch.cat(parts, dim=0)
+        # uneven shards: pad every block to the largest one (collectives need equal sizes), then trim
+        mx = max(self.counts)
+        pad = torch.zeros((mx, t.shape[1]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = torch.empty((self.world * mx, t.shape[1]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad)
+        return torch.cat([out[r * mx:r * mx + n] for r, n in enumerate(self.counts)], dim=0)
 
 
 def current_sharding(nchains_total: int):

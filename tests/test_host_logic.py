@@ -1,0 +1,149 @@
+"""Host-side mirror of the reference interface (no GPU): argument checks with the reference's error
+strings, append_chains / mcpar bookkeeping, coda's window rule, kernel constructors."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+import fmcmc_b200 as fm
+from fmcmc_b200 import _abi as A
+from fmcmc_b200.coda import Mcmc, McmcList, append_chains, window_first_row
+from fmcmc_b200.kernels import _nadapt_schedule
+
+
+def fam3():
+    return fm.ll_gaussian_lm(np.arange(6.0), np.arange(6.0))
+
+
+def test_check_initial():
+    """inst/tinytest/test-checks.R:31-41, R/checks.R:22-58"""
+    with pytest.warns(UserWarning, match="single initial point"):
+        a, names = fm.check_initial([1, 2, 3], 2)
+    assert a.shape == (2, 3) and names == ["par1", "par2", "par3"]
+    a, names = fm.check_initial({"a": 1.0, "b": 2.0}, 1)
+    assert names == ["a", "b"]
+    with pytest.raises(ValueError, match="must coincide with the number of chains"):
+        fm.check_initial(np.zeros((3, 2)), 2)
+    with pytest.raises(ValueError, match="length zero"):
+        fm.check_initial([], 1)
+    m = Mcmc(np.arange(12.0).reshape(4, 3), start=1, thin=1)
+    a, _ = fm.check_initial(m, 1)
+    assert np.array_equal(a, [[9, 10, 11]])
+
+
+def test_mcmc_argument_errors_before_the_gpu_is_touched():
+    """inst/tinytest/test-mcmc.R:4-24, test-kernels.R:14-86, test-convergence.R:57-67"""
+    f = fam3()
+    with pytest.raises(ValueError, match="burnin"):
+        fm.MCMC([1, 1, 1], f, 100, burnin=100)
+    with pytest.raises(ValueError, match="thin"):
+        fm.MCMC([1, 1, 1], f, 100, thin=100)
+    with pytest.raises(ValueError, match="should be >= 1"):
+        fm.MCMC([1, 1, 1], f, 100, thin=0)
+    with pytest.raises(TypeError, match="closure"):
+        fm.MCMC([1, 1, 1], lambda p: 0.0, 100)
+    with pytest.raises(TypeError, match="not present in -fun-"):
+        fm.MCMC([1, 1, 1], f, 100, D=3)
+    with pytest.raises(ValueError, match="multicore"):
+        fm.MCMC([1, 1, 1], f, 100, multicore=True)
+    with pytest.raises(ValueError, match="-ub- cannot be <= than -lb-."):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal_reflective(lb=1.0, ub=0.0))
+    with pytest.raises(ValueError, match="-max.- cannot be <= than -min.-."):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_unif(min_=1.0, max_=0.0))
+    with pytest.raises(ValueError, match="cannot be zero"):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal(fixed=True))
+    with pytest.raises(ValueError, match="Incorrect length of -scale-"):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal(scale=[1, 2]))
+    with pytest.raises(ValueError, match="either an integer"):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal(scheme="bogus"))
+    with pytest.raises(ValueError, match="same length as"):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal(scheme=[1, 2]))
+    with pytest.raises(ValueError, match="not included in"):
+        fm.MCMC([1, 1, 1], f, 100, kernel=fm.kernel_normal(scheme=[1, 2, 2]))
+    with pytest.raises(ValueError, match="only available when `nchains` > 1L"):
+        fm.MCMC([1, 1, 1], f, 100, conv_checker=fm.convergence_gelman(10))
+    with pytest.raises(ValueError, match="must equal the number of chains"):
+        fm.MCMC(McmcList([Mcmc(np.zeros((3, 3)))] * 2), f, 100, nchains=3)
+    with pytest.raises(ValueError, match="must be greater than `bw`"):
+        fm.kernel_adapt(bw=600, warmup=500)
+    with pytest.raises(TypeError, match="closures cannot run on the device"):
+        fm.kernel_new(lambda env: env)
+    with pytest.raises(TypeError, match="qfun"):
+        fm.kernel_ram(qfun=lambda k: np.zeros(k))
+    with pytest.raises(RuntimeError, match="CUDA kernel"):
+        fm.ith_step()
+
+
+def test_kernel_defaults_match_reference():
+    """Defaults of R/kernel_*.R constructors."""
+    k = fm.kernel_adapt()
+    assert (k.warmup, k.freq, k.eps, k.bw, k.until) == (500, 1, 1e-4, 0, math.inf)
+    k = fm.kernel_ram()
+    assert (k.arate, k.freq, k.warmup, k.eps) == (0.234, 1, 0, 1e-4)
+    k = fm.kernel_nmirror()
+    assert (k.warmup, k.nadapt, k.arate) == (500, 4, 0.4)
+    assert list(k.nadapt_schedule) == [125, 250, 375, 500]            # R/kernel_mirror.R:165
+    assert list(_nadapt_schedule(1000, 5)) == [200, 400, 600, 800, 1000]
+    s = fm.kernel_unif_reflective(min_=-2.0, max_=3.0).to_spec(2)
+    assert np.array_equal(s["lb"], [-2, -2]) and np.array_equal(s["ub"], [3, 3])   # lb = min., ub = max.
+    s = fm.kernel_normal_reflective(lb=[np.nan, 0.0], ub=np.nan).to_spec(2)        # process_bounds, R/kernel.R:25-41
+    assert s["lb"][0] == -A.DBL_MAX and s["ub"][1] == A.DBL_MAX
+    s = fm.kernel_normal(scheme=[2, 1]).to_spec(2)
+    assert s["scheme"] == A.SCHEME_EXPLICIT and list(s["order"]) == [2, 1]
+
+
+def test_append_chains_mcpar():
+    """inst/tinytest/test-append_chains.R:19-60 and R/append_chains.R:113-142"""
+    a = Mcmc(np.zeros((100, 2)), start=1, end=100, thin=1)
+    b = Mcmc(np.ones((50, 2)), start=1, end=50, thin=1)
+    ab = append_chains(a, b)
+    assert ab.mcpar == (1, 150, 1) and ab.niter() == 150
+    t1 = Mcmc(np.zeros((10, 2)), start=110, end=200, thin=10)      # burnin 100, thin 10, nsteps 200
+    t2 = Mcmc(np.zeros((20, 2)), start=10, end=200, thin=10)
+    t12 = append_chains(t1, t2)
+    assert t12.mcpar == (110, 400, 10) and t12.niter() == 30
+    assert list(t12.iterations()[:2]) == [110, 120] and t12.iterations()[-1] == 400
+    l = append_chains(McmcList([a, a]), McmcList([b, b]))
+    assert isinstance(l, McmcList) and l.nchain() == 2 and l.mcpar == (1, 150, 1)
+    with pytest.raises(ValueError, match="same number of chains"):
+        append_chains(McmcList([a, a]), McmcList([b]))
+    with pytest.raises(ValueError, match="same `thin`"):
+        append_chains(a, t1)
+    with pytest.raises(ValueError, match="same number of parameters"):
+        append_chains(a, Mcmc(np.zeros((5, 3))))
+
+
+def test_coda_window_rule():
+    """gelman.diag's autoburnin: window(x, start = end/2 + 1); off-grid starts snap UP."""
+    assert window_first_row(1, 200, 1, 200, 200 / 2 + 1) == 100
+    assert window_first_row(1, 400, 1, 400, 201) == 200
+    assert window_first_row(1, 201, 1, 201, 201 / 2 + 1) == 101          # 101.5 -> iteration 102
+    assert window_first_row(10, 2000, 10, 200, 1001) == 100              # 1001 -> iteration 1010
+    assert window_first_row(110, 400, 10, 30, 201) == 10                 # -> iteration 210
+
+
+def test_rows_kept_and_labels():
+    """R/mcmc.R:786-813: post-burnin POSITIONS with pos %% thin == 0 are kept (quirk D3)."""
+    for nsteps, burnin, thin in [(10, 0, 1), (500, 100, 7), (1000, 0, 10), (11, 10, 1), (20, 3, 4)]:
+        rows = np.arange(1, nsteps + 1)[burnin:]
+        kept = rows[(np.arange(1, len(rows) + 1) % thin) == 0]
+        assert A.rows_kept(nsteps, burnin, thin) == len(kept)
+        if len(kept):
+            assert kept[0] == burnin + thin and kept[-1] == burnin + len(kept) * thin
+
+
+def test_kernel_list_semantics():
+    """rep_kernel turns the user's object into a list in place (R/kernel.R:348-377, R/mcmc.R:526-527)."""
+    k = fm.kernel_adapt()
+    assert not k.is_list and len(k) == 1
+    k.to_spec(3)
+    k._replicate(4)
+    assert k.is_list and len(k) == 4 and k[2].type == A.KERNEL_ADAPT and k[2] is not k[1]
+    ist, dst = k.state_arrays(4, 3)
+    assert ist.shape == (4, A.ISTATE_LEN) and dst.shape == (4, 12)
+    ist[:, 0] = 7
+    ist[:, 1] = A.STATE_INIT
+    dst[1, :9] = np.eye(3).reshape(-1)
+    k.absorb_state(3)
+    assert k[1].abs_iter == 7 and np.array_equal(k[1].Sigma, np.eye(3)) and k[1].Mean_t_prev is None
