@@ -63,7 +63,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -155,7 +155,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
@@ -330,7 +330,9 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            chains_s, rows_s = 2 * threads, 4
+            chains_s = 2 * threads
+            probe = cpu_port_run(X, y, chains_s, 3, threads)                   # 2 MH steps: sizes the sample
+            rows_s = 1 + max(2, int(round(15.0 / max(probe / 2.0, 1e-3))))     # ~15 s of CPU work
             sec = cpu_port_run(X, y, chains_s, rows_s, threads)
             line["cpu_baseline"] = {"value": chains_s * (rows_s - 1) / sec, "unit": "chain-steps/s", "cores": threads,
                                     "kind": "port",

@@ -46,6 +46,7 @@ struct ModelParams {
   const double* y;  // [ld]
   const int* group; // [ld]
   double h0, h1;
+  const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
 };
 
 // Per-run device buffers shared by both paths.

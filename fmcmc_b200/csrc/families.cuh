@@ -12,24 +12,52 @@
 // log(1 + exp(-a)), a >= 0: branch-free FP64 implementation (softplus.h), <= ~2 ulp
 __device__ __forceinline__ double softplus_neg(double a) { return fm_softplus_neg(a); }
 
-// Logistic term for one observation: y==1 -> logp, y==0 -> logq, else 0
-// (sum(logp[y == 1]) + sum(logq[y == 0]), workflow-with-fmcmc.Rmd:37-39).
-__device__ __forceinline__ double logistic_term(double eta, double y) {
-  const double t = softplus_neg(fabs(eta));
-  const double v1 = fmin(eta, 0.0) - t;   // eta<0: eta - log1p(exp(eta));  else -log1p(exp(-eta))
-  const double v0 = -fmax(eta, 0.0) - t;  // eta<0: -log1p(exp(eta));       else -eta - log1p(exp(-eta))
-  return (y == 1.0) ? v1 : ((y == 0.0) ? v0 : 0.0);
+// min(z, 0) with NaN passed through, as one integer test on the high word: true for every negative
+// number (sign bit set, incl. -0 and -inf) and for the default quiet NaNs of either sign.
+__device__ __forceinline__ double fm_min0(double z) {
+  return ((uint32_t)fm_hi_word(z) > 0x7FF00000u) ? z : 0.0;
 }
 
-// Same term when y is known to be exactly +0.0 or 1.0 (ModelParams::y_binary): with z = +-eta,
-// term = min(z, 0) - log(1 + exp(-|z|)).  Sign flip, min and the y test are integer operations on the
-// high word (ALU pipe); the FP64 pipe only runs the softplus and one subtraction.
+// Logistic term for one observation: y==1 -> logp, y==0 -> logq, else 0
+// (sum(logp[y == 1]) + sum(logq[y == 0]), workflow-with-fmcmc.Rmd:37-39).  With z = eta (y == 1) or
+// -eta (y == 0): eta<0 ? eta - log1p(exp(eta)) : -log1p(exp(-eta))  ==  min(z, 0) - log1p(exp(-|z|)).
+__device__ __forceinline__ double logistic_term(double eta, double y) {
+  const double t = softplus_neg(fabs(eta));
+  const double z = (y == 1.0) ? eta : -eta;
+  const double v = fm_min0(z) - t;
+  return (y == 1.0 || y == 0.0) ? v : 0.0;
+}
+
+// Same term when y is known to be exactly +0.0 or 1.0 (ModelParams::y_binary).  Sign flip, min and the
+// y test are integer operations on the high word (ALU pipe); the FP64 pipe only runs the softplus and
+// one subtraction.
 __device__ __forceinline__ double logistic_term_binary(double eta, double y) {
   const long long flip = (fm_hi_word(y) == 0) ? (long long)0x8000000000000000ULL : 0LL;  // y == 0 -> z = -eta
   const double z = fm_bits_to_double(fm_double_to_bits(eta) ^ flip);
   const double t = softplus_neg(fabs(eta));
-  const double zmin = (fm_hi_word(z) < 0) ? z : 0.0;
-  return zmin - t;
+  return fm_min0(z) - t;
+}
+
+// Table-driven variant for the observation-tiled kernel (softplus.h, fm_softplus_tab_core): `tab` is
+// the CTA's shared-memory copy of the (S_k, G_k) table, 16 B per entry -> one LDS.128.
+template <bool YBIN>
+__device__ __forceinline__ double logistic_term_tab(double eta, double y, const double2* __restrict__ tab) {
+  double a = fabs(eta);
+  a = (fm_hi_word(a) >= 0x40500000) ? (double)FM_SP_AMAX : a;  // >= 64, inf, NaN -> 64 (NaN re-enters via fm_min0)
+  const double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52: low word of t = round(32 a)
+  const double t = fma(a, (double)FM_SP_H, MAGIC);
+  const int k = (int)(uint32_t)fm_double_to_bits(t);
+  const double d = fma(t - MAGIC, -1.0 / FM_SP_H, a);            // exact
+  const double2 sg = tab[k];
+  const double g = fm_softplus_tab_core(d, sg.x, sg.y);
+  if (YBIN) {
+    const long long flip = (fm_hi_word(y) == 0) ? (long long)0x8000000000000000ULL : 0LL;
+    const double z = fm_bits_to_double(fm_double_to_bits(eta) ^ flip);
+    return fm_min0(z) - g;
+  }
+  const double z = (y == 1.0) ? eta : -eta;
+  const double v = fm_min0(z) - g;
+  return (y == 1.0 || y == 0.0) ? v : 0.0;
 }
 
 // sum_i dnorm(r_i, 0, sd, log=TRUE) from ss = sum r_i^2 with R's dnorm edge cases

@@ -67,7 +67,7 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group;
+  DevBuf X, y, group, sp_tab;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
@@ -205,6 +205,11 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
       bin = (bits == 0 || bits == 0x3FF0000000000000LL);
     }
     mp.y_binary = bin;
+    std::vector<double> tab(2 * (size_t)FM_SP_ENTRIES);  // softplus table of the tiled kernel's epilogue
+    fm_softplus_table_fill(tab.data());
+    MC(ensure(m->sp_tab, tab.size() * 8));
+    MC(cudaMemcpy(m->sp_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    mp.sp_tab = m->sp_tab.as<double>();
   }
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
@@ -224,7 +229,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
@@ -354,7 +359,7 @@ struct Blob {  // host staging of the small kernel-spec arrays -> one H2D copy
 
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
-  const size_t smem = tiled_smem_bytes(PB);
+  const size_t smem = tiled_smem_bytes(PB, FAMILY);
 #define TL_CASE(P)                                                                                               \
   case P: {                                                                                                      \
     static bool attr_done[64] = {};                                                                              \

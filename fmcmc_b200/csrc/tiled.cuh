@@ -35,15 +35,17 @@ struct TiledBuffers {
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
 };
 
-__host__ __device__ inline size_t tiled_smem_bytes(int PB) {
-  return 128 + (size_t)TL_STAGES * ((size_t)PB * TL_TILE + TL_TILE) * sizeof(double);
+// barriers | TL_STAGES x (PB columns + y) x TL_TILE doubles | logistic: softplus table (softplus.h)
+__host__ __device__ inline size_t tiled_smem_bytes(int PB, int family) {
+  return 128 + (size_t)TL_STAGES * ((size_t)PB * TL_TILE + TL_TILE) * sizeof(double) +
+         (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0);
 }
 
 // One observation, one chain: per-observation term of the family.
 //   FAMILY logistic, YBIN: y is known to be exactly 0.0 or 1.0 (checked at model creation)
 template <int FAMILY, bool YBIN>
-__device__ __forceinline__ double tile_term(double e, double y) {
-  if (FAMILY == FMCMC_FAMILY_LOGISTIC) return YBIN ? logistic_term_binary(e, y) : logistic_term(e, y);
+__device__ __forceinline__ double tile_term(double e, double y, const double2* __restrict__ sp_tab) {
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) return logistic_term_tab<YBIN>(e, y, sp_tab);
   const double r = y - e;  // Gaussian LM: e already holds the linear predictor incl. intercept
   return r * r;
 }
@@ -59,6 +61,11 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
   constexpr int STAGE_DOUBLES = PB * TL_TILE + TL_TILE;
   const int tid = threadIdx.x, lane = tid & 31;
   if (err[0] != 0) return;
+  double2* sp_tab = reinterpret_cast<double2*>(stage0 + (size_t)TL_STAGES * STAGE_DOUBLES);
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {  // 32 KB, L2-resident after the first CTA; read by generic loads only
+    const double2* g = reinterpret_cast<const double2*>(mp.sp_tab);
+    for (int e = tid; e < FM_SP_ENTRIES; e += TL_THREADS) sp_tab[e] = g[e];
+  }
 
   const long long ntiles = (mp.ld + TL_TILE - 1) / TL_TILE;
   const int p_x = mp.p_x;
@@ -148,10 +155,10 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
 #pragma unroll
         for (int q = 0; q < TL_RO; q += 2) {
           const double2 yy = *reinterpret_cast<const double2*>(ys + o + q);
-          acc0 += tile_term<FAMILY, YBIN>(e0[q], yy.x);
-          acc1 += tile_term<FAMILY, YBIN>(e1[q], yy.x);
-          acc0 += tile_term<FAMILY, YBIN>(e0[q + 1], yy.y);
-          acc1 += tile_term<FAMILY, YBIN>(e1[q + 1], yy.y);
+          acc0 += tile_term<FAMILY, YBIN>(e0[q], yy.x, sp_tab);
+          acc1 += tile_term<FAMILY, YBIN>(e1[q], yy.x, sp_tab);
+          acc0 += tile_term<FAMILY, YBIN>(e0[q + 1], yy.y, sp_tab);
+          acc1 += tile_term<FAMILY, YBIN>(e1[q + 1], yy.y, sp_tab);
         }
       }
     } else {
@@ -164,8 +171,8 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
           e1 = fma(x, th1[j], e1);
         }
         const double yv = ys[o];
-        acc0 += tile_term<FAMILY, false>(e0, yv);
-        acc1 += tile_term<FAMILY, false>(e1, yv);
+        acc0 += tile_term<FAMILY, false>(e0, yv, sp_tab);
+        acc1 += tile_term<FAMILY, false>(e1, yv, sp_tab);
       }
     }
     __syncwarp();
