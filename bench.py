@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 N_OBS, P_X, CHAINS_PER_GPU = 1_000_000, 32, 1024
 DATA_SEED = 20260317
 KERNEL_WARMUP = 500
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
+# capture of this command (profiles/): a profiler figure, so it is a constant here, never measured in the timed run
+TRAFFIC_PER_LAUNCH = {("cfg3", 3): 269.0e6, ("cfg3", 2): 269.7e6}
 
 
 def make_data(n=N_OBS, p=P_X, seed=DATA_SEED):
@@ -152,17 +155,122 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def ess_pooled(ans):
+    """ESS of each parameter, pooled over chains: per-chain Geyer initial-positive-sequence estimator on the
+    FFT autocovariance, summed over chains.  ans: [C][T][k].  (coda::effectiveSize is third-party and
+    unpinned; this estimator is only a reported figure.)"""
+    C, T, k = ans.shape
+    x = ans - ans.mean(axis=1, keepdims=True)
+    nfft = 1 << int(np.ceil(np.log2(2 * T)))
+    f = np.fft.rfft(x, n=nfft, axis=1)
+    acov = np.fft.irfft(f * np.conj(f), n=nfft, axis=1)[:, :T, :] / T
+    var = acov[:, :1, :]
+    rho = np.where(var > 0, acov / np.where(var > 0, var, 1.0), 0.0)
+    npair = T // 2
+    pairs = rho[:, 0:2 * npair:2, :] + rho[:, 1:2 * npair:2, :]
+    pos = np.cumprod(pairs > 0, axis=1).astype(bool)             # stop at the first non-positive pair
+    tau = -1.0 + 2.0 * np.sum(np.where(pos, pairs, 0.0), axis=1)
+    tau = np.maximum(tau, 1.0 / T)
+    ess = np.where(var[:, 0, :] > 0, T / tau, 0.0)
+    return ess.sum(axis=0)
+
+
+class Workload:
+    """One BASELINE.json config as a synthetic bench workload."""
+
+    def __init__(self, key, args):
+        self.key = key
+        if key == "cfg3":            # BASELINE configs[2]: the configuration the north_star target is quoted on
+            self.family, self.n, self.p_x, self.k = "logistic", N_OBS, P_X, P_X
+            self.chains = args.chains or CHAINS_PER_GPU
+            self.kernel_name = "kernel_adapt(warmup=500, freq=1), timed rows are post-warm-up (adapting every row)"
+            self.kwarm = KERNEL_WARMUP
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 2 * P_X + 6, 2, 51
+            self.label = f"logistic n={self.n} p={self.p_x} x {self.chains} chains/GPU, kernel_adapt (BASELINE configs[2])"
+        elif key == "cfg5":          # BASELINE configs[4]: per-GPU share (8192 chains) of the 65536-chain config
+            self.family, self.n, self.p_x, self.k = "gaussian", args.n or 10_000_000, 127, 128
+            self.chains = args.chains or 8192
+            self.kernel_name = "kernel_nmirror(warmup=500, nadapt=4, lb sd = 0), timed rows are post-warm-up"
+            self.kwarm = 500
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 2 * 127 + 4, 0, 127 + 2
+            self.label = (f"gaussian_lm n={self.n} k=128 (127 columns + sd) x {self.chains} chains/GPU, kernel_nmirror "
+                          "(BASELINE configs[4], one GPU's share)")
+        elif key == "cfg4":          # BASELINE configs[3]: lifeexpect hierarchical normal, 4096 chains, kernel_ram
+            self.family, self.n, self.p_x, self.k = "hier", 1000, 0, 7
+            self.chains = args.chains or 4096
+            self.kernel_name = "kernel_ram() defaults (warmup 0: adapting every row, 2nd likelihood when reflected)"
+            self.kwarm = 0
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 3, 0, 2
+            self.label = (f"lifeexpect hier_normal (smoke x female cells, k=7) n=1000 x {self.chains} chains/GPU, kernel_ram "
+                          "(BASELINE configs[3]); on-chip data, latency-bound")
+        elif key == "cfg1":          # BASELINE configs[0]: README model shape, 1 chain, kernel_normal(scale=.1)
+            self.family, self.n, self.p_x, self.k = "gaussian", 1000, 1, 3
+            self.chains = args.chains or 1
+            self.kernel_name = "kernel_normal(scale=0.1)"
+            self.kwarm = 0
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 6, 0, 3
+            self.label = (f"README Gaussian LM shape n=1000 k=3 x {self.chains} chain(s), kernel_normal(scale=.1) "
+                          "(BASELINE configs[0]); on-chip data, latency-bound (serial steps)")
+        else:
+            raise SystemExit(f"unknown workload {key}")
+
+    def make(self, fm, A, torch, local, rank):
+        """Returns (family, device_ptrs or None, kernel, init[C][k], host X / y or None)."""
+        C, k = self.chains, self.k
+        rng = np.random.default_rng(1000 + rank)
+        if self.key == "cfg3":
+            X, y = make_data()
+            fam = fm.ll_logistic(X, y, prior_sd=2.0)
+            return fam, None, fm.kernel_adapt(), rng.normal(0, 0.1, (C, k)), (X, y)
+        if self.key == "cfg4":
+            le = np.load(os.path.join(ROOT, "tests", "golden", "lifeexpect.npz"))
+            grp = (2 * le["smoke"] + le["female"]).astype(np.int32)
+            fam = fm.ll_hier_normal(le["age"], grp, n_groups=4, gamma_bounds=(0.0, 150.0), estimate_scales=True)
+            kern = fm.kernel_ram(lb=[np.nan] * 5 + [1e-3, 1e-3])
+            init = np.tile([75.0] * 5 + [5.0, 5.0], (C, 1)) + rng.normal(0, 0.5, (C, k))
+            return fam, None, kern, init, None
+        if self.key == "cfg1":
+            X = rng.standard_normal(self.n)
+            y = 3.0 + 2.0 * X + rng.normal(0, 4.0, self.n)
+            fam = fm.ll_gaussian_lm(X.reshape(-1, 1), y, intercept=True, guard=True)
+            return fam, None, fm.kernel_normal(scale=0.1), np.tile([0.0, 0.0, float(np.std(y, ddof=1))], (C, 1)), None
+        # cfg5: 10 GB of X generated directly in HBM (torch is plumbing: device memory + RNG for SYNTHETIC data)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(DATA_SEED)
+        n, p = self.n, self.p_x
+        Xd = torch.empty((p, n), dtype=torch.float64, device="cuda")      # column-major n x p (R layout)
+        Xd[0].fill_(1.0)
+        for j in range(1, p):
+            Xd[j].normal_(generator=g)
+        beta = torch.randn(p, dtype=torch.float64, device="cuda", generator=g)
+        yd = torch.matmul(beta, Xd) + 2.0 * torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        torch.cuda.synchronize()
+        from fmcmc_b200.families import DeviceFamily
+        fam = DeviceFamily(A.FAMILY_GAUSSIAN_LM, n, p_x=p, flags=A.MODEL_GUARD)
+        self._keep = (Xd, yd)
+        centre = np.r_[beta.cpu().numpy(), 2.0]
+        lb = np.full(k, np.nan); lb[-1] = 0.0
+        kern = fm.kernel_nmirror(mu=centre, scale=2.0 / np.sqrt(n) * 0.3, lb=lb)
+        init = centre + rng.normal(0, 2.0 / np.sqrt(n), (C, k))
+        return fam, (Xd.data_ptr(), yd.data_ptr(), None), kern, init, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg1"],
+                    help="cfg3 = BASELINE configs[2] (default, the metric's configuration); cfg5 = configs[4] per-GPU share")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--n", type=int, default=None, help="observations (cfg5 only; default 1e7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-kernel-warmup", action="store_true",
-                    help="prime abs_iter instead of running kernel_adapt's 500 warm-up rows (profiling runs)")
+                    help="prime abs_iter instead of running the kernel's 500 warm-up rows (profiling runs)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"cfg3": 100, "cfg5": 5, "cfg4": 1000, "cfg1": 10000}[args.workload]
     args.steps = max(args.steps, 2)
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -189,38 +297,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    C = args.chains
+    wl = Workload(args.workload, args)
+    C, k = wl.chains, wl.k
     K, W = args.steps, args.warmup
-    X, y = make_data()
-    fam = fm.ll_logistic(X, y, prior_sd=2.0)
-    model = DeviceModel(fam, device=local)          # X, y -> HBM once (264 MB)
-    k = fam.k
+    fam, dev_ptrs, kern, init0, host_data = wl.make(fm, A, torch, local, rank)
+    model = DeviceModel(fam, device=local, device_ptrs=dev_ptrs)      # X, y -> HBM once
     chain_offset = rank * C
-    kern = fm.kernel_adapt()                        # reference defaults: warmup 500, freq 1, eps 1e-4
     spec = kern.to_spec(k)
-    dlen = A.state_len(A.KERNEL_ADAPT, k, k)
+    dlen = A.state_len(spec["type"], k, k)
     istate = np.zeros((C, A.ISTATE_LEN), dtype=np.int64)
-    dstate = np.zeros((C, dlen))
-    rng = np.random.default_rng(1000 + rank)
+    dstate = np.zeros((C, max(dlen, 1)))
     init = torch.empty((C, k), dtype=torch.float64).pin_memory().numpy()
-    init[:] = rng.normal(0, 0.1, (C, k))
+    init[:] = init0
     seed = 20260317
 
     def stream(run_index):
         return A.marshal_stream(A.STREAM_PHILOX, seed=seed, run_index=run_index)
 
-    # ---- setup (untimed): kernel_adapt's own warm-up so the timed rows do the full adaptive step
-    # (covariance recurrence + Cholesky + mvn proposal) -----------------------------------------------------
+    # ---- setup (untimed): the kernel's own warm-up so the timed rows do the full adaptive step
+    # (kernel_adapt: covariance recurrence + Cholesky + mvn proposal every row) ---------------------------------
     run_idx = 0
-    if args.skip_kernel_warmup:
-        istate[:, 0] = KERNEL_WARMUP + 1
+    if args.skip_kernel_warmup or wl.key == "cfg5":
+        # cfg5: 500 warm-up rows cost minutes of GPU time; the post-warm-up mirror step does the same work per
+        # row as a warm-up one (the adaptation is O(k) per chain), so abs_iter is primed past the warm-up instead
+        istate[:, 0] = wl.kwarm + 1
+        if wl.key == "cfg5":
+            istate[:, 1] = A.STATE_INIT | (2 << A.STATE_OBS_SHIFT)
+            dstate[:, :k] = np.asarray(spec["mu"]); dstate[:, k:2 * k] = np.asarray(spec["scale"]); dstate[:, 2 * k:] = 0.4
         model.run(spec, 3, C, initial=init, stream=stream(run_idx), istate=istate, dstate=dstate,
                   chain_offset=chain_offset, outputs=False)
     else:
-        model.run(spec, KERNEL_WARMUP + 3, C, initial=init, stream=stream(run_idx), istate=istate, dstate=dstate,
+        model.run(spec, wl.kwarm + 3, C, initial=init, stream=stream(run_idx), istate=istate, dstate=dstate,
                   chain_offset=chain_offset, outputs=False)
     run_idx += 1
-    assert istate[0, 0] > KERNEL_WARMUP
+    assert istate[0, 0] > wl.kwarm
 
     # ---- W untimed warm-up steps, then K timed steps: inputs resident in HBM ---------------------------------
     model.run(spec, W + 1, C, initial=None, stream=stream(run_idx), chain_offset=chain_offset, outputs=False,
@@ -237,13 +347,13 @@ def main():
     run_idx += 1
     rep = out["report"]
     dev_ms = float(rep.device_ms)                   # CUDA events on the library's launch stream
-    hot_ms = float(rep.hot_ms) / max(int(rep.hot_launches), 1)
+    hot_ms = float(rep.hot_ms) / int(rep.hot_launches) if int(rep.hot_launches) else dev_ms / K   # path 1: one fused launch
     launches = int(rep.n_launches)
     accept = int(rep.n_accept) / (C * K)
+    path = int(rep.path)
 
-    # ---- e2e: the public call MCMC() with HOST buffers (H2D of initial + kernel state, D2H of ans / draws /
+    # ---- e2e: the public call with HOST buffers (H2D of initial + kernel state, D2H of ans / draws /
     # logpost / state inside the timed region); data X stays cached on the device like the closure's data ----
-    last = None
     barrier()
     e2e_t0 = time.perf_counter()
     m2 = model.run(spec, K + 1, C, initial=init, stream=stream(run_idx), istate=istate.copy(), dstate=dstate.copy(),
@@ -255,6 +365,7 @@ def main():
     h2d, d2h = int(m2["report"].h2d_bytes), int(m2["report"].d2h_bytes)
 
     clocks = sampler.stop() if sampler else None
+    ess = ess_pooled(m2["ans"][:, 1:, :]) if rank == 0 else None
 
     # ---- one Gelman-Rubin check across all chains / GPUs (untimed; NCCL all_gather + all_reduce) ------------
     gel_ms, mpsrf = None, None
@@ -273,7 +384,7 @@ def main():
             xb, s2, ws = model.gelman_partials((K + 1) // 2, K + 1, free, C)
             _, mpsrf = model.gelman_finish(K + 1 - (K + 1) // 2, C, k, xb, s2, ws)
         gel_ms = 1e3 * (time.perf_counter() - g0)
-    except Exception as e:  # the R-hat of a 20-row window may be degenerate; never fail the bench on it
+    except Exception as e:  # the R-hat of a short window may be degenerate; never fail the bench on it
         mpsrf = f"unavailable: {e}"
 
     # ---- max over ranks ------------------------------------------------------------------------------------------
@@ -286,10 +397,11 @@ def main():
         hbm_peak, peak_src = load_peaks()
         total_chain_steps = C * world * K
         value = total_chain_steps / (dev_ms * 1e-3)
-        alg_bytes = 8.0 * N_OBS * (P_X + 1) + 8.0 * C * (3 * k + 2)          # SURVEY §8d, per launch (= per step per GPU)
-        achieved = alg_bytes / (hot_ms * 1e-3) / 1e9
-        evals = float(N_OBS) * C
-        flops = evals * (2 * P_X + 6)                                         # + 2 transcendentals per eval (reported apart)
+        n, p_x = wl.n, wl.p_x
+        alg_bytes = 8.0 * n * (p_x + 1) + 8.0 * C * (3 * k + 2)               # SURVEY §8d, per launch (= per step per GPU)
+        hbm_achieved = alg_bytes / (hot_ms * 1e-3) / 1e9
+        evals = float(n) * C
+        flops = evals * wl.flops_per_eval                                     # 2 p_x + 6 (+ 2 transcendentals, apart)
         fp64_peak = None
         try:
             import ctypes as Ct
@@ -299,36 +411,54 @@ def main():
                 fp64_peak = v.value
         except Exception:
             pass
+        peak_tf = fp64_peak or 37.1
+        achieved_tf = flops / (hot_ms * 1e-3) / 1e12
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
+        pipe_util = evals * wl.fp64_instr_per_eval / 32.0 / (hot_ms * 1e-3) / pipe_slots
+        kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 1: "mh_resident_kernel"}[path]
         line = {
             "metric": "MH chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"logistic n={N_OBS} p={P_X} x {C} chains/GPU, kernel_adapt (BASELINE configs[2])",
-                       "n": N_OBS, "p": P_X, "chains_per_gpu": C, "chains_total": C * world,
-                       "kernel": "kernel_adapt(warmup=500, freq=1), timed rows are post-warm-up (adapting every row)",
-                       "stream": "Philox4x32-10", "path": int(rep.path),
-                       "l2": "X (264 MB) is larger than L2 (126 MB) and streamed once per step: no flush needed"},
-            "evals_per_s": value * N_OBS,
+            "config": {"workload": wl.label, "n": n, "p": p_x, "chains_per_gpu": C, "chains_total": C * world,
+                       "kernel": wl.kernel_name, "stream": "Philox4x32-10", "path": path,
+                       "l2": (f"X ({8e-6 * n * p_x:.0f} MB) is larger than L2 (126 MB) and streamed every step: no flush needed"
+                              if path != 1 else "data staged once into shared memory by TMA: on-chip by construction")},
+            "evals_per_s": value * n,
             "accept_rate": accept,
+            "ess_per_s": float(ess.min()) * world / e2e_sec if ess is not None else None,
+            "ess": {"min_over_params": float(ess.min()), "median_over_params": float(np.median(ess)),
+                    "rows_per_chain": K, "chains": C,
+                    "method": "per-chain Geyer initial-positive-sequence, summed over rank 0's chains (x n_gpus in ess_per_s); "
+                              "time = the e2e call"} if ess is not None else None,
             "e2e": {"value": C * world * K / e2e_sec, "unit": "chain-steps/s",
                     "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "call": "fmcmc_run via the Python mirror with host numpy buffers (initial pinned): H2D initial + "
                             "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows"},
             "gpu_launches": launches,
             "wall_ms_per_step": 1e3 * t_wall / K,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "tiled_loglik_kernel<logistic,32>",
-                         "peak_source": peak_src, "launch_ms": hot_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "FP64-pipe bound, not HBM bound (SURVEY §8d: AI ~ C/4 flop/B >> ridge ~6): see fp64"},
-            "fp64": {"dfma_peak_tflops_measured": fp64_peak,
-                     "achieved_tflops_dot_plus_epilogue": flops / (hot_ms * 1e-3) / 1e12,
-                     "frac": (flops / (hot_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                     "flops_per_eval": 2 * P_X + 6, "transcendentals_per_eval": 2},
+            # The dominant kernel is bound by the FP64 pipe (DFMA / DMMA share one 64-lane datapath per SM; tcgen05
+            # has no FP64 kind), not by HBM: arithmetic intensity ~ C/4 flop/B vs a ridge of ~6.
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": TRAFFIC_PER_LAUNCH.get((wl.key, path)),
+                         "kernel": kname, "launch_ms": hot_ms,
+                         "peak_source": "FP64 DFMA/DMMA peak measured live by fmcmc_measure_fp64_peak (MEASURED_PEAKS.json "
+                                        "has no FP64 figure; the bf16 tcgen05 peak does not apply to FP64)",
+                         "algorithmic_flops_per_launch": flops,
+                         "flops_per_eval": wl.flops_per_eval, "transcendentals_per_eval_not_counted": wl.transc_per_eval,
+                         "fp64_pipe_util": pipe_util,
+                         "fp64_pipe_util_note": f"{wl.fp64_instr_per_eval} FP64-pipe instruction slots per eval (DMMA = 8 slots) x evals / "
+                                                "(148 SMs x 2 warp-instr/clk x SM clock)"},
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "north_star asks for the HBM fraction: structurally ~1 % because X is read once per step and "
+                            "shared by every resident chain"},
             "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * world},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and host_data is not None:
+            X, y = host_data
             threads = os.cpu_count() or 1
             chains_s = 2 * threads
             probe = cpu_port_run(X, y, chains_s, 3, threads)                   # 2 MH steps: sizes the sample
@@ -336,7 +466,7 @@ def main():
             sec = cpu_port_run(X, y, chains_s, rows_s, threads)
             line["cpu_baseline"] = {"value": chains_s * (rows_s - 1) / sec, "unit": "chain-steps/s", "cores": threads,
                                     "kind": "port",
-                                    "sample": f"{chains_s} chains x {rows_s - 1} MH steps over the full n={N_OBS}, "
+                                    "sample": f"{chains_s} chains x {rows_s - 1} MH steps over the full n={n}, "
                                               f"{sec:.1f} s wall on {threads} host threads (C restatement of the "
                                               "reference loop; R is not installed)"}
         print(json.dumps(line))

@@ -17,6 +17,7 @@
 #include "propose.cuh"
 #include "resident.cuh"
 #include "tiled.cuh"
+#include "tiled_mma.cuh"
 
 // --------------------------------------------------------------------------------
 // small host utilities
@@ -73,6 +74,8 @@ struct fmcmc_model {
   int sm_count = 148;
   int smem_optin = 0;
   int forced_path = 0;
+  int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
+  int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
   // run buffers (grow-only)
   DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
       errbuf, nacc, spec, fed_logu, fed_z, initial, partial, out_ans, out_draws, out_lp, tmp;
@@ -214,6 +217,8 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
 #undef MC
+  if (const char* v = getenv("FMCMC_TILED_VARIANT")) { if (atoi(v) == 2 || atoi(v) == 3) m->tiled_default = atoi(v); }
+  if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   *out = m;
   return FMCMC_OK;
 }
@@ -243,7 +248,7 @@ extern "C" void fmcmc_model_free(fmcmc_model* m) {
 }
 
 extern "C" int fmcmc_set_path(fmcmc_model* m, int path) {
-  if (!m || path < 0 || path > 2) return FMCMC_EINVAL;
+  if (!m || path < 0 || path > 3) return FMCMC_EINVAL;
   m->forced_path = path;
   return FMCMC_OK;
 }
@@ -381,6 +386,48 @@ static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const 
   }
 #undef TL_CASE
   return cudaGetLastError();
+}
+
+// DMMA variant (tiled_mma.cuh).  Geometry per padded width PB: (warps, chain tiles per warp).
+struct MmaShape { int PB, warps, NT, MO; };
+static MmaShape mma_shape(int p_x, int variant) {
+  if (p_x <= 32) {
+    switch (variant) {  // measured on B200, cfg3: 3.46 / 3.59 / 3.61 / 3.62 ms per launch (profiles/r01_*)
+      case 1: return MmaShape{32, 8, 4, 2};
+      case 2: return MmaShape{32, 8, 8, 1};
+      case 3: return MmaShape{32, 8, 4, 4};
+      default: return MmaShape{32, 16, 4, 1};
+    }
+  }
+  if (p_x <= 64) return MmaShape{64, 8, 4, 1};
+  return variant == 1 ? MmaShape{128, 8, 2, 1} : MmaShape{128, 8, 2, 2};
+}
+template <int FAMILY, bool YBIN>
+static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 grid, const RunBuffers& rb,
+                                    const TiledBuffers& tb) {
+#define TM_CASE(P, W, N, O)                                                                                      \
+  if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O) {                                                             \
+    const size_t smem = tiled_mma_smem_bytes<P>(FAMILY);                                                         \
+    static bool attr_done[64] = {};                                                                              \
+    if (!attr_done[m->device]) {                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O>,                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      if (e != cudaSuccess) return e;                                                                            \
+      attr_done[m->device] = true;                                                                               \
+    }                                                                                                            \
+    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
+                                                                                       rb.nchains, tb, rb.err);  \
+    return cudaGetLastError();                                                                                   \
+  }
+  TM_CASE(32, 8, 4, 2)
+  TM_CASE(32, 8, 4, 4)
+  TM_CASE(32, 8, 8, 1)
+  TM_CASE(32, 16, 4, 1)
+  TM_CASE(64, 8, 4, 1)
+  TM_CASE(128, 8, 2, 1)
+  TM_CASE(128, 8, 2, 2)
+#undef TM_CASE
+  return cudaErrorInvalidValue;
 }
 
 extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec* ks,
@@ -533,13 +580,17 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   rb.n_accept = m->nacc.as<unsigned long long>();
 
   // ---- choose the stepping path --------------------------------------------------------
+  // 1 = chain-resident fused kernel; 2 = observation-tiled, lane<->chain DFMA kernel (p_x <= 32);
+  // 3 = observation-tiled, DMMA kernel (p_x <= 128)
   const ModelParams& mp = m->mp;
   const size_t data_bytes = (size_t)mp.p_x * mp.ld * 8 + (size_t)mp.ld * 8 + (mp.group ? (size_t)mp.ld * 4 + 16 : 0);
-  const bool tiled_ok = (mp.family == FMCMC_FAMILY_GAUSSIAN_LM || mp.family == FMCMC_FAMILY_LOGISTIC) && mp.p_x <= 32;
+  const bool lm_or_logit = mp.family == FMCMC_FAMILY_GAUSSIAN_LM || mp.family == FMCMC_FAMILY_LOGISTIC;
+  const bool tiled_ok = lm_or_logit && mp.p_x <= 128;
   int path = m->forced_path;
-  if (path == 0) path = (tiled_ok && data_bytes > 96 * 1024) ? 2 : 1;
-  if (path == 2 && !tiled_ok) {
-    set_err(err, errlen, "the observation-tiled path supports gaussian_lm / logistic with p_x <= 32 (got family %d, p_x %d)", mp.family, mp.p_x);
+  if (path == 0)  // narrow X: the DFMA kernel's 8 / 16-column tiers do no padded work; wide X: DMMA
+    path = (tiled_ok && data_bytes > 96 * 1024) ? (mp.p_x > 32 ? 3 : (mp.p_x <= 16 ? 2 : m->tiled_default)) : 1;
+  if ((path == 2 && !(lm_or_logit && mp.p_x <= 32)) || (path == 3 && !tiled_ok)) {
+    set_err(err, errlen, "the observation-tiled paths support gaussian_lm / logistic with p_x <= 32 (path 2) or <= 128 (path 3); got family %d, p_x %d", mp.family, mp.p_x);
     return FMCMC_EUNSUP;
   }
   long long launches = 0;
@@ -576,10 +627,13 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   } else {
     // ---- path 2: observation-tiled, two launches per row ------------------------------------
     const int PB = mp.p_x <= 8 ? 8 : (mp.p_x <= 16 ? 16 : 32);
+    const MmaShape msh = mma_shape(mp.p_x, m->mma_wide);
+    const int cpb = path == 3 ? msh.warps * msh.NT * 8 : TL_CHAINS;       // chains per CTA
+    const int tile_rows = path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE;
     TiledBuffers tb{};
     tb.ncols = is_ram ? 2 * C : C;
-    const int chain_blocks = (tb.ncols + TL_CHAINS - 1) / TL_CHAINS;
-    const long long ntiles = (mp.ld + TL_TILE - 1) / TL_TILE;
+    const int chain_blocks = (tb.ncols + cpb - 1) / cpb;
+    const long long ntiles = (mp.ld + tile_rows - 1) / tile_rows;
     int gx = std::max(1, m->sm_count / chain_blocks);
     if (gx > ntiles) gx = (int)ntiles;
     tb.gx = gx;
@@ -598,10 +652,17 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
-        cudaError_t e = (mp.family == FMCMC_FAMILY_LOGISTIC)
-                            ? (mp.y_binary ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, true>(m, PB, lgrid, rb, tb)
-                                           : launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, false>(m, PB, lgrid, rb, tb))
-                            : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, PB, lgrid, rb, tb);
+        cudaError_t e;
+        if (path == 3)
+          e = (mp.family == FMCMC_FAMILY_LOGISTIC)
+                  ? (mp.y_binary ? launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, true>(m, msh, lgrid, rb, tb)
+                                 : launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, false>(m, msh, lgrid, rb, tb))
+                  : launch_tiled_mma<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, msh, lgrid, rb, tb);
+        else
+          e = (mp.family == FMCMC_FAMILY_LOGISTIC)
+                  ? (mp.y_binary ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, true>(m, PB, lgrid, rb, tb)
+                                 : launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, false>(m, PB, lgrid, rb, tb))
+                  : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, PB, lgrid, rb, tb);
         if (e != cudaSuccess) { set_err(err, errlen, "CUDA launch error %s (tiled_loglik)", cudaGetErrorString(e)); return FMCMC_ECUDA; }
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed + 1], m->stream), hot_timed++;
         launches += 1;

@@ -1,0 +1,217 @@
+// tiled_mma.cuh — observation-tiled likelihood kernel, FP64 tensor-core (DMMA) variant.
+//
+// Same contract, grid and TMA pipeline as tiled_loglik_kernel (tiled.cuh), but the X.Theta
+// contraction runs on mma.sync.aligned.m8n8k4.f64 (SASS DMMA; tcgen05 has no FP64 kind):
+//   M = 8 observations, N = 8 chains, K = 4 parameters per instruction.
+// The FP64 roof is the same as DFMA's (profiles/r01_microbench_fp64_pipes.txt: 37.1 TF/s either
+// way, shared datapath) — what changes is everything AROUND the FP64 pipe: one conflict-free
+// LDS.64 fetches an 8x4 A fragment that feeds NT MMAs (= 8*NT DFMA-equivalents per lane), against
+// one broadcast LDS.128 per 4 DFMAs in the lane<->chain kernel, whose shared-memory wavefronts ran
+// at 58 % of peak and cost ~30 % of the FP64 issue slots (profiles/r01_v1_tiled_loglik_ncu.txt,
+// profiles/r01_microbench_fp64_issue.txt).  It also scales to p_x = 128 (config 5): the B
+// fragments (Theta) of NT chain tiles stay in registers, NT * PB/4 <= 64 doubles per lane.
+//
+// Fragment layout (PTX ISA, m8n8k4 .f64), g = lane / 4, t = lane % 4:
+//   A[row = g][col = t]   = X[obs0 + g][4 s + t]          (shared memory, column stride CS)
+//   B[row = t][col = g]   = Theta[chain_tile*8 + g][4 s + t]   (registers, loaded once per launch)
+//   C[row = g][col = 2t + {0,1}] = eta[obs0 + g][chain_tile*8 + 2t + {0,1}]
+// Every lane therefore finishes 2 chains x 1 observation per (obs tile, chain tile): the family
+// epilogue runs on the C registers in place and accumulates per (chain tile, column) privately;
+// one shuffle reduction over g at the very end.  Fixed order => deterministic.
+#pragma once
+#include "tiled.cuh"
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  // volatile: keeps the source order (k-step outer, chain tile inner) so consecutive DMMAs are independent;
+  // left to itself ptxas chains the 8 k-steps of one tile back to back and waits out the latency each time
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+template <int PB>
+struct MmaGeom {
+  static constexpr int TR = PB <= 32 ? 128 : (PB == 64 ? 64 : 32);  // observations per pipeline stage
+  // column stride == 4 (mod 16) doubles: an LDS.64 is served per half-warp (g = 0..3 | 4..7, t = 0..3), and
+  // bank(t, g) = (8 t + 2 g) mod 32 is then distinct inside each half (TR + 8 gave 2-way conflicts: ncu r01)
+  static constexpr int CS = TR + 4;
+  static constexpr int KS = PB / 4;        // k-steps
+  static constexpr int STAGE_DOUBLES = PB * CS + TR;
+};
+
+template <int PB>
+__host__ __device__ inline size_t tiled_mma_smem_bytes(int family) {
+  return 128 + (size_t)TL_STAGES * MmaGeom<PB>::STAGE_DOUBLES * sizeof(double) +
+         (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0);
+}
+
+template <int FAMILY, int PB, bool YBIN, int NWARPS, int NT, int MO>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
+                        TiledBuffers tb, const int* __restrict__ err) {
+  using G = MmaGeom<PB>;
+  constexpr int TR = G::TR, CS = G::CS, KS = G::KS, STAGE_DOUBLES = G::STAGE_DOUBLES;
+  constexpr int NTHREADS = NWARPS * 32;
+  constexpr int CPB = NWARPS * NT * 8;  // chains per CTA
+  static_assert(NT * KS <= 64, "B fragments must fit in registers");
+  static_assert(TR % (8 * MO) == 0, "tile rows must be a multiple of the observation block");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + TL_STAGES;
+  double* stage0 = reinterpret_cast<double*>(smem_raw + 128);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (err[0] != 0) return;
+  double2* sp_tab = reinterpret_cast<double2*>(stage0 + (size_t)TL_STAGES * STAGE_DOUBLES);
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
+    const double2* gt = reinterpret_cast<const double2*>(mp.sp_tab);
+    for (int e = tid; e < FM_SP_ENTRIES; e += NTHREADS) sp_tab[e] = gt[e];
+  }
+
+  const long long ntiles = (mp.ld + TR - 1) / TR;
+  const int p_x = mp.p_x;
+
+  if (tid == 0) {
+    for (int s = 0; s < TL_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NWARPS);
+    }
+    mbar_fence_init();
+  }
+  // columns >= p_x of every stage are never written by TMA: zero them once (Theta is 0 there too)
+  for (int s = 0; s < TL_STAGES; s++)
+    for (int e = p_x * CS + tid; e < PB * CS; e += NTHREADS) stage0[(size_t)s * STAGE_DOUBLES + e] = 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  auto issue = [&](long long tile, int s) {  // executed by thread 0 only
+    const long long row0 = tile * TR;
+    const long long rows = min((long long)TR, mp.ld - row0);
+    const uint32_t bytes = (uint32_t)(rows * 8);
+    double* dst = stage0 + (size_t)s * STAGE_DOUBLES;
+    mbar_expect_tx(&full[s], bytes * (uint32_t)(p_x + 1));
+    for (int j = 0; j < p_x; j++) bulk_g2s(dst + (size_t)j * CS, mp.X + (size_t)j * mp.ld + row0, bytes, &full[s]);
+    bulk_g2s(dst + (size_t)PB * CS, mp.y + row0, bytes, &full[s]);
+  };
+
+  // ---- B fragments: Theta of this warp's NT chain tiles, in registers for the whole launch ----
+  const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
+  const int chain0 = blockIdx.y * CPB + warp * (NT * 8);
+  auto theta_of = [&](int col) -> const double* {
+    if (col >= tb.ncols) return nullptr;
+    return col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
+  };
+  double B[KS][NT];
+  double cinit[NT][2];
+#pragma unroll
+  for (int ct = 0; ct < NT; ct++) {
+    const double* th = theta_of(chain0 + ct * 8 + g);
+#pragma unroll
+    for (int s = 0; s < KS; s++) {
+      const int j = 4 * s + t;
+      B[s][ct] = (th && j < p_x) ? th[icpt + j] : 0.0;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const double* thc = theta_of(chain0 + ct * 8 + 2 * t + h);
+      cinit[ct][h] = (icpt && thc) ? thc[0] : 0.0;
+    }
+  }
+
+  // ---- pipeline prologue -----------------------------------------------------------
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    long long tl = first;
+    for (int s = 0; s < TL_STAGES && tl < ntiles; s++, tl += step) issue(tl, s);
+  }
+
+  double acc[NT][2];
+#pragma unroll
+  for (int ct = 0; ct < NT; ct++) acc[ct][0] = acc[ct][1] = 0.0;
+
+  long long it = 0;
+  for (long long tile = first; tile < ntiles; tile += step, it++) {
+    const int s = (int)(it % TL_STAGES);
+    const uint32_t ph = (uint32_t)((it / TL_STAGES) & 1);
+    if (tid == 0 && it >= 1) {  // refill the stage consumed in the previous iteration
+      const long long pit = it - 1;
+      const int ps = (int)(pit % TL_STAGES);
+      const long long nt = tile - step + (long long)TL_STAGES * step;
+      if (nt < ntiles) {
+        mbar_wait(&empty[ps], (uint32_t)((pit / TL_STAGES) & 1));
+        issue(nt, ps);
+      }
+    }
+    mbar_wait(&full[s], ph);
+    const double* Xs = stage0 + (size_t)s * STAGE_DOUBLES;
+    const double* ys = Xs + (size_t)PB * CS;
+    const long long row0 = tile * TR;
+    const int valid = (int)min((long long)TR, mp.n - row0);  // < TR only for the last tile
+    const double* Ag = Xs + t * CS + g;                        // this lane's A-fragment column / row
+    if (valid == TR) {
+#pragma unroll 1
+      for (int o = 0; o < TR; o += 8 * MO) {  // MO observation tiles x NT chain tiles = MO*NT independent DMMA chains
+        double c[MO][NT][2];
+#pragma unroll
+        for (int mo = 0; mo < MO; mo++)
+#pragma unroll
+          for (int ct = 0; ct < NT; ct++) { c[mo][ct][0] = cinit[ct][0]; c[mo][ct][1] = cinit[ct][1]; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+          double a[MO];
+#pragma unroll
+          for (int mo = 0; mo < MO; mo++) a[mo] = Ag[ks * 4 * CS + o + 8 * mo];
+#pragma unroll
+          for (int mo = 0; mo < MO; mo++)
+#pragma unroll
+            for (int ct = 0; ct < NT; ct++) dmma_m8n8k4(c[mo][ct][0], c[mo][ct][1], a[mo], B[ks][ct]);
+        }
+#pragma unroll
+        for (int mo = 0; mo < MO; mo++) {
+          const double yv = ys[o + 8 * mo + g];
+#pragma unroll
+          for (int ct = 0; ct < NT; ct++) {
+            acc[ct][0] += tile_term<FAMILY, YBIN>(c[mo][ct][0], yv, sp_tab);
+            acc[ct][1] += tile_term<FAMILY, YBIN>(c[mo][ct][1], yv, sp_tab);
+          }
+        }
+      }
+    } else {
+      for (int o = 0; o < valid; o += 8) {  // rows >= valid hold stale (finite or not) data: selected away
+        double c[NT][2];
+#pragma unroll
+        for (int ct = 0; ct < NT; ct++) { c[ct][0] = cinit[ct][0]; c[ct][1] = cinit[ct][1]; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+          const double a = Ag[ks * 4 * CS + o];
+#pragma unroll
+          for (int ct = 0; ct < NT; ct++) dmma_m8n8k4(c[ct][0], c[ct][1], a, B[ks][ct]);
+        }
+        const bool live = (o + g) < valid;
+        const double yv = ys[o + g];
+#pragma unroll
+        for (int ct = 0; ct < NT; ct++) {
+          const double v0 = tile_term<FAMILY, false>(c[ct][0], yv, sp_tab);
+          const double v1 = tile_term<FAMILY, false>(c[ct][1], yv, sp_tab);
+          acc[ct][0] += live ? v0 : 0.0;
+          acc[ct][1] += live ? v1 : 0.0;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- reduce over the 8 observation rows (lanes with equal t), write the CTA's partial sums ----
+#pragma unroll
+  for (int ct = 0; ct < NT; ct++)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      double v = acc[ct][h];
+      v += __shfl_xor_sync(FM_FULL, v, 4);
+      v += __shfl_xor_sync(FM_FULL, v, 8);
+      v += __shfl_xor_sync(FM_FULL, v, 16);
+      const int col = chain0 + ct * 8 + 2 * t + h;
+      if (g == 0 && col < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col] = v;
+    }
+}

@@ -132,11 +132,13 @@ def test_hier_normal_resident(oracle):
     assert_parity(g[0], o[0], 1e-11, "hier + ram")
 
 
+@pytest.mark.parametrize("path", [2, 3])
 @pytest.mark.parametrize("family", ["logistic", "gaussian"])
 @pytest.mark.parametrize("kname", ["normal", "normal_reflective", "adapt", "ram", "nmirror", "unif"])
-def test_tiled_path_parity(oracle, family, kname):
-    """Path 2 (observation-tiled, TMA pipeline) forced on a problem the oracle finishes in seconds:
-    ragged n (tail tile, odd n -> padded ld), chains not a multiple of the chain block."""
+def test_tiled_path_parity(oracle, family, kname, path):
+    """Paths 2 / 3 (observation-tiled TMA pipeline; DFMA lane<->chain kernel / DMMA kernel) forced on a
+    problem the oracle finishes in seconds: ragged n (tail tile, odd n -> padded ld), chains not a
+    multiple of the chain block."""
     rng = np.random.default_rng(33)
     n, p = 2 * 128 * 3 + 77, 7
     if family == "logistic":
@@ -155,22 +157,47 @@ def test_tiled_path_parity(oracle, family, kname):
                 spec[key] = -A.DBL_MAX if key == "lb" else A.DBL_MAX
     if "scale" in spec:
         spec["scale"] = 0.05
-    g, o, _ = run_both(oracle, fam, spec, init, 140, 70, rng=rng, path=2)
-    assert g[0]["report"].path == 2
-    assert_parity(g[0], o[0], 1e-11, f"{family}/{kname}")
+    g, o, _ = run_both(oracle, fam, spec, init, 140, 70, rng=rng, path=path)
+    assert g[0]["report"].path == path
+    assert_parity(g[0], o[0], RTOL, f"{family}/{kname}")
 
 
-def test_tiled_many_chain_blocks(oracle):
-    """> 512 chains => two chain blocks in the tiled grid; p_x = 32 (the bench's register tier)."""
+@pytest.mark.parametrize("path", [2, 3])
+def test_tiled_many_chain_blocks(oracle, path):
+    """> 512 chains => several chain blocks in the tiled grid; p_x = 32 (the bench's register tier)."""
     rng = np.random.default_rng(44)
     fam = _logistic_family(rng, 1500, 32)
     spec = dict(type=A.KERNEL_NORMAL, k=32, mu=0.0, scale=0.03)
-    g, o, _ = run_both(oracle, fam, spec, rng.normal(0, 0.1, (600, 32)), 40, 600, rng=rng, path=2)
-    assert_parity(g[0], o[0], 1e-11)
+    g, o, _ = run_both(oracle, fam, spec, rng.normal(0, 0.1, (600, 32)), 40, 600, rng=rng, path=path)
+    assert_parity(g[0], o[0], RTOL)
+
+
+@pytest.mark.parametrize("family,p", [("gaussian", 127), ("gaussian", 50), ("logistic", 100), ("logistic", 33)])
+def test_tiled_wide_design_matrix(oracle, family, p):
+    """p_x > 32 (config 5 has k = 128): only the DMMA kernel handles it; Theta stays in registers as B
+    fragments, the stage holds 64 / 32 observations.  Ragged n, chains not a multiple of the chain block."""
+    rng = np.random.default_rng(55)
+    n, C = 1000 + 13, 150
+    if family == "logistic":
+        fam, k = _logistic_family(rng, n, p), p
+        init = rng.normal(0, 0.05, (C, k))
+        spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.02)
+    else:
+        from fmcmc_b200 import ll_gaussian_lm
+        X = rng.standard_normal((n, p))
+        y = 1.0 + X @ rng.standard_normal(p) + rng.normal(0, 2.0, n)
+        fam, k = ll_gaussian_lm(X, y, intercept=True, guard=True), p + 2
+        init = np.c_[rng.normal(0, 0.1, (C, k - 1)), np.full(C, 3.0)]
+        lb = np.full(k, -A.DBL_MAX); lb[-1] = 0.0
+        spec = dict(type=A.KERNEL_NMIRROR, k=k, mu=0.0, scale=0.05, warmup=30, arate=0.4, lb=lb, ub=A.DBL_MAX,
+                    nadapt=np.array([10, 20, 30]))
+    g, o, _ = run_both(oracle, fam, spec, init, 60, C, rng=rng)
+    assert g[0]["report"].path == 3
+    assert_parity(g[0], o[0], RTOL, f"{family}/p={p}")
 
 
 @pytest.mark.parametrize("kname", ["normal", "adapt", "ram", "nmirror", "normal_reflective"])
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 def test_philox_stream_matches_oracle(oracle, readme_data, kname, path):
     """Production streams: the device Philox4x32-10 + AS241 inversion is the oracle's, so whole
     runs agree (up to libm ulps in log/qnorm tails; a flipped decision would show up as O(1) error)."""
