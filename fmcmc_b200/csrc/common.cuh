@@ -46,6 +46,7 @@ struct ModelParams {
   const double* y;  // [ld]
   const int* group; // [ld]
   double h0, h1;
+  const double* Xt;      // tile-major copy of X / y for the DMMA kernel (tiled_mma.cuh), or null
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
 };
 

@@ -68,7 +68,8 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group, sp_tab;
+  DevBuf X, y, group, sp_tab, Xt;
+  int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
@@ -234,7 +235,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->Xt, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
@@ -402,6 +403,29 @@ static MmaShape mma_shape(int p_x, int variant) {
   if (p_x <= 64) return MmaShape{64, 8, 4, 1};
   return variant == 1 ? MmaShape{128, 8, 2, 1} : MmaShape{128, 8, 2, 2};
 }
+// Builds the tile-major copy of X / y (tiled_mma.cuh) once per model.
+static cudaError_t ensure_packed_tiles(fmcmc_model* m, int PB) {
+  if (m->xt_PB == PB) return cudaSuccess;
+  const ModelParams& mp = m->mp;
+  const int TR = PB <= 32 ? 128 : (PB == 64 ? 64 : 32);
+  const long long ntiles = (mp.n + TR - 1) / TR;
+  const size_t stage_doubles = (size_t)PB * (TR + 4) + TR;
+  cudaError_t e = ensure(m->Xt, (size_t)ntiles * stage_doubles * 8);
+  if (e != cudaSuccess) return e;
+  double* xt = m->Xt.as<double>();
+  switch (PB) {
+    case 32: pack_tiles_kernel<32><<<(unsigned)ntiles, 256, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, mp.p_x, xt); break;
+    case 64: pack_tiles_kernel<64><<<(unsigned)ntiles, 256, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, mp.p_x, xt); break;
+    case 128: pack_tiles_kernel<128><<<(unsigned)ntiles, 256, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, mp.p_x, xt); break;
+    default: return cudaErrorInvalidValue;
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  m->mp.Xt = xt;
+  m->xt_PB = PB;
+  return cudaSuccess;
+}
+
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 grid, const RunBuffers& rb,
                                     const TiledBuffers& tb) {
@@ -630,16 +654,27 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const MmaShape msh = mma_shape(mp.p_x, m->mma_wide);
     const int cpb = path == 3 ? msh.warps * msh.NT * 8 : TL_CHAINS;       // chains per CTA
     const int tile_rows = path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE;
+    if (path == 3) {
+      cudaError_t pe = ensure_packed_tiles(m, msh.PB);
+      if (pe == cudaErrorMemoryAllocation) { set_err(err, errlen, "out of device memory for the tile-major copy of X"); return FMCMC_ENOMEM; }
+      if (pe != cudaSuccess) { set_err(err, errlen, "CUDA error %s (pack_tiles)", cudaGetErrorString(pe)); return FMCMC_ECUDA; }
+    }
     TiledBuffers tb{};
     tb.ncols = is_ram ? 2 * C : C;
     const int chain_blocks = (tb.ncols + cpb - 1) / cpb;
     const long long ntiles = (mp.ld + tile_rows - 1) / tile_rows;
     int gx = std::max(1, m->sm_count / chain_blocks);
+    if (path == 3) {  // gx * chain_blocks = a whole number of waves of one CTA per SM (148 / gcd slices)
+      int a = chain_blocks, b = m->sm_count;
+      while (b) { const int r = a % b; a = b; b = r; }
+      gx = m->sm_count / a;
+    }
     if (gx > ntiles) gx = (int)ntiles;
     tb.gx = gx;
+    tb.cb = chain_blocks;
     CU_CHECK(ensure(m->partial, (size_t)gx * tb.ncols * 8));
     tb.partial = m->partial.as<double>();
-    const dim3 lgrid(gx, chain_blocks);
+    const dim3 lgrid = path == 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const size_t hsmem = (size_t)TL_HEAD_WARPS * 4 * k * 8;
     if (m->hot_ev.empty()) {

@@ -32,6 +32,7 @@
 struct TiledBuffers {
   double* partial;  // [gx][ncols]
   int gx;           // observation slices (gridDim.x of tiled_loglik)
+  int cb;           // chain blocks (DMMA kernel: 1-D grid of gx * cb CTAs, chain block fastest)
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
 };
 

@@ -39,6 +39,32 @@ struct MmaGeom {
   static constexpr int STAGE_DOUBLES = PB * CS + TR;
 };
 
+// ---- tile-major copy of X / y in HBM ---------------------------------------------------------------
+// The DMMA kernel's pipeline stage is stored in HBM exactly as it sits in shared memory: for tile i,
+//   Xt[i] = { PB columns x CS rows (rows >= TR and columns >= p_x are zero padding), y[TR] }
+// so that ONE cp.async.bulk of STAGE_DOUBLES * 8 bytes (35-37 KB) fills a stage.  Built once per model
+// (fmcmc_run, first DMMA launch).  Without it a stage takes p_x + 1 column copies of TR * 8 bytes
+// (127 x 256 B at p_x = 127), all issued by one thread: that was the bottleneck of config 5 (38 % of the
+// FP64 roof, profiles/r01_bench_v2_dmma_cfg5_first.json).
+template <int PB>
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                         long long n, long long ld, int p_x, double* __restrict__ Xt) {
+  using G = MmaGeom<PB>;
+  const long long tile = blockIdx.x, row0 = tile * G::TR;
+  double* dst = Xt + (size_t)tile * G::STAGE_DOUBLES;
+  for (int e = threadIdx.x; e < G::STAGE_DOUBLES; e += blockDim.x) {
+    double v = 0.0;
+    if (e < PB * G::CS) {
+      const int j = e / G::CS, r = e % G::CS;
+      if (j < p_x && r < G::TR && row0 + r < n) v = X[(size_t)j * ld + row0 + r];
+    } else {
+      const int r = e - PB * G::CS;
+      if (row0 + r < n) v = y[row0 + r];
+    }
+    dst[e] = v;
+  }
+}
+
 template <int PB>
 __host__ __device__ inline size_t tiled_mma_smem_bytes(int family) {
   return 128 + (size_t)TL_STAGES * MmaGeom<PB>::STAGE_DOUBLES * sizeof(double) +
@@ -62,13 +88,16 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   if (err[0] != 0) return;
+  // 1-D grid of gx * cb CTAs, chain block fastest: CTAs that run at the same time stream the SAME
+  // observation slices, so X comes from HBM once per step and from L2 for the other chain blocks
+  const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
   double2* sp_tab = reinterpret_cast<double2*>(stage0 + (size_t)TL_STAGES * STAGE_DOUBLES);
   if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
     const double2* gt = reinterpret_cast<const double2*>(mp.sp_tab);
     for (int e = tid; e < FM_SP_ENTRIES; e += NTHREADS) sp_tab[e] = gt[e];
   }
 
-  const long long ntiles = (mp.ld + TR - 1) / TR;
+  const long long ntiles = (mp.n + TR - 1) / TR;
   const int p_x = mp.p_x;
 
   if (tid == 0) {
@@ -78,25 +107,17 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
     }
     mbar_fence_init();
   }
-  // columns >= p_x of every stage are never written by TMA: zero them once (Theta is 0 there too)
-  for (int s = 0; s < TL_STAGES; s++)
-    for (int e = p_x * CS + tid; e < PB * CS; e += NTHREADS) stage0[(size_t)s * STAGE_DOUBLES + e] = 0.0;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  auto issue = [&](long long tile, int s) {  // executed by thread 0 only
-    const long long row0 = tile * TR;
-    const long long rows = min((long long)TR, mp.ld - row0);
-    const uint32_t bytes = (uint32_t)(rows * 8);
-    double* dst = stage0 + (size_t)s * STAGE_DOUBLES;
-    mbar_expect_tx(&full[s], bytes * (uint32_t)(p_x + 1));
-    for (int j = 0; j < p_x; j++) bulk_g2s(dst + (size_t)j * CS, mp.X + (size_t)j * mp.ld + row0, bytes, &full[s]);
-    bulk_g2s(dst + (size_t)PB * CS, mp.y + row0, bytes, &full[s]);
+  auto issue = [&](long long tile, int s) {  // executed by thread 0 only: one bulk copy per stage (tile-major Xt)
+    constexpr uint32_t BYTES = (uint32_t)(STAGE_DOUBLES * sizeof(double));
+    mbar_expect_tx(&full[s], BYTES);
+    bulk_g2s(stage0 + (size_t)s * STAGE_DOUBLES, mp.Xt + (size_t)tile * STAGE_DOUBLES, BYTES, &full[s]);
   };
 
   // ---- B fragments: Theta of this warp's NT chain tiles, in registers for the whole launch ----
   const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
-  const int chain0 = blockIdx.y * CPB + warp * (NT * 8);
+  const int chain0 = chain_block * CPB + warp * (NT * 8);
   auto theta_of = [&](int col) -> const double* {
     if (col >= tb.ncols) return nullptr;
     return col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
@@ -119,7 +140,7 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   }
 
   // ---- pipeline prologue -----------------------------------------------------------
-  const long long first = blockIdx.x, step = gridDim.x;
+  const long long first = slice, step = tb.gx;
   if (tid == 0) {
     long long tl = first;
     for (int s = 0; s < TL_STAGES && tl < ntiles; s++, tl += step) issue(tl, s);
@@ -177,7 +198,7 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
         }
       }
     } else {
-      for (int o = 0; o < valid; o += 8) {  // rows >= valid hold stale (finite or not) data: selected away
+      for (int o = 0; o < valid; o += 8) {  // rows >= valid are zero padding (eta = intercept): selected away
         double c[NT][2];
 #pragma unroll
         for (int ct = 0; ct < NT; ct++) { c[ct][0] = cinit[ct][0]; c[ct][1] = cinit[ct][1]; }
@@ -212,6 +233,6 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
       v += __shfl_xor_sync(FM_FULL, v, 8);
       v += __shfl_xor_sync(FM_FULL, v, 16);
       const int col = chain0 + ct * 8 + 2 * t + h;
-      if (g == 0 && col < tb.ncols) tb.partial[(size_t)blockIdx.x * tb.ncols + col] = v;
+      if (g == 0 && col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
     }
 }
