@@ -180,6 +180,7 @@ class Workload:
 
     def __init__(self, key, args):
         self.key = key
+        self.bound = "tensor"
         if key == "cfg3":            # BASELINE configs[2]: the configuration the north_star target is quoted on
             self.family, self.n, self.p_x, self.k = "logistic", N_OBS, P_X, P_X
             self.chains = args.chains or CHAINS_PER_GPU
@@ -195,6 +196,15 @@ class Workload:
             self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 2 * 127 + 4, 0, 127 + 2
             self.label = (f"gaussian_lm n={self.n} k=128 (127 columns + sd) x {self.chains} chains/GPU, kernel_nmirror "
                           "(BASELINE configs[4], one GPU's share)")
+        elif key == "few":           # the reference's typical usage: a handful of chains on a large n (README: 1-4 chains)
+            self.family, self.n, self.p_x, self.k = "logistic", N_OBS, P_X, P_X
+            self.chains = args.chains or 4
+            self.kernel_name = "kernel_adapt(warmup=500, freq=1), timed rows are post-warm-up"
+            self.kwarm = KERNEL_WARMUP
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 2 * P_X + 6, 2, 51
+            self.bound = "hbm"
+            self.label = (f"logistic n={self.n} p={self.p_x} x {self.chains} chains/GPU, kernel_adapt (few-chain regime: "
+                          "observation-split DMMA mapping, HBM-bound)")
         elif key == "cfg4":          # BASELINE configs[3]: lifeexpect hierarchical normal, 4096 chains, kernel_ram
             self.family, self.n, self.p_x, self.k = "hier", 1000, 0, 7
             self.chains = args.chains or 4096
@@ -218,7 +228,7 @@ class Workload:
         """Returns (family, device_ptrs or None, kernel, init[C][k], host X / y or None)."""
         C, k = self.chains, self.k
         rng = np.random.default_rng(1000 + rank)
-        if self.key == "cfg3":
+        if self.key in ("cfg3", "few"):
             X, y = make_data()
             fam = fm.ll_logistic(X, y, prior_sd=2.0)
             return fam, None, fm.kernel_adapt(), rng.normal(0, 0.1, (C, k)), (X, y)
@@ -261,7 +271,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg1"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg1", "few"],
                     help="cfg3 = BASELINE configs[2] (default, the metric's configuration); cfg5 = configs[4] per-GPU share")
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
     ap.add_argument("--n", type=int, default=None, help="observations (cfg5 only; default 1e7)")
@@ -270,7 +280,7 @@ def main():
                     help="prime abs_iter instead of running the kernel's 500 warm-up rows (profiling runs)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {"cfg3": 100, "cfg5": 5, "cfg4": 1000, "cfg1": 10000}[args.workload]
+        args.steps = {"cfg3": 100, "cfg5": 5, "cfg4": 1000, "cfg1": 10000, "few": 1000}[args.workload]
     args.steps = max(args.steps, 2)
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -438,25 +448,29 @@ def main():
                             "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows"},
             "gpu_launches": launches,
             "wall_ms_per_step": 1e3 * t_wall / K,
-            # The dominant kernel is bound by the FP64 pipe (DFMA / DMMA share one 64-lane datapath per SM; tcgen05
-            # has no FP64 kind), not by HBM: arithmetic intensity ~ C/4 flop/B vs a ridge of ~6.
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": TRAFFIC_PER_LAUNCH.get((wl.key, path)),
-                         "kernel": kname, "launch_ms": hot_ms,
-                         "peak_source": "FP64 DFMA/DMMA peak measured live by fmcmc_measure_fp64_peak (MEASURED_PEAKS.json "
-                                        "has no FP64 figure; the bf16 tcgen05 peak does not apply to FP64)",
-                         "algorithmic_flops_per_launch": flops,
-                         "flops_per_eval": wl.flops_per_eval, "transcendentals_per_eval_not_counted": wl.transc_per_eval,
-                         "fp64_pipe_util": pipe_util,
-                         "fp64_pipe_util_note": f"{wl.fp64_instr_per_eval} FP64-pipe instruction slots per eval (DMMA = 8 slots) x evals / "
-                                                "(148 SMs x 2 warp-instr/clk x SM clock)"},
-            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "north_star asks for the HBM fraction: structurally ~1 % because X is read once per step and "
-                            "shared by every resident chain"},
+            "roofline": None, "roofline_other": None,
             "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * world},
             "clocks": clocks,
         }
+        # The many-chain kernel is bound by the FP64 pipe (DFMA / DMMA share one 64-lane datapath per SM; tcgen05 has
+        # no FP64 kind), not by HBM: arithmetic intensity ~ C/4 flop/B vs a ridge of ~6.  With a handful
+        # of chains (workload "few") the same kernel family is HBM-bound instead.
+        fp64_roof = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": TRAFFIC_PER_LAUNCH.get((wl.key, path)),
+                     "kernel": kname, "launch_ms": hot_ms,
+                     "peak_source": "FP64 DFMA/DMMA peak measured live by fmcmc_measure_fp64_peak (MEASURED_PEAKS.json "
+                                    "has no FP64 figure; the bf16 tcgen05 peak does not apply to FP64)",
+                     "algorithmic_flops_per_launch": flops,
+                     "flops_per_eval": wl.flops_per_eval, "transcendentals_per_eval_not_counted": wl.transc_per_eval,
+                     "fp64_pipe_util": pipe_util,
+                     "fp64_pipe_util_note": f"{wl.fp64_instr_per_eval} FP64-pipe instruction slots per eval (DMMA = 8 slots) x evals / "
+                                            "(148 SMs x 2 warp-instr/clk x SM clock)"}
+        hbm_roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "traffic": TRAFFIC_PER_LAUNCH.get((wl.key, path)), "kernel": kname, "launch_ms": hot_ms,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "8 n (p_x + 1) + 8 C (3k + 2) bytes per launch (SURVEY §8d).  With many chains this fraction is "
+                            "structurally ~1 %: X is read once per step and shared by every resident chain"}
+        line["roofline"], line["roofline_other"] = (hbm_roof, fp64_roof) if wl.bound == "hbm" else (fp64_roof, hbm_roof)
         if not args.no_cpu_baseline and world == 1 and host_data is not None:
             X, y = host_data
             threads = os.cpu_count() or 1

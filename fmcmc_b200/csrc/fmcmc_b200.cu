@@ -290,7 +290,6 @@ static int validate_run(const fmcmc_model* m, const fmcmc_run_spec* run, const f
   }
   if (ks->type == FMCMC_KERNEL_ADAPT) {
     if (ks->bw > 0 && ks->bw > ks->warmup) { set_err(err, errlen, "The `warmup` parameter must be greater than `bw`."); return FMCMC_EINVAL; }
-    if (ks->bw > 0) { set_err(err, errlen, "kernel_adapt(bw > 0) (windowed covariance) is not built on the device yet"); return FMCMC_EUNSUP; }
     if (ks->mvn_method != FMCMC_MVN_CHOLESKY) { set_err(err, errlen, "the device draws mvrnorm through the Cholesky factor (FMCMC_MVN_CHOLESKY) only"); return FMCMC_EUNSUP; }
     if (ks->freq < 1) { set_err(err, errlen, "-freq- must be >= 1."); return FMCMC_EINVAL; }
   }
@@ -390,18 +389,24 @@ static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const 
 }
 
 // DMMA variant (tiled_mma.cuh).  Geometry per padded width PB: (warps, chain tiles per warp).
-struct MmaShape { int PB, warps, NT, MO; };
-static MmaShape mma_shape(int p_x, int variant) {
+struct MmaShape { int PB, warps, NT, MO, osplit; };
+// Few columns (chains): all warps share NT*8 chains and split the observations (HBM-bound mapping);
+// many: every warp owns NT*8 chains (FP64-bound mapping).  tiled_mma.cuh explains both.
+static MmaShape mma_shape(int p_x, int ncols, int variant) {
   if (p_x <= 32) {
+    if (ncols <= 8) return MmaShape{32, 8, 1, 2, 1};
+    if (ncols <= 16) return MmaShape{32, 8, 2, 2, 1};
+    if (ncols <= 128) return MmaShape{32, 8, 4, 2, 1};
     switch (variant) {  // measured on B200, cfg3: 3.46 / 3.59 / 3.61 / 3.62 ms per launch (profiles/r01_*)
-      case 1: return MmaShape{32, 8, 4, 2};
-      case 2: return MmaShape{32, 8, 8, 1};
-      case 3: return MmaShape{32, 8, 4, 4};
-      default: return MmaShape{32, 16, 4, 1};
+      case 1: return MmaShape{32, 8, 4, 2, 0};
+      case 2: return MmaShape{32, 8, 8, 1, 0};
+      case 3: return MmaShape{32, 8, 4, 4, 0};
+      default: return MmaShape{32, 16, 4, 1, 0};
     }
   }
-  if (p_x <= 64) return MmaShape{64, 8, 4, 1};
-  return variant == 1 ? MmaShape{128, 8, 2, 1} : MmaShape{128, 8, 2, 2};
+  if (p_x <= 64) return ncols <= 32 ? MmaShape{64, 8, 4, 1, 1} : MmaShape{64, 8, 4, 1, 0};
+  if (ncols <= 16) return MmaShape{128, 4, 2, 1, 1};
+  return variant == 1 ? MmaShape{128, 8, 2, 1, 0} : MmaShape{128, 8, 2, 2, 0};
 }
 // Builds the tile-major copy of X / y (tiled_mma.cuh) once per model.
 static cudaError_t ensure_packed_tiles(fmcmc_model* m, int PB) {
@@ -429,27 +434,32 @@ static cudaError_t ensure_packed_tiles(fmcmc_model* m, int PB) {
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 grid, const RunBuffers& rb,
                                     const TiledBuffers& tb) {
-#define TM_CASE(P, W, N, O)                                                                                      \
-  if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O) {                                                             \
+#define TM_CASE(P, W, N, O, S)                                                                                      \
+  if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O && sh.osplit == (S ? 1 : 0)) {                                                             \
     const size_t smem = tiled_mma_smem_bytes<P>(FAMILY);                                                         \
     static bool attr_done[64] = {};                                                                              \
     if (!attr_done[m->device]) {                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O>,                    \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S>,                    \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
       attr_done[m->device] = true;                                                                               \
     }                                                                                                            \
-    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
+    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
                                                                                        rb.nchains, tb, rb.err);  \
     return cudaGetLastError();                                                                                   \
   }
-  TM_CASE(32, 8, 4, 2)
-  TM_CASE(32, 8, 4, 4)
-  TM_CASE(32, 8, 8, 1)
-  TM_CASE(32, 16, 4, 1)
-  TM_CASE(64, 8, 4, 1)
-  TM_CASE(128, 8, 2, 1)
-  TM_CASE(128, 8, 2, 2)
+  TM_CASE(32, 8, 1, 2, true)
+  TM_CASE(32, 8, 2, 2, true)
+  TM_CASE(32, 8, 4, 2, true)
+  TM_CASE(32, 8, 4, 2, false)
+  TM_CASE(32, 8, 4, 4, false)
+  TM_CASE(32, 8, 8, 1, false)
+  TM_CASE(32, 16, 4, 1, false)
+  TM_CASE(64, 8, 4, 1, true)
+  TM_CASE(64, 8, 4, 1, false)
+  TM_CASE(128, 4, 2, 1, true)
+  TM_CASE(128, 8, 2, 1, false)
+  TM_CASE(128, 8, 2, 2, false)
 #undef TM_CASE
   return cudaErrorInvalidValue;
 }
@@ -623,7 +633,11 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   if (path == 1) {
     // ---- path 1: chain-resident fused kernel, one launch per bulk -------------------------
     const bool wpc = C >= 2 * m->sm_count;
-    const int chain_smem_doubles = 7 * k;
+    // shared-memory matrix scratch of the adaptive kernels (4 kf^2 doubles per chain) when it is small enough
+    const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
+    const size_t mat_bytes = adaptive ? (size_t)4 * kf * kf * 8 : 0;
+    const int mat_doubles = (mat_bytes && mat_bytes <= (wpc ? (size_t)8 * 1024 : (size_t)40 * 1024)) ? 4 * kf * kf : 0;
+    const int chain_smem_doubles = 7 * k + mat_doubles;
     int threads, chains_per_block;
     if (wpc) { threads = 256; chains_per_block = threads / 32; }
     else {
@@ -641,18 +655,19 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const int blocks = (C + chains_per_block - 1) / chains_per_block;
     if (wpc) {
       CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_resident_kernel<true><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles);
+      mh_resident_kernel<true><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles, mat_doubles);
     } else {
       CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_resident_kernel<false><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles);
+      mh_resident_kernel<false><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles, mat_doubles);
     }
     CU_CHECK(cudaGetLastError());
     launches += 1;
   } else {
     // ---- path 2: observation-tiled, two launches per row ------------------------------------
     const int PB = mp.p_x <= 8 ? 8 : (mp.p_x <= 16 ? 16 : 32);
-    const MmaShape msh = mma_shape(mp.p_x, m->mma_wide);
-    const int cpb = path == 3 ? msh.warps * msh.NT * 8 : TL_CHAINS;       // chains per CTA
+    const int ncols_all = is_ram ? 2 * C : C;
+    const MmaShape msh = mma_shape(mp.p_x, ncols_all, m->mma_wide);
+    const int cpb = path == 3 ? (msh.osplit ? msh.NT * 8 : msh.warps * msh.NT * 8) : TL_CHAINS;   // chains per CTA
     const int tile_rows = path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE;
     if (path == 3) {
       cudaError_t pe = ensure_packed_tiles(m, msh.PB);
@@ -663,12 +678,10 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     tb.ncols = is_ram ? 2 * C : C;
     const int chain_blocks = (tb.ncols + cpb - 1) / cpb;
     const long long ntiles = (mp.ld + tile_rows - 1) / tile_rows;
-    int gx = std::max(1, m->sm_count / chain_blocks);
-    if (path == 3) {  // gx * chain_blocks = a whole number of waves of one CTA per SM (148 / gcd slices)
-      int a = chain_blocks, b = m->sm_count;
-      while (b) { const int r = a % b; a = b; b = r; }
-      gx = m->sm_count / a;
-    }
+    // One observation slice per SM, whatever the number of chains: chain_blocks waves of sm_count CTAs.  Keeping
+    // gx independent of C makes the summation tree - hence every log-posterior bit - independent of how the
+    // chains are sharded over calls / GPUs (as long as the same mapping, chain- or observation-split, is used).
+    int gx = m->sm_count;
     if (gx > ntiles) gx = (int)ntiles;
     tb.gx = gx;
     tb.cb = chain_blocks;
@@ -676,13 +689,17 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     tb.partial = m->partial.as<double>();
     const dim3 lgrid = path == 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
-    const size_t hsmem = (size_t)TL_HEAD_WARPS * 4 * k * 8;
+    const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
+    const size_t mat_bytes = adaptive ? (size_t)4 * kf * kf * 8 : 0;
+    const int mat_doubles = (mat_bytes && mat_bytes <= (size_t)40 * 1024) ? 4 * kf * kf : 0;
+    const size_t hsmem = (size_t)TL_HEAD_WARPS * (4 * k + mat_doubles) * 8;
+    if (hsmem > 48 * 1024) CU_CHECK(cudaFuncSetAttribute(tiled_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
     if (m->hot_ev.empty()) {
       m->hot_ev.resize(2 * FM_HOT_EVENTS);
       for (auto& e : m->hot_ev) CU_CHECK(cudaEventCreate(&e));
     }
     for (long long row = 1; row <= T + 1; row++) {
-      tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row);
+      tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row, mat_doubles);
       launches += 1;
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;

@@ -24,6 +24,8 @@ struct ChainCtx {
   double* scr;            // shared-memory scratch, >= 4*k doubles, private to the warp
   const double* ans;      // this run's ans buffer base ([T][C][k]); row r (1-based) of chain c at
   long long ans_stride;   //   ans[(r-1)*ans_stride + c*k + j], ans_stride = C*k
+  double* mat;            // shared-memory matrix scratch private to the warp (4 kf^2 doubles) or null: the
+                          //   factorisations then run in global memory (rb.work), ~20x the latency per access
 };
 
 __device__ __forceinline__ const double* ans_row(const ChainCtx& cx, const KParams& kp, long long r) {
@@ -114,7 +116,7 @@ __device__ int ram_adapt_warp(const KParams& kp, const RunBuffers& rb, const Cha
   const int kf = kp.kf;
   double* S = rb.dstate + (size_t)cx.c * kp.dlen;
   const double* U = rb.ubuf + (size_t)cx.c * kf;
-  double* Mid = rb.work + (size_t)cx.c * rb.worklen;  // 4 * kf*kf doubles of scratch
+  double* Mid = cx.mat ? cx.mat : rb.work + (size_t)cx.c * rb.worklen;  // 4 * kf*kf doubles of scratch
   double* T1 = Mid + kf * kf;
   double* Mx = T1 + kf * kf;
   double* L = Mx + kf * kf;
@@ -242,10 +244,38 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
         __syncwarp();
       }
       if (kp.until > (double)abs_iter && abs_iter > kp.warmup && i > 2 && (i % kp.freq) == 0) {  // :118
-        if (kp.bw > 0) return FMCMC_EUNSUP;
         double* x = cx.scr;
         double* m = cx.scr + kf;
         double* mp = cx.scr + 2 * kf;
+        if (kp.bw > 0) {  // :119-125 windowed: Sigma <- Sd * (cov(ans[(i-bw+1):(i-1), which.]) + Ik)
+          const long long r0 = i - kp.bw + 1, r1 = i - 1;
+          if (r0 < 1) return FMCMC_EUNSUP;  // the reference indexes row <= 0 here
+          const double nr = (double)(r1 - r0 + 1);
+          const double Sd = kp.Sd > 0.0 ? kp.Sd : 5.76 / kf;
+          for (int a = lane; a < kf; a += FM_WARP) {  // column means of the window (Neumaier-compensated)
+            double hi = 0.0, lo = 0.0;
+            for (long long r = r0; r <= r1; r++) {
+              const double v = ans_row(cx, kp, r)[kp.free_idx[a]];
+              const double sum = xadd(hi, v), bp = xsub(sum, hi);
+              lo = xadd(lo, xadd(xsub(hi, xsub(sum, bp)), xsub(v, bp)));
+              hi = sum;
+            }
+            m[a] = xdiv(xadd(hi, lo), nr);
+          }
+          __syncwarp();
+          for (int e = lane; e < kf * kf; e += FM_WARP) {
+            const int a = e % kf, b = e / kf;
+            const int ja = kp.free_idx[a], jb = kp.free_idx[b];
+            const double ma = m[a], mb = m[b];
+            double sacc = 0.0;
+            for (long long r = r0; r <= r1; r++) {
+              const double* xr = ans_row(cx, kp, r);
+              sacc = fma(xr[ja] - ma, xr[jb] - mb, sacc);
+            }
+            Sigma[e] = xmul(Sd, xadd(xdiv(sacc, nr - 1.0), a == b ? kp.eps : 0.0));
+          }
+          __syncwarp();
+        } else {
         if (!(flags & FMCMC_STATE_HAS_MEAN)) {  // :130-131
           // colMeans(): R accumulates in long double; the running column sum is kept as a
           // compensated (hi, lo) pair so the mean is the correctly rounded one as well
@@ -286,11 +316,23 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
           for (int a = lane; a < kf; a += FM_WARP) Mean_prev[a] = m[a];
           __syncwarp();
         }
+        }  // bw <= 0
         dirty = true;
       }
       abs_iter += 1;  // :170
+      const double* Lr = L;  // factor the matvec below reads
       if (dirty) {
-        if (chol_lower_warp(kf, Sigma, L, lane)) return FMCMC_ENOTPD;  // mvrnorm: "'Sigma' is not positive definite"
+        if (cx.mat) {  // factorise in shared memory, keep a copy in HBM for the rows that do not re-adapt
+          double* As = cx.mat;
+          double* Ls = cx.mat + (size_t)kf * kf;
+          for (int e = lane; e < kf * kf; e += FM_WARP) As[e] = Sigma[e];
+          __syncwarp();
+          if (chol_lower_warp(kf, As, Ls, lane)) return FMCMC_ENOTPD;
+          for (int e = lane; e < kf * kf; e += FM_WARP) L[e] = Ls[e];
+          Lr = Ls;
+        } else if (chol_lower_warp(kf, Sigma, L, lane)) {
+          return FMCMC_ENOTPD;  // mvrnorm: "'Sigma' is not positive definite"
+        }
         if (lane == 0) *cflag |= 2;
       }
       double* z = cx.scr + 3 * kf;
@@ -299,7 +341,7 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       __syncwarp();
       for (int a = lane; a < kf; a += FM_WARP) {  // :173-180
         double s = 0.0;
-        for (int b = 0; b <= a; b++) s = xadd(s, xmul(L[a + b * kf], z[b]));
+        for (int b = 0; b <= a; b++) s = xadd(s, xmul(Lr[a + b * kf], z[b]));
         const int w = kp.free_idx[a];
         th1[w] = reflect1(xadd(th0[w], xadd(kp.mu[w], s)), kp.lb[w], kp.ub[w]);
       }

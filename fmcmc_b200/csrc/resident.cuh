@@ -38,7 +38,7 @@ __device__ __forceinline__ double group_reduce(double v, double* red, int& parit
 template <bool WPC>
 __global__ void __launch_bounds__(256)
 mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, const double* initial,
-                   int data_in_smem, int chain_smem_doubles) {
+                   int data_in_smem, int chain_smem_doubles, int mat_doubles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sm = reinterpret_cast<double*>(smem_raw + 128);
@@ -126,6 +126,7 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
   ChainCtx cx;
   cx.c = c; cx.theta0 = th0; cx.theta1 = th1; cx.theta1u = th1u; cx.scr = scr;
   cx.ans = rb.ans; cx.ans_stride = (long long)rb.nchains * k;
+  cx.mat = mat_doubles ? scr + 4 * k : nullptr;  // chain_smem_doubles = 7k + mat_doubles
 
   // ---- rows 2..T: R/mcmc.R:749-783 ----------------------------------------------
   for (long long i = 2; i <= rb.T; i++) {

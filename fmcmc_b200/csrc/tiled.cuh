@@ -193,13 +193,13 @@ __device__ __forceinline__ double reduce_partials(const TiledBuffers& tb, long l
 // Finishes row `row - 1` and proposes row `row` (1 <= row <= T + 1).
 __global__ void __launch_bounds__(TL_HEAD_WARPS * 32)
 tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, TiledBuffers tb,
-                  const double* initial, long long row) {
+                  const double* initial, long long row, int mat_doubles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long c = (long long)blockIdx.x * TL_HEAD_WARPS + warp;
   if (c >= rb.nchains || rb.err[0] != 0) return;
   const int k = kp.k;
-  double* scr = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 4 * k;
+  double* scr = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (4 * k + mat_doubles);
   double* th0 = rb.cur_theta + (size_t)c * k;
   double* th1 = rb.prop + (size_t)c * k;
   double* th1u = rb.prop_u + (size_t)c * k;
@@ -220,6 +220,7 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
   ChainCtx cx;
   cx.c = c; cx.theta0 = th0; cx.theta1 = th1; cx.theta1u = th1u; cx.scr = scr;
   cx.ans = rb.ans; cx.ans_stride = (long long)rb.nchains * k;
+  cx.mat = mat_doubles ? scr + 4 * k : nullptr;
 
   // ---- finish row r = row - 1 -------------------------------------------------------
   const long long r = row - 1;

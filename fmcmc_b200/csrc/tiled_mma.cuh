@@ -71,16 +71,23 @@ __host__ __device__ inline size_t tiled_mma_smem_bytes(int family) {
          (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0);
 }
 
-template <int FAMILY, int PB, bool YBIN, int NWARPS, int NT, int MO>
+// OSPLIT = false: the CTA's warps own different chains (NWARPS * NT * 8 chains per CTA) and every warp walks
+//                 all observations of the CTA's slice — the many-chain mapping (configs 3, 5).
+// OSPLIT = true : all warps share the same NT * 8 chains and split the observation tiles of a stage between
+//                 them — the few-chain mapping (the reference's typical 1-4 chains on a huge n).  With <= 16
+//                 chains the FP64 work per observation drops below the time HBM needs to deliver it, and the
+//                 kernel becomes HBM-bound: X streams through the TMA pipeline at the memory roof.
+template <int FAMILY, int PB, bool YBIN, int NWARPS, int NT, int MO, bool OSPLIT>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
                         TiledBuffers tb, const int* __restrict__ err) {
   using G = MmaGeom<PB>;
   constexpr int TR = G::TR, CS = G::CS, KS = G::KS, STAGE_DOUBLES = G::STAGE_DOUBLES;
   constexpr int NTHREADS = NWARPS * 32;
-  constexpr int CPB = NWARPS * NT * 8;  // chains per CTA
+  constexpr int CPB = OSPLIT ? NT * 8 : NWARPS * NT * 8;  // chains per CTA
+  constexpr int OSTEP = OSPLIT ? NWARPS * 8 * MO : 8 * MO;  // observations between two blocks of one warp
   static_assert(NT * KS <= 64, "B fragments must fit in registers");
-  static_assert(TR % (8 * MO) == 0, "tile rows must be a multiple of the observation block");
+  static_assert(TR % OSTEP == 0, "tile rows must be a multiple of the observation block");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + TL_STAGES;
@@ -117,7 +124,8 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
 
   // ---- B fragments: Theta of this warp's NT chain tiles, in registers for the whole launch ----
   const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
-  const int chain0 = chain_block * CPB + warp * (NT * 8);
+  const int chain0 = chain_block * CPB + (OSPLIT ? 0 : warp * (NT * 8));
+  const int ofirst = OSPLIT ? warp * 8 * MO : 0;
   auto theta_of = [&](int col) -> const double* {
     if (col >= tb.ncols) return nullptr;
     return col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
@@ -171,7 +179,7 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
     const double* Ag = Xs + t * CS + g;                        // this lane's A-fragment column / row
     if (valid == TR) {
 #pragma unroll 1
-      for (int o = 0; o < TR; o += 8 * MO) {  // MO observation tiles x NT chain tiles = MO*NT independent DMMA chains
+      for (int o = ofirst; o < TR; o += OSTEP) {  // MO observation tiles x NT chain tiles = MO*NT independent DMMA chains
         double c[MO][NT][2];
 #pragma unroll
         for (int mo = 0; mo < MO; mo++)
@@ -198,7 +206,7 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
         }
       }
     } else {
-      for (int o = 0; o < valid; o += 8) {  // rows >= valid are zero padding (eta = intercept): selected away
+      for (int o = OSPLIT ? warp * 8 : 0; o < valid; o += OSPLIT ? NWARPS * 8 : 8) {  // rows >= valid: zero padding, selected away
         double c[NT][2];
 #pragma unroll
         for (int ct = 0; ct < NT; ct++) { c[ct][0] = cinit[ct][0]; c[ct][1] = cinit[ct][1]; }
@@ -224,6 +232,8 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   }
 
   // ---- reduce over the 8 observation rows (lanes with equal t), write the CTA's partial sums ----
+  double* red = stage0;  // OSPLIT: [NWARPS][NT * 8] cross-warp staging; the pipeline stages are drained by now
+  if (OSPLIT) __syncthreads();
 #pragma unroll
   for (int ct = 0; ct < NT; ct++)
 #pragma unroll
@@ -232,7 +242,21 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
       v += __shfl_xor_sync(FM_FULL, v, 4);
       v += __shfl_xor_sync(FM_FULL, v, 8);
       v += __shfl_xor_sync(FM_FULL, v, 16);
-      const int col = chain0 + ct * 8 + 2 * t + h;
-      if (g == 0 && col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
+      const int lc = ct * 8 + 2 * t + h;
+      if (OSPLIT) {
+        if (g == 0) red[warp * (NT * 8) + lc] = v;
+      } else {
+        const int col = chain0 + lc;
+        if (g == 0 && col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
+      }
     }
+  if (OSPLIT) {
+    __syncthreads();
+    if (tid < NT * 8) {
+      double v = 0.0;
+      for (int w = 0; w < NWARPS; w++) v += red[w * (NT * 8) + tid];  // fixed order: deterministic
+      const int col = chain0 + tid;
+      if (col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
+    }
+  }
 }

@@ -27,6 +27,7 @@ def _kernels(k):
         "unif_reflective": dict(type=A.KERNEL_UNIF_REFLECTIVE, k=k, min_=-0.5, max_=0.5, lb=lb, ub=6.0),
         "adapt": dict(type=A.KERNEL_ADAPT, k=k, mu=0.0, warmup=50, freq=1, eps=1e-4, lb=lb, ub=A.DBL_MAX),
         "adapt_freq3": dict(type=A.KERNEL_ADAPT, k=k, mu=0.0, warmup=40, freq=3, eps=1e-4, lb=lb, ub=A.DBL_MAX),
+        "adapt_bw30": dict(type=A.KERNEL_ADAPT, k=k, mu=0.0, warmup=45, freq=2, bw=30, eps=1e-4, lb=lb, ub=A.DBL_MAX),
         "ram": dict(type=A.KERNEL_RAM, k=k, warmup=0, freq=1, eps=1e-2, arate=0.234, lb=lb, ub=A.DBL_MAX),
         "nmirror": dict(type=A.KERNEL_NMIRROR, k=k, mu=0.0, scale=0.5, warmup=100, arate=0.4, lb=lb, ub=A.DBL_MAX,
                         nadapt=np.array([25, 50, 75, 100])),
@@ -194,6 +195,30 @@ def test_tiled_wide_design_matrix(oracle, family, p):
     g, o, _ = run_both(oracle, fam, spec, init, 60, C, rng=rng)
     assert g[0]["report"].path == 3
     assert_parity(g[0], o[0], RTOL, f"{family}/p={p}")
+
+
+@pytest.mark.parametrize("family,p,C", [("logistic", 32, 1), ("logistic", 9, 5), ("logistic", 20, 12), ("gaussian", 6, 3),
+                                        ("gaussian", 100, 2), ("logistic", 127, 16), ("gaussian", 60, 30)])
+def test_tiled_few_chains(oracle, family, p, C):
+    """Few chains on a large n (the reference's typical usage): the DMMA kernel's observation-split mapping —
+    all warps share the chains and split the observations of each stage; cross-warp reduction in fixed order."""
+    rng = np.random.default_rng(66)
+    n = 3000 + 41
+    if family == "logistic":
+        fam, k = _logistic_family(rng, n, p), p
+        init = rng.normal(0, 0.05, (C, k))
+        spec = dict(type=A.KERNEL_ADAPT, k=k, mu=0.0, warmup=15, freq=1, eps=1e-4)
+    else:
+        from fmcmc_b200 import ll_gaussian_lm
+        X = rng.standard_normal((n, p))
+        y = 1.0 + X @ rng.standard_normal(p) + rng.normal(0, 2.0, n)
+        fam, k = ll_gaussian_lm(X, y, intercept=True, guard=True), p + 2
+        init = np.c_[rng.normal(0, 0.1, (C, k - 1)), np.full(C, 3.0)]
+        lb = np.full(k, -A.DBL_MAX); lb[-1] = 0.0
+        spec = dict(type=A.KERNEL_RAM, k=k, warmup=0, freq=1, eps=1e-3, arate=0.234, lb=lb, ub=A.DBL_MAX)
+    g, o, _ = run_both(oracle, fam, spec, init, 50, C, rng=rng, path=3)
+    assert g[0]["report"].path == 3
+    assert_parity(g[0], o[0], RTOL, f"{family}/p={p}/C={C}")
 
 
 @pytest.mark.parametrize("kname", ["normal", "adapt", "ram", "nmirror", "normal_reflective"])
