@@ -643,6 +643,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     else {
       long long want = (mp.n + 3) / 4;
       threads = (int)std::min<long long>(256, std::max<long long>(32, ((want + 31) / 32) * 32));
+      if (const char* v = getenv("FMCMC_RES_THREADS")) { const int t = atoi(v); if (t >= 32 && t <= 256 && t % 32 == 0) threads = t; }  // tuning only
       chains_per_block = 1;
     }
     const size_t chain_bytes = (size_t)chains_per_block * chain_smem_doubles * 8 + 2 * RES_MAX_WARPS * 8 + 128;

@@ -446,26 +446,28 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
   return FMCMC_EINVAL;
 }
 
-// Accept / reject + bookkeeping for row i (lane 0 of the chain's warp, or any single
-// thread).  R/mcmc.R:752-778.  th0/th1 are the chain's state vectors (any address
-// space); returns the (possibly updated) f0 or NaN after an error.
-__device__ __forceinline__ double accept_row(const KParams& kp, const StreamParams& sp, const RunBuffers& rb,
-                                             long long c, long long i, double* th0, const double* th1,
-                                             double f0, double f1, unsigned long long& n_acc, bool& failed) {
+// Accept / reject + bookkeeping for row i, executed by ALL 32 lanes of the chain's warp (coordinates are
+// lane-strided: the chain state may live in HBM, where a serial loop costs one L2 round trip per
+// coordinate).  R/mcmc.R:752-778.  th0/th1 are the chain's state vectors (any address space); returns the
+// (possibly updated) f0, warp-uniform.  n_acc is only meaningful in lane 0.
+__device__ __forceinline__ double accept_row_warp(const KParams& kp, const StreamParams& sp, const RunBuffers& rb,
+                                                  long long c, long long i, double* th0, const double* th1,
+                                                  double f0, double f1, int lane, unsigned long long& n_acc,
+                                                  bool& failed) {
   const int k = kp.k;
   const size_t row_off = ((size_t)(i - 1) * rb.nchains + (size_t)c);
   double* draws = rb.draws + row_off * k;
   double* ans = rb.ans + row_off * k;
-  for (int j = 0; j < k; j++) draws[j] = th1[j];
-  rb.logpost[row_off] = f1;
+  for (int j = lane; j < k; j += FM_WARP) draws[j] = th1[j];
+  if (lane == 0) rb.logpost[row_off] = f1;
   if (isnan(f1)) {  // :758-765
-    set_error(rb.err, FMCMC_ENAN, c + 1, i);
+    if (lane == 0) set_error(rb.err, FMCMC_ENAN, c + 1, i);
     failed = true;
     return f0;
   }
   const double ratio = f1 - f0;  // R/kernel.R:302-303
   if (isnan(ratio)) {            // quirk D10
-    set_error(rb.err, FMCMC_ENANRATIO, c + 1, i);
+    if (lane == 0) set_error(rb.err, FMCMC_ENANRATIO, c + 1, i);
     failed = true;
     return f0;
   }
@@ -477,19 +479,24 @@ __device__ __forceinline__ double accept_row(const KParams& kp, const StreamPara
     philox_u2(sp.seed, (uint32_t)(rb.chain_offset + c), sp.run, (uint32_t)i, 0u, u0, u1);
     logu = log(u0);
   }
-  if (logu < ratio) {  // :770
+  if (logu < ratio) {  // :770 (warp-uniform)
     bool changed = false;
-    for (int j = 0; j < k; j++) {
-      changed |= (th0[j] != th1[j]);
-      th0[j] = th1[j];
+    for (int j = lane; j < k; j += FM_WARP) {
+      const double v = th1[j];
+      changed |= (th0[j] != v);
+      th0[j] = v;
     }
-    if (changed) rb.istate[c * FMCMC_ISTATE_LEN + 3] += 1;
+    changed = __any_sync(FM_FULL, changed);
+    if (lane == 0) {
+      if (changed) rb.istate[c * FMCMC_ISTATE_LEN + 3] += 1;
+      n_acc += 1;
+    }
     f0 = f1;
-    n_acc += 1;
   }
+  __syncwarp();
+  for (int j = lane; j < k; j += FM_WARP) ans[j] = th0[j];
   double* cs = rb.colsum + (size_t)c * 2 * kp.kf;
-  for (int j = 0; j < k; j++) ans[j] = th0[j];
-  for (int a = 0; a < kp.kf; a++) {  // Neumaier two-sum: (hi, lo) += theta0
+  for (int a = lane; a < kp.kf; a += FM_WARP) {  // Neumaier two-sum: (hi, lo) += theta0
     const double x = th0[kp.free_idx[a]], hi = cs[2 * a];
     const double sum = xadd(hi, x);
     const double bp = xsub(sum, hi);
@@ -497,5 +504,6 @@ __device__ __forceinline__ double accept_row(const KParams& kp, const StreamPara
     cs[2 * a] = sum;
     cs[2 * a + 1] = xadd(cs[2 * a + 1], e);
   }
+  __syncwarp();
   return f0;
 }

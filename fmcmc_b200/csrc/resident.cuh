@@ -113,13 +113,15 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
   // reference recomputes at R/mcmc.R:742), so the first likelihood pass is skipped
   double f0 = initial ? loglik(th0) : rb.cur_f[c];
   unsigned long long n_acc = 0;
-  if (leader_warp && lane == 0) {
+  if (leader_warp) {
     const size_t off = (size_t)c;
-    for (int j = 0; j < k; j++) { rb.ans[off * k + j] = th0[j]; rb.draws[off * k + j] = th0[j]; }
-    rb.logpost[off] = f0;
-    for (int a = 0; a < kp.kf; a++) { rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]]; rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0; }
-    rb.istate[c * FMCMC_ISTATE_LEN + 3] = 0;
-    rb.chain_flags[c] = 0;
+    for (int j = lane; j < k; j += FM_WARP) { rb.ans[off * k + j] = th0[j]; rb.draws[off * k + j] = th0[j]; }
+    for (int a = lane; a < kp.kf; a += FM_WARP) { rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]]; rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0; }
+    if (lane == 0) {
+      rb.logpost[off] = f0;
+      rb.istate[c * FMCMC_ISTATE_LEN + 3] = 0;
+      rb.chain_flags[c] = 0;
+    }
   }
   group_sync<WPC>();
 
@@ -158,11 +160,13 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
       group_sync<WPC>();
       if (*gflag == 4) break;
     }
-    if (leader_warp && lane == 0) {
+    if (leader_warp) {
       bool failed = false;
-      f0 = accept_row(kp, sp, rb, c, i, th0, th1, f0, f1, n_acc, failed);
-      scr[0] = f0;
-      *gflag = failed ? 4 : 0;
+      f0 = accept_row_warp(kp, sp, rb, c, i, th0, th1, f0, f1, lane, n_acc, failed);
+      if (lane == 0) {
+        scr[0] = f0;
+        *gflag = failed ? 4 : 0;
+      }
     }
     group_sync<WPC>();
     f0 = scr[0];

@@ -232,14 +232,14 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
     f1 = family_finish(mp, th1, s);
   }
   if (r == 1) {
+    for (int j = lane; j < k; j += FM_WARP) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
+    for (int a = lane; a < kp.kf; a += FM_WARP) {
+      rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]];
+      rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0;
+    }
     if (lane == 0) {
-      for (int j = 0; j < k; j++) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
       rb.logpost[c] = f1;
       rb.cur_f[c] = f1;
-      for (int a = 0; a < kp.kf; a++) {
-        rb.colsum[((size_t)c * kp.kf + a) * 2] = th0[kp.free_idx[a]];
-        rb.colsum[((size_t)c * kp.kf + a) * 2 + 1] = 0.0;
-      }
     }
   } else {
     double f0 = rb.cur_f[c];
@@ -250,17 +250,14 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
       const int rc = ram_adapt_warp(kp, rb, cx, f1u, lane);
       if (rc) { if (lane == 0) set_error(rb.err, rc, c + 1, r); return; }
     }
-    int failed_i = 0;
+    bool failed = false;
+    unsigned long long n_acc = 0;
+    f0 = accept_row_warp(kp, sp, rb, c, r, th0, th1, f0, f1, lane, n_acc, failed);
+    if (failed) return;
     if (lane == 0) {
-      bool failed = false;
-      unsigned long long n_acc = 0;
-      f0 = accept_row(kp, sp, rb, c, r, th0, th1, f0, f1, n_acc, failed);
       rb.cur_f[c] = f0;
       if (n_acc) atomicAdd(rb.n_accept, n_acc);
-      failed_i = failed;
     }
-    failed_i = __shfl_sync(FM_FULL, failed_i, 0);
-    if (failed_i) return;
   }
   __syncwarp();
 
