@@ -654,13 +654,22 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       return FMCMC_EUNSUP;
     }
     const int blocks = (C + chains_per_block - 1) / chains_per_block;
-    if (wpc) {
-      CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_resident_kernel<true><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles, mat_doubles);
-    } else {
-      CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_resident_kernel<false><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0, chain_smem_doubles, mat_doubles);
-    }
+#define RES_LAUNCH(W, K)                                                                                         \
+  do {                                                                                                           \
+    CU_CHECK(cudaFuncSetAttribute(mh_resident_kernel<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mh_resident_kernel<W, K><<<blocks, threads, smem, m->stream>>>(mp, kp, sp, rb, d_initial, in_smem ? 1 : 0,   \
+                                                                   chain_smem_doubles, mat_doubles);             \
+  } while (0)
+#define RES_DISPATCH(W)                                                   \
+  switch (kernel_class(ks->type)) {                                      \
+    case KC_ADAPT: RES_LAUNCH(W, KC_ADAPT); break;                       \
+    case KC_RAM: RES_LAUNCH(W, KC_RAM); break;                           \
+    case KC_MIRROR: RES_LAUNCH(W, KC_MIRROR); break;                     \
+    default: RES_LAUNCH(W, KC_PLAIN); break;                             \
+  }
+    if (wpc) { RES_DISPATCH(true) } else { RES_DISPATCH(false) }
+#undef RES_DISPATCH
+#undef RES_LAUNCH
     CU_CHECK(cudaGetLastError());
     launches += 1;
   } else {
@@ -694,13 +703,32 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const size_t mat_bytes = adaptive ? (size_t)4 * kf * kf * 8 : 0;
     const int mat_doubles = (mat_bytes && mat_bytes <= (size_t)40 * 1024) ? 4 * kf * kf : 0;
     const size_t hsmem = (size_t)TL_HEAD_WARPS * (4 * k + mat_doubles) * 8;
-    if (hsmem > 48 * 1024) CU_CHECK(cudaFuncSetAttribute(tiled_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+    const int kclass = kernel_class(ks->type);
+    auto head_launch = [&](long long row) -> cudaError_t {
+#define HEAD_CASE(K)                                                                                              \
+  case K:                                                                                                          \
+    if (hsmem > 48 * 1024) {                                                                                       \
+      cudaError_t e_ = cudaFuncSetAttribute(tiled_head_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem); \
+      if (e_ != cudaSuccess) return e_;                                                                            \
+    }                                                                                                              \
+    tiled_head_kernel<K><<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row, mat_doubles); \
+    break;
+      switch (kclass) {
+        HEAD_CASE(KC_ADAPT)
+        HEAD_CASE(KC_RAM)
+        HEAD_CASE(KC_MIRROR)
+        default:
+        HEAD_CASE(KC_PLAIN)
+      }
+#undef HEAD_CASE
+      return cudaSuccess;
+    };
     if (m->hot_ev.empty()) {
       m->hot_ev.resize(2 * FM_HOT_EVENTS);
       for (auto& e : m->hot_ev) CU_CHECK(cudaEventCreate(&e));
     }
     for (long long row = 1; row <= T + 1; row++) {
-      tiled_head_kernel<<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row, mat_doubles);
+      { cudaError_t he = head_launch(row); if (he != cudaSuccess) { set_err(err, errlen, "CUDA error %s (tiled_head)", cudaGetErrorString(he)); return FMCMC_ECUDA; } }
       launches += 1;
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;

@@ -13,6 +13,20 @@
 #pragma once
 #include "common.cuh"
 
+// Kernel classes: the stepping kernels are instantiated once per class so that each instance only carries
+// the code of its own transition kernel (the all-in-one build stalled on instruction fetch: ncu
+// `no_instruction`, profiles/r01_v2_cfg4_*).
+enum { KC_PLAIN = 0 /* normal / unif (+ reflective) */, KC_ADAPT = 1, KC_RAM = 2, KC_MIRROR = 3 };
+__host__ __device__ inline int kernel_class(int type) {
+  switch (type) {
+    case FMCMC_KERNEL_ADAPT: return KC_ADAPT;
+    case FMCMC_KERNEL_RAM: return KC_RAM;
+    case FMCMC_KERNEL_NMIRROR:
+    case FMCMC_KERNEL_UMIRROR: return KC_MIRROR;
+  }
+  return KC_PLAIN;
+}
+
 // Everything a chain's warp needs while proposing row `i` (1-based, R's i).
 struct ChainCtx {
   long long c;            // local chain
@@ -192,6 +206,7 @@ __device__ int ram_adapt_warp(const KParams& kp, const RunBuffers& rb, const Cha
 // (warp-uniform).  For kernel_ram this is phase A only: theta1u is the un-reflected
 // proposal, theta1 its reflection, and chain_flags bit0 says whether phase B
 // (ram_adapt_warp, needs f(theta1u)) must run before the accept step.
+template <int KC>
 __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const RunBuffers& rb, ChainCtx& cx,
                             int lane) {
   const int k = kp.k, kf = kp.kf;
@@ -202,11 +217,8 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
   double* th1 = cx.theta1;
   const double* th0 = cx.theta0;
 
-  switch (kp.type) {
-    case FMCMC_KERNEL_NORMAL:
-    case FMCMC_KERNEL_NORMAL_REFLECTIVE:
-    case FMCMC_KERNEL_UNIF:
-    case FMCMC_KERNEL_UNIF_REFLECTIVE: {
+  {
+    if (KC == KC_PLAIN) {
       const bool unif = kp.type == FMCMC_KERNEL_UNIF || kp.type == FMCMC_KERNEL_UNIF_REFLECTIVE;
       const bool refl = kp.type == FMCMC_KERNEL_NORMAL_REFLECTIVE || kp.type == FMCMC_KERNEL_UNIF_REFLECTIVE;
       for (int j = lane; j < k; j += FM_WARP) th1[j] = th0[j];
@@ -231,7 +243,7 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       return 0;
     }
 
-    case FMCMC_KERNEL_ADAPT: {
+    if (KC == KC_ADAPT) {
       double* Sigma = rb.dstate + (size_t)cx.c * kp.dlen;
       double* Mean_prev = Sigma + (size_t)kf * kf;
       double* L = rb.work + (size_t)cx.c * rb.worklen;  // cached Cholesky factor
@@ -350,7 +362,7 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       return 0;
     }
 
-    case FMCMC_KERNEL_RAM: {
+    if (KC == KC_RAM) {
       double* S = rb.dstate + (size_t)cx.c * kp.dlen;
       double* U = rb.ubuf + (size_t)cx.c * kf;
       if (!(flags & FMCMC_STATE_INIT)) {  // R/kernel_ram.R:114-116
@@ -380,8 +392,7 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       return 0;
     }
 
-    case FMCMC_KERNEL_NMIRROR:
-    case FMCMC_KERNEL_UMIRROR: {
+    if (KC == KC_MIRROR) {
       double* mu = rb.dstate + (size_t)cx.c * kp.dlen;
       double* scale = mu + k;
       double* obs = mu + 2 * k;

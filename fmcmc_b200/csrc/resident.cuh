@@ -35,7 +35,7 @@ __device__ __forceinline__ double group_reduce(double v, double* red, int& parit
   return s;
 }
 
-template <bool WPC>
+template <bool WPC, int KC>
 __global__ void __launch_bounds__(256)
 mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, const double* initial,
                    int data_in_smem, int chain_smem_doubles, int mat_doubles) {
@@ -134,11 +134,11 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
   for (long long i = 2; i <= rb.T; i++) {
     cx.i = i; cx.f0 = f0;
     if (leader_warp) {
-      int rc = propose_warp(kp, sp, rb, cx, lane);
+      int rc = propose_warp<KC>(kp, sp, rb, cx, lane);
       if (lane == 0) {
         int fl = 0;
         if (rc) { set_error(rb.err, rc, c + 1, i); fl = 4; }
-        else if (kp.type == FMCMC_KERNEL_RAM && (rb.chain_flags[c] & 1)) {
+        else if (KC == KC_RAM && (rb.chain_flags[c] & 1)) {
           bool same = true;
           for (int j = 0; j < k; j++) same &= (th1[j] == th1u[j]);
           fl = same ? 1 : 2;  // 1: adapt with f1u = f1, 2: adapt, evaluate f(theta1u)
@@ -150,7 +150,7 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
     const int fl = *gflag;
     if (fl == 4) break;
     const double f1 = loglik(th1);
-    if (fl) {  // kernel_ram phase B, R/kernel_ram.R:129-150
+    if (KC == KC_RAM && fl) {  // kernel_ram phase B, R/kernel_ram.R:129-150
       const double f1u = (fl == 1) ? f1 : loglik(th1u);
       int rc = 0;
       if (leader_warp) rc = ram_adapt_warp(kp, rb, cx, f1u, lane);

@@ -191,6 +191,7 @@ __device__ __forceinline__ double reduce_partials(const TiledBuffers& tb, long l
 }
 
 // Finishes row `row - 1` and proposes row `row` (1 <= row <= T + 1).
+template <int KC>
 __global__ void __launch_bounds__(TL_HEAD_WARPS * 32)
 tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, TiledBuffers tb,
                   const double* initial, long long row, int mat_doubles) {
@@ -244,7 +245,7 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
   } else {
     double f0 = rb.cur_f[c];
     cx.i = r; cx.f0 = f0;
-    if (kp.type == FMCMC_KERNEL_RAM && (rb.chain_flags[c] & 1)) {  // phase B, R/kernel_ram.R:129-150
+    if (KC == KC_RAM && (rb.chain_flags[c] & 1)) {  // phase B, R/kernel_ram.R:129-150
       const double su = reduce_partials(tb, (long long)rb.nchains + c, lane);
       const double f1u = family_finish(mp, th1u, su);
       const int rc = ram_adapt_warp(kp, rb, cx, f1u, lane);
@@ -265,7 +266,7 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
   if (row <= rb.T) {
     cx.i = row;
     cx.f0 = rb.cur_f[c];
-    const int rc = propose_warp(kp, sp, rb, cx, lane);
+    const int rc = propose_warp<KC>(kp, sp, rb, cx, lane);
     if (rc && lane == 0) set_error(rb.err, rc, c + 1, row);
   }
 }
