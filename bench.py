@@ -476,7 +476,7 @@ def main():
             threads = os.cpu_count() or 1
             chains_s = 2 * threads
             probe = cpu_port_run(X, y, chains_s, 3, threads)                   # 2 MH steps: sizes the sample
-            rows_s = 1 + max(2, int(round(15.0 / max(probe / 2.0, 1e-3))))     # ~15 s of CPU work
+            rows_s = 1 + max(2, int(round(20.0 / max(probe / 2.0, 1e-3))))     # 10-20 s of CPU work
             sec = cpu_port_run(X, y, chains_s, rows_s, threads)
             line["cpu_baseline"] = {"value": chains_s * (rows_s - 1) / sec, "unit": "chain-steps/s", "cores": threads,
                                     "kind": "port",

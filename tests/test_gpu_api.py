@@ -72,6 +72,45 @@ def test_posterior_mean_band(readme_data):
     assert np.all(x[:, :, 2] > 0)
 
 
+@pytest.mark.parametrize("kname", ["normal_reflective", "adapt", "ram", "nmirror"])
+def test_production_streams_agree_with_reference_streams(oracle, readme_data, kname):
+    """north_star correctness (2): production Philox streams on the GPU agree DISTRIBUTIONALLY with the reference's
+    own streams (R's Mersenne-Twister + inversion, replayed by the oracle in the serial path's order): posterior
+    means within 4 MCSE, posterior sds within 10 %, and the two sets of chains are indistinguishable to
+    Gelman-Rubin (R-hat of the pooled set < 1.05)."""
+    from fmcmc_b200 import _abi as A
+    from helpers import r_fed_stream, readme_model
+    ll = _readme_ll(readme_data)
+    C, T, burn = 32, 3000, 1000
+    lb = [np.nan, np.nan, 0.0]
+    kern = {"normal_reflective": lambda: fm.kernel_normal_reflective(scale=.1, lb=lb),
+            "adapt": lambda: fm.kernel_adapt(warmup=300, lb=lb),
+            "ram": lambda: fm.kernel_ram(lb=lb),
+            "nmirror": lambda: fm.kernel_nmirror(mu=[3.0, 2.0, 4.0], scale=.2, warmup=400, lb=lb)}[kname]
+    init = np.tile([3.0, 2.0, 4.0], (C, 1))
+    g = fm.MCMC(init, ll, T, nchains=C, burnin=burn, seed=11, kernel=kern()).as_array()        # [C][T-burn][3]
+    # the reference's streams: R RNG -> fed into the oracle (kernel_ram's U = rt(k, k) is third-party: numpy t)
+    R = oracle.RRng
+    R.set_seed(4242)
+    spec = kern().to_spec(3)                                                                   # a fresh kernel object
+    kd = 3
+    if kname == "ram":
+        rng = np.random.default_rng(4242)
+        logu, z = np.log(rng.random((C, T))), rng.standard_t(3, size=(C, T, kd))
+    else:
+        logu, z = r_fed_stream(R, C, T, kd)
+    o = oracle.run(readme_model(readme_data), spec, init, T, nchains=C, burnin=burn,
+                   stream=A.marshal_stream(A.STREAM_FED, logu=logu, z=z), threads=8)["ans"]
+    mg, mo = g.mean(axis=1), o.mean(axis=1)                                                     # per-chain means
+    mcse = np.sqrt(mg.var(axis=0, ddof=1) / C + mo.var(axis=0, ddof=1) / C)
+    assert np.all(np.abs(mg.mean(0) - mo.mean(0)) < 4 * mcse), (mg.mean(0), mo.mean(0), mcse)
+    sg, so = g.reshape(-1, 3).std(axis=0, ddof=1), o.reshape(-1, 3).std(axis=0, ddof=1)
+    assert np.all(np.abs(sg / so - 1) < 0.10), (sg, so)
+    pooled = np.concatenate([g, o], axis=0)
+    psrf, mpsrf, rc = oracle.gelman(pooled)
+    assert rc == 0 and mpsrf < 1.05 and np.all(psrf < 1.05), (psrf, mpsrf)
+
+
 def test_fixed_and_bounds(readme_data):
     """test-mcmc.R:155-162 (fixed column constant), test-na-bounds.R:63-93 (NA == +-xmax, samples in range)."""
     ll = _readme_ll(readme_data)
