@@ -91,6 +91,15 @@ class RunReport(C.Structure):
     ]
 
 
+class ShardHandles(C.Structure):
+    """fmcmc_shard_handles (observation sharding across GPUs)."""
+    _fields_ = [
+        ("partial", C.c_ubyte * 64), ("flags", C.c_ubyte * 64),
+        ("partial_ptr", C.c_void_p), ("flags_ptr", C.c_void_p),
+        ("device", C.c_int32), ("pid", C.c_int32),
+    ]
+
+
 def _as_f64(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if shape is not None:

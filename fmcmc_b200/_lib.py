@@ -85,6 +85,10 @@ def lib():
                                       C.c_double, dp, dp, dp, C.c_char_p, C.c_size_t]
     L.fmcmc_reflect.restype = C.c_int
     L.fmcmc_reflect.argtypes = [C.c_int, C.c_int32, C.c_int64, dp, dp, dp, u8p, C.c_char_p, C.c_size_t]
+    L.fmcmc_shard_alloc.restype = C.c_int
+    L.fmcmc_shard_alloc.argtypes = [vp, C.c_int, C.c_int, C.c_int64, C.POINTER(A.ShardHandles), C.c_char_p, C.c_size_t]
+    L.fmcmc_shard_attach.restype = C.c_int
+    L.fmcmc_shard_attach.argtypes = [vp, C.c_int, C.c_int, C.POINTER(A.ShardHandles), C.c_char_p, C.c_size_t]
     L.fmcmc_measure_fp64_peak.restype = C.c_int
     L.fmcmc_measure_fp64_peak.argtypes = [C.c_int, dp, C.c_char_p, C.c_size_t]
     L.fmcmc_test_softplus.restype = C.c_int
@@ -99,7 +103,7 @@ EXPORTED_SYMBOLS = [
     "fmcmc_version", "fmcmc_device_count", "fmcmc_model_nparams", "fmcmc_kernel_state_len",
     "fmcmc_rows_kept", "fmcmc_model_create", "fmcmc_model_create_device", "fmcmc_model_free",
     "fmcmc_set_path", "fmcmc_run", "fmcmc_logpost", "fmcmc_store_reset", "fmcmc_store_rows",
-    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
+    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_shard_alloc", "fmcmc_shard_attach", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
 ]
 
 

@@ -105,7 +105,8 @@ def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_i
 
 
 def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel=None, multicore=False,
-         conv_checker=None, cl=None, progress=False, chain_id=1, device=None, fed=None, path=0, **dots):
+         conv_checker=None, cl=None, progress=False, chain_id=1, device=None, fed=None, path=0,
+         shard="chains", **dots):
     """Drop-in for fmcmc::MCMC (R/mcmc.R:325-479).
 
     initial   vector (recycled), nchains x k matrix, or a previous Mcmc / McmcList (restart)
@@ -117,6 +118,10 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
               GPU(s).  Under torchrun (torch.distributed initialised) chains are sharded over ranks
               and each rank returns its own chains.
     fed       FedStream or a list of FedStream (one per bulk): verification mode
+    shard     under torchrun: "chains" (default; each rank owns a range of chains, no data-path collective) or
+              "observations" (few chains on a huge n: each rank holds a row slice of X / y, every rank runs
+              ALL chains and returns the same result; the per-step exchange of partial sums runs inside the
+              CUDA kernels over NVLink peer memory)
     """
     if dots:
         raise TypeError("The following arguments passed via -...- are not present in -fun-:\n - "
@@ -145,7 +150,14 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
     if conv_checker is not None and isinstance(conv_checker, GelmanChecker) and nchains < 2:
         raise ValueError("Convergence test with the Gelman is only available when `nchains` > 1L.")
 
-    sharding = current_sharding(nchains)
+    if shard not in ("chains", "observations"):
+        raise ValueError('`shard` must be "chains" or "observations".')
+    obs_sharding = None
+    if shard == "observations":
+        from .dist import ObservationSharding, current_sharding as _cs
+        if _cs(nchains) is not None:
+            obs_sharding = ObservationSharding()
+    sharding = current_sharding(nchains) if obs_sharding is None else None
     nlocal = sharding.local if sharding else nchains
     init_all, names = check_initial(initial, nchains)
     if init_all.shape[1] != fun.k:
@@ -153,15 +165,21 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
     kernel.to_spec(fun.k) if not kernel.is_list else None       # validates the kernel before touching the GPU
     init_local = init_all[sharding.offset:sharding.offset + nlocal] if sharding else init_all
     if device is None:
-        device = sharding.device.index if (sharding and sharding.on_cuda) else 0
+        device = sharding.device.index if (sharding and sharding.on_cuda) else (obs_sharding.device if obs_sharding else 0)
     if seed is None:
         seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array([1, 1 << 32], dtype=np.uint64))
+        if obs_sharding is not None:                            # every rank must draw the same streams
+            box = [seed]
+            obs_sharding.dist.broadcast_object_list(box, src=0)
+            seed = box[0]
 
     info.MCMC_OUTPUT.clear(nlocal)
     info.MCMC_init(initial=init_all, nsteps=nsteps, seed=seed, nchains=nchains, burnin=burnin, thin=thin,
                    kernel=kernel, conv_checker=conv_checker)
     info.MCMC_OUTPUT.kernel = kernel
-    model = DeviceModel(fun, device=device)
+    model = DeviceModel(obs_sharding.local_family(fun) if obs_sharding else fun, device=device)
+    if obs_sharding:
+        obs_sharding.attach(model, fun.n, 2 * nchains)          # kernel_ram evaluates 2 columns per chain
     if path:
         model.set_path(path)
     feds = fed if isinstance(fed, (list, tuple)) else ([fed] if fed is not None else None)

@@ -38,7 +38,8 @@ struct StreamParams {
 struct ModelParams {
   int family;
   unsigned flags;
-  long long n;     // observations
+  long long n;     // observations held by this GPU
+  long long n_total;  // observations of the whole model (== n unless sharded over observations across GPUs)
   long long ld;    // leading dimension of X (>= n, even)
   int p_x, n_groups, k;
   int y_binary;    // logistic: every y is exactly +0.0 or 1.0 (fast epilogue)

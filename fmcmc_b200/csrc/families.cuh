@@ -88,7 +88,7 @@ __device__ __forceinline__ double dnorm_log1(double x, double mu, double sd) {
 __device__ __forceinline__ double family_finish(const ModelParams& mp, const double* th, double s) {
   switch (mp.family) {
     case FMCMC_FAMILY_GAUSSIAN_LM: {
-      double v = gauss_sum_from_ss(s, (double)mp.n, th[mp.k - 1]);
+      double v = gauss_sum_from_ss(s, (double)mp.n_total, th[mp.k - 1]);
       if ((mp.flags & FMCMC_MODEL_GUARD) && !isfinite(v)) v = -INFINITY;  // README.md:135-136
       return v;
     }
@@ -103,7 +103,7 @@ __device__ __forceinline__ double family_finish(const ModelParams& mp, const dou
       const double gamma = th[G];
       double sigma = 1.0, tau = 1.0;
       if (mp.flags & FMCMC_MODEL_SCALES) { sigma = th[G + 1]; tau = th[G + 2]; }
-      double v = gauss_sum_from_ss(s, (double)mp.n, sigma);
+      double v = gauss_sum_from_ss(s, (double)mp.n_total, sigma);
       double pr = 0.0;
       for (int g = 0; g < G; g++) pr += dnorm_log1(th[g], gamma, tau);
       double du;

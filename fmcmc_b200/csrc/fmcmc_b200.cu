@@ -1,6 +1,7 @@
 // fmcmc_b200.cu — C ABI (include/fmcmc_b200.h) + host orchestration.
 // Single translation unit; device code lives in the .cuh files next to it.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -88,6 +89,15 @@ struct fmcmc_model {
   long long store_cap = 0, store_rows = 0;
   // gelman scratch
   DevBuf g_xbar, g_s2, g_wsum, g_wpart, g_mask;
+  // observation sharding (fmcmc_shard_*): exchange buffers are plain cudaMalloc so they can be IPC-exported
+  int shard_world = 0, shard_rank = 0, shard_max_cols = 0;
+  double* shard_partial = nullptr;               // [2][world * sm_count][max_cols]
+  unsigned long long* shard_flags = nullptr;     // [world]
+  unsigned int* shard_done = nullptr;
+  double* shard_peer_partial[FM_MAX_PEERS] = {};
+  unsigned long long* shard_peer_flags[FM_MAX_PEERS] = {};
+  bool shard_ipc_opened[FM_MAX_PEERS] = {};
+  unsigned long long shard_step = 0;
 };
 
 static int count_free(const fmcmc_kernel_spec* ks, std::vector<int>& free_idx) {
@@ -157,7 +167,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   const long long n = d->n, ld = (n + 1) & ~1LL;  // even leading dimension: 16-byte aligned columns for TMA
   ModelParams& mp = m->mp;
   mp.family = d->family; mp.flags = d->flags; mp.n = n; mp.ld = ld; mp.p_x = d->p_x; mp.n_groups = d->n_groups;
-  mp.k = k; mp.h0 = d->hyper[0]; mp.h1 = d->hyper[1];
+  mp.k = k; mp.h0 = d->hyper[0]; mp.h1 = d->hyper[1]; mp.n_total = n;
   const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 #define MC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); fmcmc_model_free(m); return FMCMC_ECUDA; } } while (0)
   MC(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -241,11 +251,92 @@ extern "C" void fmcmc_model_free(fmcmc_model* m) {
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
                     &m->g_mask};
   for (DevBuf* b : bufs) release(*b);
+  for (int g = 0; g < FM_MAX_PEERS; g++)
+    if (m->shard_ipc_opened[g]) { cudaIpcCloseMemHandle(m->shard_peer_partial[g]); cudaIpcCloseMemHandle(m->shard_peer_flags[g]); }
+  if (m->shard_partial) cudaFree(m->shard_partial);
+  if (m->shard_flags) cudaFree(m->shard_flags);
+  if (m->shard_done) cudaFree(m->shard_done);
   for (auto& e : m->hot_ev) cudaEventDestroy(e);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
+}
+
+// --------------------------------------------------------------------------------
+// observation sharding across GPUs
+// --------------------------------------------------------------------------------
+extern "C" int fmcmc_shard_alloc(fmcmc_model* m, int world, int max_cols, int64_t n_total, fmcmc_shard_handles* out,
+                                 char* err, size_t errlen) {
+  if (!m || !out || world < 2 || world > FM_MAX_PEERS || max_cols < 1 || n_total < m->mp.n) {
+    set_err(err, errlen, "fmcmc_shard_alloc: bad argument (world 2..%d, max_cols >= 1, n_total >= local n)", FM_MAX_PEERS);
+    return FMCMC_EINVAL;
+  }
+  if (m->shard_partial) { set_err(err, errlen, "fmcmc_shard_alloc: the model is already sharded"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  const size_t pbytes = (size_t)2 * world * m->sm_count * max_cols * 8;
+  CU_CHECK(cudaMalloc((void**)&m->shard_partial, pbytes));
+  CU_CHECK(cudaMalloc((void**)&m->shard_flags, (size_t)FM_MAX_PEERS * 8));
+  CU_CHECK(cudaMalloc((void**)&m->shard_done, 16));
+  CU_CHECK(cudaMemset(m->shard_partial, 0, pbytes));
+  CU_CHECK(cudaMemset(m->shard_flags, 0, (size_t)FM_MAX_PEERS * 8));
+  CU_CHECK(cudaMemset(m->shard_done, 0, 16));
+  CU_CHECK(cudaDeviceSynchronize());
+  memset(out, 0, sizeof(*out));
+  cudaIpcMemHandle_t h;
+  CU_CHECK(cudaIpcGetMemHandle(&h, m->shard_partial));
+  memcpy(out->partial, &h, sizeof(h));
+  CU_CHECK(cudaIpcGetMemHandle(&h, m->shard_flags));
+  memcpy(out->flags, &h, sizeof(h));
+  out->partial_ptr = m->shard_partial;
+  out->flags_ptr = m->shard_flags;
+  out->device = m->device;
+  out->pid = (int32_t)getpid();
+  m->shard_world = -world;  // allocated, not attached yet
+  m->shard_max_cols = max_cols;
+  m->mp.n_total = n_total;
+  return FMCMC_OK;
+}
+
+extern "C" int fmcmc_shard_attach(fmcmc_model* m, int rank, int world, const fmcmc_shard_handles* all, char* err,
+                                  size_t errlen) {
+  if (!m || !all || m->shard_world != -world || rank < 0 || rank >= world) {
+    set_err(err, errlen, "fmcmc_shard_attach: call fmcmc_shard_alloc with the same world first");
+    return FMCMC_EINVAL;
+  }
+  if (all[rank].partial_ptr != m->shard_partial || all[rank].pid != (int32_t)getpid()) {
+    set_err(err, errlen, "fmcmc_shard_attach: all[rank] is not this model's own handle");
+    return FMCMC_EINVAL;
+  }
+  CU_CHECK(cudaSetDevice(m->device));
+  for (int g = 0; g < world; g++) {
+    if (g == rank) {
+      m->shard_peer_partial[g] = m->shard_partial;
+      m->shard_peer_flags[g] = m->shard_flags;
+    } else if (all[g].pid == (int32_t)getpid()) {  // peer model in this process: direct peer access
+      int can = 0;
+      CU_CHECK(cudaDeviceCanAccessPeer(&can, m->device, all[g].device));
+      if (!can) { set_err(err, errlen, "GPU %d cannot access GPU %d's memory (no NVLink / P2P)", m->device, all[g].device); return FMCMC_ECUDA; }
+      cudaError_t pe = cudaDeviceEnablePeerAccess(all[g].device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU_CHECK(pe);
+      cudaGetLastError();
+      m->shard_peer_partial[g] = (double*)all[g].partial_ptr;
+      m->shard_peer_flags[g] = (unsigned long long*)all[g].flags_ptr;
+    } else {  // peer process: CUDA IPC
+      cudaIpcMemHandle_t h;
+      void* p = nullptr;
+      memcpy(&h, all[g].partial, sizeof(h));
+      CU_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      m->shard_peer_partial[g] = (double*)p;
+      memcpy(&h, all[g].flags, sizeof(h));
+      CU_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      m->shard_peer_flags[g] = (unsigned long long*)p;
+      m->shard_ipc_opened[g] = true;
+    }
+  }
+  m->shard_world = world;
+  m->shard_rank = rank;
+  return FMCMC_OK;
 }
 
 extern "C" int fmcmc_set_path(fmcmc_model* m, int path) {
@@ -621,6 +712,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   const bool lm_or_logit = mp.family == FMCMC_FAMILY_GAUSSIAN_LM || mp.family == FMCMC_FAMILY_LOGISTIC;
   const bool tiled_ok = lm_or_logit && mp.p_x <= 128;
   int path = m->forced_path;
+  if (m->shard_world > 1) path = 3;
   if (path == 0)  // narrow X: the DFMA kernel's 8 / 16-column tiers do no padded work; wide X: DMMA
     path = (tiled_ok && data_bytes > 96 * 1024) ? (mp.p_x > 32 ? 3 : (mp.p_x <= 16 ? 2 : m->tiled_default)) : 1;
   if ((path == 2 && !(lm_or_logit && mp.p_x <= 32)) || (path == 3 && !tiled_ok)) {
@@ -695,8 +787,23 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     if (gx > ntiles) gx = (int)ntiles;
     tb.gx = gx;
     tb.cb = chain_blocks;
-    CU_CHECK(ensure(m->partial, (size_t)gx * tb.ncols * 8));
-    tb.partial = m->partial.as<double>();
+    const bool sharded = m->shard_world > 1;
+    if (sharded) {  // observation sharding: partial sums live in the exchange buffer, one block per step parity
+      if (path != 3 || gx != m->sm_count || tb.ncols > m->shard_max_cols) {
+        set_err(err, errlen, "observation sharding needs the DMMA path, >= %d observation tiles per rank and <= %d likelihood columns (got path %d, %d slices, %d columns)",
+                m->sm_count, m->shard_max_cols, path, gx, tb.ncols);
+        return FMCMC_EINVAL;
+      }
+      tb.sx.world = m->shard_world; tb.sx.rank = m->shard_rank; tb.sx.done = m->shard_done;
+      tb.sx.parity_stride = (long long)m->shard_world * m->sm_count * m->shard_max_cols;
+      for (int g = 0; g < m->shard_world; g++) { tb.sx.peer_partial[g] = m->shard_peer_partial[g]; tb.sx.peer_flags[g] = m->shard_peer_flags[g]; }
+      tb.gx_total = m->shard_world * gx;
+      tb.partial = m->shard_partial;
+    } else {
+      CU_CHECK(ensure(m->partial, (size_t)gx * tb.ncols * 8));
+      tb.partial = m->partial.as<double>();
+      tb.gx_total = gx;
+    }
     const dim3 lgrid = path == 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
@@ -732,6 +839,10 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       launches += 1;
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;
+        if (sharded) {
+          tb.sx.step = ++m->shard_step;
+          tb.partial = m->shard_partial + (size_t)(tb.sx.step & 1ULL) * tb.sx.parity_stride;
+        }
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
         cudaError_t e;
         if (path == 3)
@@ -788,6 +899,9 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         break;
       case FMCMC_ENOTPD:
         set_err(err, errlen, "'Sigma' is not positive definite (step i = %d, chain %d).", herr[2], herr[1]);
+        break;
+      case FMCMC_EPEER:
+        set_err(err, errlen, "observation sharding: a peer GPU did not publish its partial sums within 20 s (step i = %d)", herr[2]);
         break;
       case FMCMC_EUNSUP:
         set_err(err, errlen, "the kernel reached a state the reference itself mishandles at step i = %d, chain %d (SURVEY App. D: mirror quirk D8 / adapt update range / t. = 0)", herr[2], herr[1]);

@@ -90,7 +90,10 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
   double* th1u = th1 + k;
   double* scr = th1u + k;  // 4k doubles
   __shared__ int s_flag[RES_MAX_WARPS];
+  __shared__ int s_flag_b[RES_MAX_WARPS];  // status of kernel_ram's phase B: a separate word, so that the accept
+                                           // step's write to gflag cannot race with slower warps still reading it
   int* gflag = &s_flag[WPC ? warp : 0];
+  int* gflag_b = &s_flag_b[WPC ? warp : 0];
 
   const int gtid = WPC ? lane : tid;
   const int gsize = WPC ? FM_WARP : (int)blockDim.x;
@@ -156,9 +159,9 @@ mh_resident_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, c
       if (leader_warp) rc = ram_adapt_warp(kp, rb, cx, f1u, lane);
       if (leader_warp && lane == 0 && rc) set_error(rb.err, rc, c + 1, i);
       if (rc) { /* leader warp only; others learn via failed flag below */ }
-      if (leader_warp && lane == 0) *gflag = rc ? 4 : 0;
+      if (leader_warp && lane == 0) *gflag_b = rc ? 4 : 0;
       group_sync<WPC>();
-      if (*gflag == 4) break;
+      if (*gflag_b == 4) break;
     }
     if (leader_warp) {
       bool failed = false;

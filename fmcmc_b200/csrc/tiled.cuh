@@ -29,8 +29,26 @@
 #define TL_RO 4
 #endif
 
+#define FM_MAX_PEERS 8
+// Observation sharding across GPUs (few chains, huge n): every rank holds a row slice of X / y and runs the SAME
+// chains.  The likelihood kernel of rank r stores its per-slice partial sums straight into EVERY rank's exchange
+// buffer over NVLink (peer stores) and, once its last CTA is done, raises flag[r] = step on every rank.  The head
+// kernel of each rank waits for all flags and reduces the world * gx partials in one fixed order, so all ranks take
+// bit-identical decisions with no host-side collective on the step path.  Double-buffered by step parity: a peer
+// can be at most one step ahead (its next head needs this rank's next flag).
+struct ShardExchange {
+  int world, rank;                              // world == 0 / 1: not sharded
+  double* peer_partial[FM_MAX_PEERS];           // rank g's buffer: [2][world * gx][ncols_max]
+  unsigned long long* peer_flags[FM_MAX_PEERS]; // rank g's flags:  [world]
+  unsigned long long step;                      // value the flags take when this launch's partials are complete
+  unsigned int* done;                           // local CTA-completion counter of the likelihood kernel
+  long long parity_stride;                      // doubles between the two parity blocks
+};
+
 struct TiledBuffers {
-  double* partial;  // [gx][ncols]
+  ShardExchange sx;
+  double* partial;  // [gx_total][ncols]: this step's (parity) block, all ranks' slices when sharded
+  int gx_total;     // slices the head kernel reduces (world * gx when sharded, else gx)
   int gx;           // observation slices (gridDim.x of tiled_loglik)
   int cb;           // chain blocks (DMMA kernel: 1-D grid of gx * cb CTAs, chain block fastest)
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
@@ -186,7 +204,7 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
 // Fixed-order reduction of one column of the partial sums by one warp.
 __device__ __forceinline__ double reduce_partials(const TiledBuffers& tb, long long col, int lane) {
   double s = 0.0;
-  for (int g = lane; g < tb.gx; g += FM_WARP) s += tb.partial[(size_t)g * tb.ncols + col];
+  for (int g = lane; g < tb.gx_total; g += FM_WARP) s += __ldcg(&tb.partial[(size_t)g * tb.ncols + col]);
   return warp_sum(s);
 }
 
@@ -225,6 +243,22 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
 
   // ---- finish row r = row - 1 -------------------------------------------------------
   const long long r = row - 1;
+  if (tb.sx.world > 1 && !(r == 1 && !initial)) {  // observation-sharded: all ranks' partials of this step must have landed
+    bool ok = true;
+    if (lane < tb.sx.world) {
+      const volatile unsigned long long* fl = tb.sx.peer_flags[tb.sx.rank] + lane;
+      unsigned long long t0 = 0, now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*fl < tb.sx.step) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 20000000000ULL || rb.err[0] != 0) { ok = false; break; }  // 20 s: a peer died
+        __nanosleep(200);
+      }
+    }
+    ok = __all_sync(FM_FULL, ok);
+    __threadfence_system();
+    if (!ok) { if (lane == 0) set_error(rb.err, FMCMC_EPEER, c + 1, r); return; }
+  }
   double f1;
   if (r == 1 && !initial) {
     f1 = rb.cur_f[c];  // continuing from the resident state: f(theta0) is known, no loglik launch was made

@@ -232,6 +232,18 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   }
 
   // ---- reduce over the 8 observation rows (lanes with equal t), write the CTA's partial sums ----
+  // Sharded over observations: the sums go to every rank's exchange buffer (peer stores over NVLink), at
+  // slice index rank * gx + slice, then the last CTA of the grid publishes the step flag everywhere.
+  const int world = tb.sx.world > 1 ? tb.sx.world : 1;
+  auto store_partial = [&](int col, double v) {
+    if (world == 1) {
+      tb.partial[(size_t)slice * tb.ncols + col] = v;
+    } else {
+      const size_t off = (size_t)(tb.sx.step & 1ULL) * tb.sx.parity_stride +
+                         ((size_t)tb.sx.rank * tb.gx + slice) * tb.ncols + col;
+      for (int pg = 0; pg < world; pg++) tb.sx.peer_partial[pg][off] = v;
+    }
+  };
   double* red = stage0;  // OSPLIT: [NWARPS][NT * 8] cross-warp staging; the pipeline stages are drained by now
   if (OSPLIT) __syncthreads();
 #pragma unroll
@@ -247,7 +259,7 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
         if (g == 0) red[warp * (NT * 8) + lc] = v;
       } else {
         const int col = chain0 + lc;
-        if (g == 0 && col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
+        if (g == 0 && col < tb.ncols) store_partial(col, v);
       }
     }
   if (OSPLIT) {
@@ -256,7 +268,24 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
       double v = 0.0;
       for (int w = 0; w < NWARPS; w++) v += red[w * (NT * 8) + tid];  // fixed order: deterministic
       const int col = chain0 + tid;
-      if (col < tb.ncols) tb.partial[(size_t)slice * tb.ncols + col] = v;
+      if (col < tb.ncols) store_partial(col, v);
+    }
+  }
+  if (world > 1) {  // publish: every CTA fences its peer stores, the last one raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int total = gridDim.x;
+      const unsigned int prev = atomicAdd(tb.sx.done, 1u);
+      if (prev == total - 1) {
+        *tb.sx.done = 0u;
+        __threadfence_system();
+        for (int pg = 0; pg < world; pg++) {
+          volatile unsigned long long* fl = tb.sx.peer_flags[pg] + tb.sx.rank;
+          *fl = tb.sx.step;
+        }
+        __threadfence_system();
+      }
     }
   }
 }

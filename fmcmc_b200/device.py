@@ -85,6 +85,18 @@ class DeviceModel:
             raise e
         return dict(ans=ans, draws=draws, logpost=lp, report=rep, istate=istate, dstate=dstate)
 
+    # ---- observation sharding across GPUs (include/fmcmc_b200.h: fmcmc_shard_*) -----------------
+    def shard_alloc(self, world: int, max_cols: int, n_total: int) -> "A.ShardHandles":
+        h = A.ShardHandles()
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_shard_alloc(self._h, world, max_cols, n_total, C.byref(h), err, len(err)), err)
+        return h
+
+    def shard_attach(self, rank: int, world: int, handles) -> None:
+        arr = (A.ShardHandles * world)(*handles)
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_shard_attach(self._h, rank, world, arr, err, len(err)), err)
+
     # ---- sample store + Gelman -------------------------------------------------------------
     def store_reset(self, nchains, capacity_rows):
         err = _lib.errbuf()

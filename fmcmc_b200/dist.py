@@ -68,3 +68,44 @@ def current_sharding(nchains_total: int):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return None
     return ChainSharding(nchains_total)
+
+
+class ObservationSharding:
+    """Few chains on a huge n: rows of X / y are split over the ranks, every rank runs the SAME chains, and the
+    per-step exchange of partial log-likelihood sums happens inside the CUDA kernels over NVLink peer memory
+    (include/fmcmc_b200.h, fmcmc_shard_*): torch.distributed only carries the 144-byte IPC handles once."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = int(os.environ.get("LOCAL_RANK", 0))
+
+    def row_slice(self, n: int) -> slice:
+        """Even-sized contiguous row blocks (16-byte aligned columns), the remainder goes to the last rank."""
+        per = (n // self.world) & ~1
+        lo = self.rank * per
+        return slice(lo, n if self.rank == self.world - 1 else lo + per)
+
+    def local_family(self, family):
+        """The rank's row slice of a device family (gaussian_lm / logistic)."""
+        from . import _abi as A
+        from .families import DeviceFamily
+        if family.family == A.FAMILY_HIER_NORMAL:
+            raise ValueError("observation sharding supports ll_gaussian_lm and ll_logistic")
+        sl = self.row_slice(family.n)
+        X = family.X[sl]
+        import numpy as np
+        return DeviceFamily(family.family, X.shape[0], p_x=family.p_x, X=np.asfortranarray(X), y=family.y[sl],
+                            flags=family.flags, hyper=family.hyper)
+
+    def attach(self, model, n_total: int, max_cols: int) -> None:
+        import ctypes as C
+        from . import _abi as A
+        mine = model.shard_alloc(self.world, max_cols, n_total)
+        blobs = [None] * self.world
+        self.dist.all_gather_object(blobs, bytes(mine))
+        handles = [A.ShardHandles.from_buffer_copy(b) for b in blobs]
+        model.shard_attach(self.rank, self.world, handles)
+        self.dist.barrier()

@@ -53,7 +53,8 @@ enum {
   FMCMC_ENOMEM    = 4,
   FMCMC_ENOTPD    = 5,  /* kernel_adapt: Sigma not positive definite (MASS::mvrnorm stop) */
   FMCMC_EUNSUP    = 6,  /* configuration the reference itself mishandles or not built */
-  FMCMC_ENANRATIO = 7   /* f1 - f0 is NaN, R: "missing value where TRUE/FALSE needed" (D10) */
+  FMCMC_ENANRATIO = 7,  /* f1 - f0 is NaN, R: "missing value where TRUE/FALSE needed" (D10) */
+  FMCMC_EPEER     = 8   /* observation sharding: a peer GPU did not publish its partial sums in time */
 };
 
 /* ---- log-posterior families (the device-side replacement of `fun`) ------- */
@@ -304,6 +305,34 @@ int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, in
  * on everything in the store; `start_iter`/`end_iter`/`thin` describe mcpar. */
 int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double* mpsrf,
                  int64_t* niter_used, char* err, size_t errlen);
+
+/* ---- observation sharding across GPUs (few chains, huge n) -------------------------
+ * Every rank creates its model on a ROW SLICE of X / y and runs the SAME chains with the same streams.  The
+ * likelihood kernel of each rank stores its per-slice partial sums straight into every rank's exchange buffer
+ * (peer stores over NVLink) and raises a per-step flag; each rank's head kernel waits for all flags and reduces
+ * all ranks' partials in one fixed order, so every rank takes bit-identical accept/reject decisions with no
+ * host-side collective on the step path.  This replaces nothing in the reference (its chains are never split
+ * over workers, R/mcmc.R:593-627): it is the multi-GPU mode for the reference's typical few-chain usage.
+ *   1. every rank:  fmcmc_shard_alloc()   -> its exchange buffer + CUDA IPC handles
+ *   2. all_gather the handles (torch.distributed / MPI / anything)
+ *   3. every rank:  fmcmc_shard_attach()  -> opens the peers' buffers; from now on fmcmc_run() is collective:
+ *      all ranks must call it with the same run / kernel / stream arguments.                              */
+typedef struct fmcmc_shard_handles {
+  unsigned char partial[64]; /* cudaIpcMemHandle_t of the partial-sum exchange buffer */
+  unsigned char flags[64];   /* cudaIpcMemHandle_t of the step flags                  */
+  void* partial_ptr;         /* the same two buffers as raw device pointers, for peers living in  */
+  void* flags_ptr;           /* the SAME process (IPC handles cannot be opened by their creator)   */
+  int32_t device;            /* CUDA ordinal owning them                                            */
+  int32_t pid;               /* creator process id                                                  */
+} fmcmc_shard_handles;
+
+/* max_cols: the largest number of likelihood columns a run will use (nchains, x2 for kernel_ram);
+ * n_total: observations over all ranks (the Gaussian families' normalising term needs it). */
+int fmcmc_shard_alloc(fmcmc_model* m, int world, int max_cols, int64_t n_total, fmcmc_shard_handles* out,
+                      char* err, size_t errlen);
+/* all[world]: every rank's handles in rank order (all[rank] must be this model's own). */
+int fmcmc_shard_attach(fmcmc_model* m, int rank, int world, const fmcmc_shard_handles* all,
+                       char* err, size_t errlen);
 
 /* ---- exported helpers of the reference, device implementations ---------- */
 /* R/recursive.R:124-139 / 63-120 applied to `rows` consecutive rows of X

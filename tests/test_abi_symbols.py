@@ -46,16 +46,16 @@ def test_struct_layouts_match_header():
     """sizeof of the ctypes mirrors == what a C compiler makes of the header."""
     import subprocess
     import tempfile
-    src = ('#include "%s/include/fmcmc_b200.h"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n",'
+    src = ('#include "%s/include/fmcmc_b200.h"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",'
            'sizeof(fmcmc_model_desc),sizeof(fmcmc_kernel_spec),sizeof(fmcmc_kernel_state),sizeof(fmcmc_stream_spec),'
-           'sizeof(fmcmc_run_spec),sizeof(fmcmc_run_report));return 0;}') % ROOT
+           'sizeof(fmcmc_run_spec),sizeof(fmcmc_run_report),sizeof(fmcmc_shard_handles));return 0;}') % ROOT
     with tempfile.TemporaryDirectory() as td:
         c, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
         open(c, "w").write(src)
         subprocess.run(["gcc", "-o", exe, c], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(A.ModelDesc), C.sizeof(A.KernelSpec), C.sizeof(A.KernelState), C.sizeof(A.StreamSpec),
-                     C.sizeof(A.RunSpec), C.sizeof(A.RunReport)]
+                     C.sizeof(A.RunSpec), C.sizeof(A.RunReport), C.sizeof(A.ShardHandles)]
 
 
 def test_no_gpu_is_a_loud_error():
