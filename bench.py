@@ -34,14 +34,15 @@ KERNEL_WARMUP = 500
 TRAFFIC_PER_LAUNCH = {("cfg3", 3): 269.0e6, ("cfg3", 2): 269.7e6}
 
 
-def make_data(n=N_OBS, p=P_X, seed=DATA_SEED):
-    """X[:,0] = 1, X[:,1:] ~ N(0,1)/sqrt(p), beta* ~ N(0,1), y ~ Bernoulli(plogis(X beta*))."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+def make_data(n=N_OBS, p=P_X, seed=DATA_SEED, block=0):
+    """X[:,0] = 1, X[:,1:] ~ N(0,1)/sqrt(p), beta* ~ N(0,1), y ~ Bernoulli(plogis(X beta*)).
+    block > 0: another block of rows of the same model (same beta*), for observation-sharded runs."""
+    beta = np.random.Generator(np.random.PCG64(seed + 7919)).standard_normal(p)
+    rng = np.random.Generator(np.random.PCG64(seed + 104729 * block))
     X = np.empty((n, p), order="F")
     X[:, 0] = 1.0
     for j in range(1, p):
         X[:, j] = rng.standard_normal(n) / np.sqrt(p)
-    beta = rng.standard_normal(p)
     eta = X @ beta
     y = (rng.random(n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
     return X, y
@@ -197,7 +198,7 @@ class Workload:
             self.label = (f"gaussian_lm n={self.n} k=128 (127 columns + sd) x {self.chains} chains/GPU, kernel_nmirror "
                           "(BASELINE configs[4], one GPU's share)")
         elif key == "few":           # the reference's typical usage: a handful of chains on a large n (README: 1-4 chains)
-            self.family, self.n, self.p_x, self.k = "logistic", N_OBS, P_X, P_X
+            self.family, self.n, self.p_x, self.k = "logistic", args.n or N_OBS, P_X, P_X
             self.chains = args.chains or 4
             self.kernel_name = "kernel_adapt(warmup=500, freq=1), timed rows are post-warm-up"
             self.kwarm = KERNEL_WARMUP
@@ -229,7 +230,14 @@ class Workload:
         C, k = self.chains, self.k
         rng = np.random.default_rng(1000 + rank)
         if self.key in ("cfg3", "few"):
-            X, y = make_data()
+            if getattr(self, "obs_shard", None):                 # this rank's rows only (same beta* on every rank)
+                world = self.obs_shard
+                per = (self.n // world) & ~1
+                nloc = per if rank < world - 1 else self.n - per * (world - 1)
+                X, y = make_data(n=nloc, block=rank + 1)
+                rng = np.random.default_rng(1000)                # identical chains on every rank
+            else:
+                X, y = make_data(n=self.n)
             fam = fm.ll_logistic(X, y, prior_sd=2.0)
             return fam, None, fm.kernel_adapt(), rng.normal(0, 0.1, (C, k)), (X, y)
         if self.key == "cfg4":
@@ -274,7 +282,10 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg1", "few"],
                     help="cfg3 = BASELINE configs[2] (default, the metric's configuration); cfg5 = configs[4] per-GPU share")
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
-    ap.add_argument("--n", type=int, default=None, help="observations (cfg5 only; default 1e7)")
+    ap.add_argument("--nobs", dest="n", type=int, default=None, help="observations (cfg5: default 1e7; few: default 1e6)")
+    ap.add_argument("--shard", default="chains", choices=["chains", "observations"],
+                    help="multi-GPU mode: chains (default, weak scaling) or observations (workload few: rows of X split over "
+                         "ranks, every rank runs all chains, partial sums exchanged over NVLink inside the kernels; strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-kernel-warmup", action="store_true",
                     help="prime abs_iter instead of running the kernel's 500 warm-up rows (profiling runs)")
@@ -308,11 +319,20 @@ def main():
         torch.cuda.synchronize()
 
     wl = Workload(args.workload, args)
+    obs_shard = args.shard == "observations" and world > 1
+    if obs_shard:
+        if args.workload != "few":
+            raise SystemExit("--shard observations is for --workload few")
+        wl.obs_shard = world
     C, k = wl.chains, wl.k
     K, W = args.steps, args.warmup
     fam, dev_ptrs, kern, init0, host_data = wl.make(fm, A, torch, local, rank)
     model = DeviceModel(fam, device=local, device_ptrs=dev_ptrs)      # X, y -> HBM once
     chain_offset = rank * C
+    if obs_shard:
+        from fmcmc_b200.dist import ObservationSharding
+        ObservationSharding().attach(model, wl.n, 2 * C)
+        chain_offset = 0
     spec = kern.to_spec(k)
     dlen = A.state_len(spec["type"], k, k)
     istate = np.zeros((C, A.ISTATE_LEN), dtype=np.int64)
@@ -386,7 +406,7 @@ def main():
         free = np.ones(k, dtype=np.uint8)
         torch.cuda.synchronize()
         g0 = time.perf_counter()
-        if world > 1:
+        if world > 1 and not obs_shard:
             from fmcmc_b200.dist import ChainSharding
             sh = ChainSharding(C * world)
             _, mpsrf = sh.gelman(model, (K + 1) // 2, K + 1, free, C, k, K + 1 - (K + 1) // 2)
@@ -405,9 +425,12 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
-        total_chain_steps = C * world * K
+        cw = 1 if obs_shard else world                                        # observation sharding: the SAME chains on every rank
+        total_chain_steps = C * cw * K
         value = total_chain_steps / (dev_ms * 1e-3)
         n, p_x = wl.n, wl.p_x
+        if obs_shard:
+            n = int(fam.n)                                                      # rank 0's rows: what ITS kernel streams per launch
         alg_bytes = 8.0 * n * (p_x + 1) + 8.0 * C * (3 * k + 2)               # SURVEY §8d, per launch (= per step per GPU)
         hbm_achieved = alg_bytes / (hot_ms * 1e-3) / 1e9
         evals = float(n) * C
@@ -429,27 +452,30 @@ def main():
         kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 1: "mh_resident_kernel"}[path]
         line = {
             "metric": "MH chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "strong" if obs_shard else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.label, "n": n, "p": p_x, "chains_per_gpu": C, "chains_total": C * world,
+            "config": {"workload": wl.label, "n": n, "p": p_x, "chains_per_gpu": C, "chains_total": C * cw,
+                       "sharding": "observations (rows of X split over ranks; partial sums exchanged over NVLink peer memory "
+                                   "inside the kernels)" if obs_shard else "chains",
                        "kernel": wl.kernel_name, "stream": "Philox4x32-10", "path": path,
                        "l2": (f"X ({8e-6 * n * p_x:.0f} MB) is larger than L2 (126 MB) and streamed every step: no flush needed"
                               if path != 1 else "data staged once into shared memory by TMA: on-chip by construction")},
-            "evals_per_s": value * n,
+            "evals_per_s": value * wl.n,
             "accept_rate": accept,
-            "ess_per_s": float(ess.min()) * world / e2e_sec if ess is not None else None,
+            "ess_per_s": float(ess.min()) * cw / e2e_sec if ess is not None else None,
             "ess": {"min_over_params": float(ess.min()), "median_over_params": float(np.median(ess)),
                     "rows_per_chain": K, "chains": C,
                     "method": "per-chain Geyer initial-positive-sequence, summed over rank 0's chains (x n_gpus in ess_per_s); "
                               "time = the e2e call"} if ess is not None else None,
-            "e2e": {"value": C * world * K / e2e_sec, "unit": "chain-steps/s",
+            "e2e": {"value": C * cw * K / e2e_sec, "unit": "chain-steps/s",
                     "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "call": "fmcmc_run via the Python mirror with host numpy buffers (initial pinned): H2D initial + "
                             "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows"},
             "gpu_launches": launches,
             "wall_ms_per_step": 1e3 * t_wall / K,
             "roofline": None, "roofline_other": None,
-            "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * world},
+            "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * cw},
             "clocks": clocks,
         }
         # The many-chain kernel is bound by the FP64 pipe (DFMA / DMMA share one 64-lane datapath per SM; tcgen05 has
