@@ -108,16 +108,22 @@ __device__ int chol_lower_warp(int k, const double* A, double* L, int lane) {
   for (int e = lane; e < k * k; e += FM_WARP) L[e] = 0.0;
   __syncwarp();
   for (int j = 0; j < k; j++) {
-    double s = A[j + j * k];
-    for (int p = 0; p < j; p++) s = xsub(s, xmul(L[j + p * k], L[j + p * k]));
-    if (!(s > 0.0)) return j + 1;  // warp-uniform: every lane computed the same s
-    const double ljj = sqrt(s);
-    __syncwarp();
-    for (int i = j + lane; i < k; i += FM_WARP) {
-      if (i == j) { L[j + j * k] = ljj; continue; }
+    // every row i >= j (lane-strided) forms v_i = A[i][j] - sum_{p<j} L[i][p] L[j][p] in the oracle's order;
+    // row j's value is the pivot s, so the diagonal costs no extra serial pass
+    const int owner = j & (FM_WARP - 1);  // lane that holds row j: rows are dealt out as i = j + lane - owner ...
+    double vj = 0.0;
+    for (int i = j + ((lane - owner) & (FM_WARP - 1)); i < k; i += FM_WARP) {
       double v = A[i + j * k];
       for (int p = 0; p < j; p++) v = xsub(v, xmul(L[i + p * k], L[j + p * k]));
-      L[i + j * k] = xdiv(v, ljj);
+      if (i == j) vj = v;
+      else L[i + j * k] = v;  // un-normalised; divided by the pivot below
+    }
+    const double s = __shfl_sync(FM_FULL, vj, owner);
+    if (!(s > 0.0)) return j + 1;  // warp-uniform
+    const double ljj = sqrt(s);
+    for (int i = j + ((lane - owner) & (FM_WARP - 1)); i < k; i += FM_WARP) {
+      if (i == j) L[j + j * k] = ljj;
+      else L[i + j * k] = xdiv(L[i + j * k], ljj);
     }
     __syncwarp();
   }

@@ -147,3 +147,34 @@ def test_kernel_list_semantics():
     dst[1, :9] = np.eye(3).reshape(-1)
     k.absorb_state(3)
     assert k[1].abs_iter == 7 and np.array_equal(k[1].Sigma, np.eye(3)) and k[1].Mean_t_prev is None
+
+
+def test_observation_sharding_row_slices_partition_the_rows():
+    """dist.ObservationSharding.row_slice: contiguous, even-sized blocks (16-byte aligned columns) that cover [0, n)."""
+    from fmcmc_b200.dist import ObservationSharding
+    for n in (40_006, 1_000_001, 17):
+        for world in (2, 3, 8):
+            covered = []
+            for rank in range(world):
+                sh = ObservationSharding.__new__(ObservationSharding)
+                sh.rank, sh.world = rank, world
+                sl = sh.row_slice(n)
+                covered.append((sl.start, sl.stop))
+                if rank < world - 1:
+                    assert (sl.stop - sl.start) % 2 == 0
+            assert covered[0][0] == 0 and covered[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+
+
+def test_bench_ess_estimator_on_ar1():
+    """bench.py's pooled ESS (Geyer initial positive sequence) recovers (1 - phi) / (1 + phi) on an AR(1) chain."""
+    import bench
+    rng = np.random.default_rng(0)
+    C, T, phi = 40, 3000, 0.8
+    x = np.zeros((C, T, 2))
+    e = rng.standard_normal((C, T, 2))
+    for t in range(1, T):
+        x[:, t, 0] = phi * x[:, t - 1, 0] + e[:, t, 0]
+    x[:, :, 1] = e[:, :, 1]
+    ess = bench.ess_pooled(x) / (C * T)
+    assert abs(ess[0] - (1 - phi) / (1 + phi)) < 0.02 and abs(ess[1] - 1.0) < 0.1
