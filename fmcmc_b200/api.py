@@ -92,6 +92,9 @@ def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_i
         stream = A.marshal_stream(A.STREAM_FED, logu=fed.logu, z=fed.z)
     else:
         stream = A.marshal_stream(A.STREAM_PHILOX, seed=seed, run_index=run_index)
+    obs = getattr(info.MCMC_OUTPUT, "obs_sharding", None)
+    if obs is not None:
+        obs.dist.barrier()                                       # fmcmc_run is collective when observation-sharded
     out = model.run(spec, nsteps, nchains, initial=initial, burnin=burnin, thin=thin, stream=stream,
                     istate=istate, dstate=dstate if dstate.size and A.state_len(spec["type"], k, kernel._kf) else None,
                     flags=A.RUN_APPEND if append else 0, chain_offset=sharding.offset if sharding else 0,
@@ -177,6 +180,7 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
     info.MCMC_init(initial=init_all, nsteps=nsteps, seed=seed, nchains=nchains, burnin=burnin, thin=thin,
                    kernel=kernel, conv_checker=conv_checker)
     info.MCMC_OUTPUT.kernel = kernel
+    info.MCMC_OUTPUT.obs_sharding = obs_sharding
     model = DeviceModel(obs_sharding.local_family(fun) if obs_sharding else fun, device=device)
     if obs_sharding:
         obs_sharding.attach(model, fun.n, 2 * nchains)          # kernel_ram evaluates 2 columns per chain

@@ -480,7 +480,7 @@ static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const 
 }
 
 // DMMA variant (tiled_mma.cuh).  Geometry per padded width PB: (warps, chain tiles per warp).
-struct MmaShape { int PB, warps, NT, MO, osplit; };
+struct MmaShape { int PB, warps, NT, MO, osplit, pipe; };
 // Few columns (chains): all warps share NT*8 chains and split the observations (HBM-bound mapping);
 // many: every warp owns NT*8 chains (FP64-bound mapping).  tiled_mma.cuh explains both.
 static MmaShape mma_shape(int p_x, int ncols, int variant) {
@@ -488,11 +488,14 @@ static MmaShape mma_shape(int p_x, int ncols, int variant) {
     if (ncols <= 8) return MmaShape{32, 8, 1, 2, 1};
     if (ncols <= 16) return MmaShape{32, 8, 2, 2, 1};
     if (ncols <= 128) return MmaShape{32, 8, 4, 2, 1};
-    switch (variant) {  // measured on B200, cfg3: 3.46 / 3.59 / 3.61 / 3.62 ms per launch (profiles/r01_*)
-      case 1: return MmaShape{32, 8, 4, 2, 0};
-      case 2: return MmaShape{32, 8, 8, 1, 0};
-      case 3: return MmaShape{32, 8, 4, 4, 0};
-      default: return MmaShape{32, 16, 4, 1, 0};
+    switch (variant) {  // measured on B200, cfg3, ms per launch (profiles/r01_*): 3.30 default; 3.33 / 3.38 / 3.41 / 3.59 / 3.61 / 3.62
+      case 1: return MmaShape{32, 8, 4, 2, 0, 0};
+      case 2: return MmaShape{32, 8, 8, 1, 0, 0};
+      case 3: return MmaShape{32, 8, 4, 4, 0, 0};
+      case 4: return MmaShape{32, 8, 4, 1, 0, 1};
+      case 6: return MmaShape{32, 16, 4, 1, 0, 1};
+      case 7: return MmaShape{32, 16, 4, 1, 0, 0};
+      default: return MmaShape{32, 8, 4, 2, 0, 1};  // software-pipelined: DMMAs of block t+1 ahead of the epilogue of block t
     }
   }
   if (p_x <= 64) return ncols <= 32 ? MmaShape{64, 8, 4, 1, 1} : MmaShape{64, 8, 4, 1, 0};
@@ -525,32 +528,35 @@ static cudaError_t ensure_packed_tiles(fmcmc_model* m, int PB) {
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 grid, const RunBuffers& rb,
                                     const TiledBuffers& tb) {
-#define TM_CASE(P, W, N, O, S)                                                                                      \
-  if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O && sh.osplit == (S ? 1 : 0)) {                                                             \
+#define TM_CASE(P, W, N, O, S, PP)                                                                                      \
+  if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O && sh.osplit == (S ? 1 : 0) && sh.pipe == (PP ? 1 : 0)) {                                                             \
     const size_t smem = tiled_mma_smem_bytes<P>(FAMILY);                                                         \
     static bool attr_done[64] = {};                                                                              \
     if (!attr_done[m->device]) {                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S>,                    \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S, PP>,                    \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return e;                                                                            \
       attr_done[m->device] = true;                                                                               \
     }                                                                                                            \
-    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
+    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S, PP><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
                                                                                        rb.nchains, tb, rb.err);  \
     return cudaGetLastError();                                                                                   \
   }
-  TM_CASE(32, 8, 1, 2, true)
-  TM_CASE(32, 8, 2, 2, true)
-  TM_CASE(32, 8, 4, 2, true)
-  TM_CASE(32, 8, 4, 2, false)
-  TM_CASE(32, 8, 4, 4, false)
-  TM_CASE(32, 8, 8, 1, false)
-  TM_CASE(32, 16, 4, 1, false)
-  TM_CASE(64, 8, 4, 1, true)
-  TM_CASE(64, 8, 4, 1, false)
-  TM_CASE(128, 4, 2, 1, true)
-  TM_CASE(128, 8, 2, 1, false)
-  TM_CASE(128, 8, 2, 2, false)
+  TM_CASE(32, 8, 1, 2, true, false)
+  TM_CASE(32, 8, 2, 2, true, false)
+  TM_CASE(32, 8, 4, 2, true, false)
+  TM_CASE(32, 8, 4, 2, false, false)
+  TM_CASE(32, 8, 4, 4, false, false)
+  TM_CASE(32, 8, 8, 1, false, false)
+  TM_CASE(32, 16, 4, 1, false, false)
+  TM_CASE(32, 8, 4, 1, false, true)
+  TM_CASE(32, 8, 4, 2, false, true)
+  TM_CASE(32, 16, 4, 1, false, true)
+  TM_CASE(64, 8, 4, 1, true, false)
+  TM_CASE(64, 8, 4, 1, false, false)
+  TM_CASE(128, 4, 2, 1, true, false)
+  TM_CASE(128, 8, 2, 1, false, false)
+  TM_CASE(128, 8, 2, 2, false, false)
 #undef TM_CASE
   return cudaErrorInvalidValue;
 }
@@ -901,7 +907,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         set_err(err, errlen, "'Sigma' is not positive definite (step i = %d, chain %d).", herr[2], herr[1]);
         break;
       case FMCMC_EPEER:
-        set_err(err, errlen, "observation sharding: a peer GPU did not publish its partial sums within 20 s (step i = %d)", herr[2]);
+        set_err(err, errlen, "observation sharding: a peer GPU did not publish its partial sums within 60 s (step i = %d)", herr[2]);
         break;
       case FMCMC_EUNSUP:
         set_err(err, errlen, "the kernel reached a state the reference itself mishandles at step i = %d, chain %d (SURVEY App. D: mirror quirk D8 / adapt update range / t. = 0)", herr[2], herr[1]);

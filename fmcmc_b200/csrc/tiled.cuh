@@ -251,7 +251,7 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       while (*fl < tb.sx.step) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > 20000000000ULL || rb.err[0] != 0) { ok = false; break; }  // 20 s: a peer died
+        if (now - t0 > 60000000000ULL || rb.err[0] != 0) { ok = false; break; }  // 60 s: a peer died / never started
         __nanosleep(200);
       }
     }

@@ -77,7 +77,10 @@ __host__ __device__ inline size_t tiled_mma_smem_bytes(int family) {
 //                 them — the few-chain mapping (the reference's typical 1-4 chains on a huge n).  With <= 16
 //                 chains the FP64 work per observation drops below the time HBM needs to deliver it, and the
 //                 kernel becomes HBM-bound: X streams through the TMA pipeline at the memory roof.
-template <int FAMILY, int PB, bool YBIN, int NWARPS, int NT, int MO, bool OSPLIT>
+// PIPE = true: software pipelining inside the warp — the DMMAs of observation block t+1 are issued before the
+//               epilogue of block t (two C-fragment sets, ping-pong), so the FP64 pipe has independent work
+//               while the epilogue's dependent polynomial chains wait out their latency.
+template <int FAMILY, int PB, bool YBIN, int NWARPS, int NT, int MO, bool OSPLIT, bool PIPE = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
                         TiledBuffers tb, const int* __restrict__ err) {
@@ -177,32 +180,51 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
     const long long row0 = tile * TR;
     const int valid = (int)min((long long)TR, mp.n - row0);  // < TR only for the last tile
     const double* Ag = Xs + t * CS + g;                        // this lane's A-fragment column / row
-    if (valid == TR) {
-#pragma unroll 1
-      for (int o = ofirst; o < TR; o += OSTEP) {  // MO observation tiles x NT chain tiles = MO*NT independent DMMA chains
-        double c[MO][NT][2];
+    auto mma_block = [&](double (&c)[MO][NT][2], int o) {  // MO observation tiles x NT chain tiles = MO*NT independent DMMA chains
+#pragma unroll
+      for (int mo = 0; mo < MO; mo++)
+#pragma unroll
+        for (int ct = 0; ct < NT; ct++) { c[mo][ct][0] = cinit[ct][0]; c[mo][ct][1] = cinit[ct][1]; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        double a[MO];
+#pragma unroll
+        for (int mo = 0; mo < MO; mo++) a[mo] = Ag[ks * 4 * CS + o + 8 * mo];
 #pragma unroll
         for (int mo = 0; mo < MO; mo++)
 #pragma unroll
-          for (int ct = 0; ct < NT; ct++) { c[mo][ct][0] = cinit[ct][0]; c[mo][ct][1] = cinit[ct][1]; }
+          for (int ct = 0; ct < NT; ct++) dmma_m8n8k4(c[mo][ct][0], c[mo][ct][1], a[mo], B[ks][ct]);
+      }
+    };
+    auto epilogue_block = [&](double (&c)[MO][NT][2], int o) {
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-          double a[MO];
+      for (int mo = 0; mo < MO; mo++) {
+        const double yv = ys[o + 8 * mo + g];
 #pragma unroll
-          for (int mo = 0; mo < MO; mo++) a[mo] = Ag[ks * 4 * CS + o + 8 * mo];
-#pragma unroll
-          for (int mo = 0; mo < MO; mo++)
-#pragma unroll
-            for (int ct = 0; ct < NT; ct++) dmma_m8n8k4(c[mo][ct][0], c[mo][ct][1], a[mo], B[ks][ct]);
+        for (int ct = 0; ct < NT; ct++) {
+          acc[ct][0] += tile_term<FAMILY, YBIN>(c[mo][ct][0], yv, sp_tab);
+          acc[ct][1] += tile_term<FAMILY, YBIN>(c[mo][ct][1], yv, sp_tab);
         }
-#pragma unroll
-        for (int mo = 0; mo < MO; mo++) {
-          const double yv = ys[o + 8 * mo + g];
-#pragma unroll
-          for (int ct = 0; ct < NT; ct++) {
-            acc[ct][0] += tile_term<FAMILY, YBIN>(c[mo][ct][0], yv, sp_tab);
-            acc[ct][1] += tile_term<FAMILY, YBIN>(c[mo][ct][1], yv, sp_tab);
-          }
+      }
+    };
+    if (valid == TR) {
+      if (PIPE) {
+        static_assert(!PIPE || ((TR / OSTEP) % 2 == 0), "ping-pong needs an even number of blocks per stage");
+        double c0[MO][NT][2], c1[MO][NT][2];
+        mma_block(c0, ofirst);
+#pragma unroll 1
+        for (int o = ofirst; o < TR; o += 2 * OSTEP) {
+          mma_block(c1, o + OSTEP);
+          epilogue_block(c0, o);
+          if (o + 2 * OSTEP < TR) mma_block(c0, o + 2 * OSTEP);
+          epilogue_block(c1, o + OSTEP);
+        }
+      } else {
+#pragma unroll 1
+        for (int o = ofirst; o < TR; o += OSTEP) {
+          double c[MO][NT][2];
+          mma_block(c, o);
+          epilogue_block(c, o);
         }
       }
     } else {

@@ -316,7 +316,8 @@ int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double*
  *   1. every rank:  fmcmc_shard_alloc()   -> its exchange buffer + CUDA IPC handles
  *   2. all_gather the handles (torch.distributed / MPI / anything)
  *   3. every rank:  fmcmc_shard_attach()  -> opens the peers' buffers; from now on fmcmc_run() is collective:
- *      all ranks must call it with the same run / kernel / stream arguments.                              */
+ *      all ranks must call it with the same run / kernel / stream arguments, within 60 s of each other
+ *      (a rank that waits longer for a peer's partial sums gives up with FMCMC_EPEER).                    */
 typedef struct fmcmc_shard_handles {
   unsigned char partial[64]; /* cudaIpcMemHandle_t of the partial-sum exchange buffer */
   unsigned char flags[64];   /* cudaIpcMemHandle_t of the step flags                  */

@@ -125,6 +125,29 @@ def test_fixed_and_bounds(readme_data):
     assert d[:, 2].min() >= 3.5 and d[:, 2].max() <= 4.5
 
 
+def test_restart_from_mcmc_list_and_kernel_reuse(readme_data):
+    """inst/tinytest/test-mcmc.R:252-267 (initial = a previous mcmc.list) and the workflow vignette's kernel reuse
+    (vignettes/workflow-with-fmcmc.Rmd:162-252): the second run starts from the last row of the first one, and the
+    adaptive kernel's state (abs_iter, Sigma, Mean_t_prev) carries over through the kernel object."""
+    ll = _readme_ll(readme_data)
+    kern = fm.kernel_adapt(warmup=100, lb=[np.nan, np.nan, 0.0])
+    a = fm.MCMC(np.tile([3.0, 2.0, 4.0], (3, 1)), ll, 400, nchains=3, seed=5, kernel=kern)
+    assert kern.is_list and [kc.abs_iter for kc in kern] == [399] * 3
+    sig1 = [kc.Sigma.copy() for kc in kern]
+    b = fm.MCMC(a, ll, 300, nchains=3, seed=6, kernel=kern)            # restart: initial = the mcmc.list
+    assert [kc.abs_iter for kc in kern] == [399 + 299] * 3
+    for c in range(3):
+        assert np.array_equal(b[c].data[0], a[c].data[-1])              # first row = where the last run stopped
+        assert not np.array_equal(kern[c].Sigma, sig1[c])               # still adapting, from the carried state
+        assert np.all(np.linalg.eigvalsh(kern[c].Sigma) > 0)
+    x = b.as_array()
+    X1 = np.c_[np.ones(readme_data["n"]), readme_data["X"]]
+    bhat = np.linalg.lstsq(X1, readme_data["y"], rcond=None)[0]
+    assert np.all(np.abs(x[:, :, :2].mean(axis=(0, 1)) - bhat) < 0.25)
+    with pytest.raises(ValueError, match="nchains"):
+        fm.MCMC(a, ll, 100, nchains=2, kernel=fm.kernel_normal())       # R/mcmc.R:382-392
+
+
 def test_ordered_scheme_alternates(readme_data):
     """inst/tinytest/test-kernel_normal.R:92-98"""
     ll = _readme_ll(readme_data)
