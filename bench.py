@@ -449,7 +449,7 @@ def main():
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
         pipe_util = evals * wl.fp64_instr_per_eval / 32.0 / (hot_ms * 1e-3) / pipe_slots
-        kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 1: "mh_resident_kernel"}[path]
+        kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 4: "tiled_loglik_i8_kernel", 1: "mh_resident_kernel"}[path]
         line = {
             "metric": "MH chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,

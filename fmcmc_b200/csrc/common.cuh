@@ -48,6 +48,9 @@ struct ModelParams {
   const int* group; // [ld]
   double h0, h1;
   const double* Xt;      // tile-major copy of X / y for the DMMA kernel (tiled_mma.cuh), or null
+  const unsigned char* Xq;  // tile-major int8 slices of X (+ y) for the tcgen05 kernel (tiled_i8.cuh), or null
+  const int* i8_cexp;       // [p_x] column exponents of the slicing
+  const double* i8_sxy;     // [p_x] sum_i (y_i - 1/2) x_ij (binary logistic)
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
 };
 

@@ -19,6 +19,7 @@
 #include "resident.cuh"
 #include "tiled.cuh"
 #include "tiled_mma.cuh"
+#include "tiled_i8.cuh"
 
 // --------------------------------------------------------------------------------
 // small host utilities
@@ -69,14 +70,18 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group, sp_tab, Xt;
+  DevBuf X, y, group, sp_tab, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
+  int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
+  int i8_slices = 0;      // int8 slices per operand of path 4: 0 = 6, or 7 for kernel_ram whose adaptation consumes f itself
+                          // (FMCMC_I8_SLICES = 6 | 7 overrides; tiled_i8.cuh has the error bound)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
   int smem_optin = 0;
   int forced_path = 0;
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
+  int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
   int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
   // run buffers (grow-only)
   DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
@@ -229,7 +234,10 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   MC(ensure(m->nacc, sizeof(unsigned long long)));
 #undef MC
   if (const char* v = getenv("FMCMC_TILED_VARIANT")) { if (atoi(v) == 2 || atoi(v) == 3) m->tiled_default = atoi(v); }
+  if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
+  if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
+  if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= 6 && atoi(v) <= 7) m->i8_slices = atoi(v); }
   *out = m;
   return FMCMC_OK;
 }
@@ -245,7 +253,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->Xt, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
@@ -340,7 +348,7 @@ extern "C" int fmcmc_shard_attach(fmcmc_model* m, int rank, int world, const fmc
 }
 
 extern "C" int fmcmc_set_path(fmcmc_model* m, int path) {
-  if (!m || path < 0 || path > 3) return FMCMC_EINVAL;
+  if (!m || path < 0 || path > 4) return FMCMC_EINVAL;
   m->forced_path = path;
   return FMCMC_OK;
 }
@@ -561,6 +569,85 @@ static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 gri
   return cudaErrorInvalidValue;
 }
 
+// ---- path 4: split-integer tensor-core kernel (tiled_i8.cuh) ------------------------------------------
+static int i8_kblocks(int p_x) { return p_x <= 32 ? 1 : (p_x <= 64 ? 2 : 4); }
+static int i8_tile_rows(int KB) { return KB == 1 ? 128 : (KB == 2 ? 64 : 32); }
+#define I8_FOR_SHAPES(X) X(6, 1) X(6, 2) X(6, 4) X(7, 1) X(7, 2) X(7, 4)
+// Builds the int8 slice tiles of X once per model.  Returns cudaErrorNotSupported when X holds non-finite
+// values (or magnitudes beyond the exponent window): the caller falls back to the FP64 kernels.
+static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
+  if (m->xq_NS == NS && m->xq_KB == KB) return cudaSuccess;
+  if (m->xq_NS == -1) return cudaErrorNotSupported;
+  const ModelParams& mp = m->mp;
+  const int TO = i8_tile_rows(KB);
+  const long long ntiles = (mp.n + TO - 1) / TO;
+  size_t stage_bytes = 0;
+#define I8_CASE(N, K) if (NS == N && KB == K) stage_bytes = I8Geom<N, K>::STAGE_BYTES;
+  I8_FOR_SHAPES(I8_CASE)
+#undef I8_CASE
+  if (!stage_bytes) return cudaErrorInvalidValue;
+  cudaError_t e = ensure(m->Xq, (size_t)ntiles * stage_bytes);
+  if (e != cudaSuccess) return e;
+  e = ensure(m->xq_bad, sizeof(int));
+  if (e != cudaSuccess) return e;
+  // aux: [p_x] column maxima (u64 bit patterns) | [p_x] sxy (f64) | [p_x] column exponents (i32)
+  const size_t px = (size_t)mp.p_x;
+  e = ensure(m->xq_aux, px * 8 + px * 8 + px * 4);
+  if (e != cudaSuccess) return e;
+  unsigned long long* colmax = m->xq_aux.as<unsigned long long>();
+  double* sxy = reinterpret_cast<double*>(colmax + px);
+  int* cexp = reinterpret_cast<int*>(sxy + px);
+  e = cudaMemsetAsync(m->xq_bad.p, 0, sizeof(int), m->stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(m->xq_aux.p, 0, px * 20, m->stream);
+  if (e != cudaSuccess) return e;
+  unsigned char* xq = m->Xq.as<unsigned char>();
+  const unsigned ychunks = (unsigned)std::min<long long>(64, (mp.n + 255) / 256);
+  i8_colmax_kernel<<<dim3((unsigned)mp.p_x, ychunks), 256, 0, m->stream>>>(mp.X, mp.n, mp.ld, colmax, m->xq_bad.as<int>());
+  i8_colexp_kernel<<<(mp.p_x + 127) / 128, 128, 0, m->stream>>>(colmax, mp.p_x, cexp);
+  i8_sxy_kernel<<<(unsigned)mp.p_x, 1024, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, sxy);
+#define I8_CASE(N, K) if (NS == N && KB == K) pack_i8_kernel<N, K><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, mp.p_x, cexp, xq);
+  I8_FOR_SHAPES(I8_CASE)
+#undef I8_CASE
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int bad = 0;
+  e = cudaMemcpyAsync(&bad, m->xq_bad.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(m->stream);
+  if (e != cudaSuccess) return e;
+  if (bad) { m->xq_NS = -1; release(m->Xq); return cudaErrorNotSupported; }
+  m->mp.i8_cexp = cexp;
+  m->mp.i8_sxy = sxy;
+  m->mp.Xq = xq;
+  m->xq_NS = NS;
+  m->xq_KB = KB;
+  return cudaSuccess;
+}
+
+#define I8_EPI_WARPS 16   // 4 epilogue warps per TMEM lane quarter, 8 observations each per block (B200: 2.37 ms per cfg3
+#define I8_EPI_CHUNK 8    // launch; 8 warps x 2 chunks of 8: 2.78 ms; 16 x 2 chunks of 4: 2.75 ms - profiles/r01_i8_*.txt)
+template <int FAMILY, bool YBIN>
+static cudaError_t launch_tiled_i8(fmcmc_model* m, int NS, int KB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
+#define I8_CASE(N, K)                                                                                             \
+  if (NS == N && KB == K) {                                                                                       \
+    const size_t smem = tiled_i8_smem_bytes<N, K>(FAMILY);                                                        \
+    static bool attr_done[64] = {};                                                                               \
+    if (!attr_done[m->device]) {                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(tiled_loglik_i8_kernel<FAMILY, YBIN, N, K, I8_EPI_WARPS, I8_EPI_CHUNK>, \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      if (e != cudaSuccess) { cudaGetLastError(); return e; }                                                     \
+      attr_done[m->device] = true;                                                                                \
+    }                                                                                                             \
+    tiled_loglik_i8_kernel<FAMILY, YBIN, N, K, I8_EPI_WARPS, I8_EPI_CHUNK>                                        \
+        <<<grid, (I8_EPI_WARPS + 2) * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, rb.nchains, tb, rb.err);  \
+    return cudaGetLastError();                                                                                    \
+  }
+  I8_FOR_SHAPES(I8_CASE)
+#undef I8_CASE
+  return cudaErrorInvalidValue;
+}
+
 extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec* ks,
                          fmcmc_kernel_state* state, const fmcmc_stream_spec* stream, double* ans_out,
                          double* draws_out, double* logpost_out, fmcmc_run_report* report, char* err,
@@ -719,11 +806,32 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   const bool tiled_ok = lm_or_logit && mp.p_x <= 128;
   int path = m->forced_path;
   if (m->shard_world > 1) path = 3;
-  if (path == 0)  // narrow X: the DFMA kernel's 8 / 16-column tiers do no padded work; wide X: DMMA
-    path = (tiled_ok && data_bytes > 96 * 1024) ? (mp.p_x > 32 ? 3 : (mp.p_x <= 16 ? 2 : m->tiled_default)) : 1;
-  if ((path == 2 && !(lm_or_logit && mp.p_x <= 32)) || (path == 3 && !tiled_ok)) {
-    set_err(err, errlen, "the observation-tiled paths support gaussian_lm / logistic with p_x <= 32 (path 2) or <= 128 (path 3); got family %d, p_x %d", mp.family, mp.p_x);
+  if (path == 0) {
+    // narrow X: the DFMA kernel's 8 / 16-column tiers do no padded work.  Otherwise, many likelihood columns (chains):
+    // the split-integer tcgen05 kernel (path 4), whose FP64 pipe only runs the family epilogue; few columns: the
+    // DMMA kernel's observation-split mapping, which is HBM-bound (tiled_mma.cuh)
+    const int ncols_auto = is_ram ? 2 * C : C;
+    path = (tiled_ok && data_bytes > 96 * 1024)
+               ? (mp.p_x <= 16 ? 2 : ((ncols_auto > 128 && m->tiled_default != 2) ? m->tiled_many : (mp.p_x > 32 ? 3 : m->tiled_default)))
+               : 1;
+  }
+  if ((path == 2 && !(lm_or_logit && mp.p_x <= 32)) || ((path == 3 || path == 4) && !tiled_ok)) {
+    set_err(err, errlen, "the observation-tiled paths support gaussian_lm / logistic with p_x <= 32 (path 2) or <= 128 (paths 3, 4); got family %d, p_x %d", mp.family, mp.p_x);
     return FMCMC_EUNSUP;
+  }
+  const int i8_NS = m->i8_slices ? m->i8_slices : (is_ram ? 7 : 6), i8_KB = i8_kblocks(mp.p_x);
+  if (path == 4) {  // int8 slice tiles of X (once per model); X with non-finite entries cannot be sliced
+    cudaError_t pe = ensure_packed_i8(m, i8_NS, i8_KB);
+    if (pe == cudaErrorNotSupported) {
+      if (m->forced_path == 4) { set_err(err, errlen, "path 4 (split-integer tensor cores) needs finite X with |x| < 2^480"); return FMCMC_EUNSUP; }
+      path = 3;
+    } else if (pe == cudaErrorMemoryAllocation) {
+      set_err(err, errlen, "out of device memory for the int8 slice tiles of X");
+      return FMCMC_ENOMEM;
+    } else if (pe != cudaSuccess) {
+      set_err(err, errlen, "CUDA error %s (pack_i8)", cudaGetErrorString(pe));
+      return FMCMC_ECUDA;
+    }
   }
   long long launches = 0;
   int hot_timed = 0;
@@ -775,8 +883,8 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const int PB = mp.p_x <= 8 ? 8 : (mp.p_x <= 16 ? 16 : 32);
     const int ncols_all = is_ram ? 2 * C : C;
     const MmaShape msh = mma_shape(mp.p_x, ncols_all, m->mma_wide);
-    const int cpb = path == 3 ? (msh.osplit ? msh.NT * 8 : msh.warps * msh.NT * 8) : TL_CHAINS;   // chains per CTA
-    const int tile_rows = path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE;
+    const int cpb = path == 4 ? I8_CHAINS : (path == 3 ? (msh.osplit ? msh.NT * 8 : msh.warps * msh.NT * 8) : TL_CHAINS);   // chains per CTA
+    const int tile_rows = path == 4 ? i8_tile_rows(i8_KB) : (path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE);
     if (path == 3) {
       cudaError_t pe = ensure_packed_tiles(m, msh.PB);
       if (pe == cudaErrorMemoryAllocation) { set_err(err, errlen, "out of device memory for the tile-major copy of X"); return FMCMC_ENOMEM; }
@@ -810,7 +918,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       tb.partial = m->partial.as<double>();
       tb.gx_total = gx;
     }
-    const dim3 lgrid = path == 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
+    const dim3 lgrid = path >= 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
     const size_t mat_bytes = adaptive ? (size_t)4 * kf * kf * 8 : 0;
@@ -851,7 +959,12 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         }
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed], m->stream);
         cudaError_t e;
-        if (path == 3)
+        if (path == 4)
+          e = (mp.family == FMCMC_FAMILY_LOGISTIC)
+                  ? (mp.y_binary ? launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, true>(m, i8_NS, i8_KB, lgrid, rb, tb)
+                                 : launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, false>(m, i8_NS, i8_KB, lgrid, rb, tb))
+                  : launch_tiled_i8<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, i8_NS, i8_KB, lgrid, rb, tb);
+        else if (path == 3)
           e = (mp.family == FMCMC_FAMILY_LOGISTIC)
                   ? (mp.y_binary ? launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, true>(m, msh, lgrid, rb, tb)
                                  : launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, false>(m, msh, lgrid, rb, tb))

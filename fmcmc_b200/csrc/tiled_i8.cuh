@@ -1,0 +1,524 @@
+// tiled_i8.cuh — observation-tiled likelihood kernel, split-integer tensor-core variant (path 4).
+//
+// Same contract and grid as tiled_loglik_mma_kernel (tiled_mma.cuh): a CTA owns one observation slice and
+// one block of chains and writes partial[slice][chain].  What changes is where the X.Theta contraction runs.
+// The FP64 pipe is the binding roof of paths 2 / 3, and 32 of its 51 instruction slots per
+// evaluation are the dot product.  tcgen05 has no FP64 kind, but B200's 5th-generation tensor cores multiply
+// int8 with exact int32 accumulation (tcgen05.mma kind::i8, SASS UTCIMMA), so the product is computed
+// EXACTLY on integer slices of the operands (Ozaki splitting) and only reassembled in FP64:
+//
+//   row i of X:     x_ij   = 2^ex_i  * sum_s  sx_s[i][j] * 2^(-6 - 7 s),   sx_s in [-64, 64]   (once per model)
+//   chain c:        th_cj  = 2^eth_c * sum_s  sth_s[c][j] * 2^(-6 - 7 s)                        (once per launch)
+//   eta_ic = 2^(ex_i + eth_c - 12) * sum_d 2^(-7 d) * a_d,     a_d = sum_{s + s' = d} sum_j sx_s[i][j] sth_s'[c][j]
+//
+// a_d (d = 0 .. NS-1) are int32 accumulators in tensor memory, one tcgen05.mma per slice pair (NS (NS+1) / 2
+// instructions of M = 128 chains x N = 32 observations x K = 32 per block).  Dropping the pairs with
+// s + s' >= NS leaves an absolute error of ~2^(-7 NS - 5) * 2^(ex + eth) in eta (NS = 6: ~1e-12 |x|max |th|max —
+// the size of the FP64 rounding error of the 32-term dot product is ~1e-15; the log-posterior, a sum over n
+// terms with unbiased errors, stays ~1e-15 relative; tests/test_gpu_i8.py measures it).  Everything is integer
+// until the reassembly, so results are bit-reproducible and independent of how chains are grouped into CTAs
+// (per-row and per-chain exponents, no block-wide scaling).
+//
+// Mapping: TMEM lane = chain (A operand = Theta slices, written once per launch into tensor memory with
+// tcgen05.st when they fit, else shared memory), TMEM column = observation (B operand = the X slice tile,
+// streamed from HBM by one cp.async.bulk per stage in exactly the core-matrix layout the MMA reads).  An epilogue
+// thread owns one chain: it reads the NS accumulators of an observation with tcgen05.ld, reassembles eta with
+// 6 FP64 instructions (pairs of diagonals are merged in int32 first), runs the family epilogue and adds to a
+// private sum — no cross-lane reduction.  Warp roles: 8 epilogue warps (two per TMEM lane quarter, splitting
+// the 32 columns), 1 TMA producer, 1 MMA issuer; accumulators are double-buffered in TMEM so the tensor pipe
+// works on block t+1 while the FP64 pipe finishes block t.
+//
+// FP64-pipe slots per evaluation: 6 (reassembly) + 19 (logistic epilogue) = 25 against 51 on path 3; Gaussian:
+// 6 + 2 against 2 p_x + 2.
+#pragma once
+#include "tiled.cuh"
+
+#define I8_CHAINS 128
+#define I8_MAX_EPI_WARPS 16
+
+template <int NS, int KB>
+struct I8Geom {
+  static constexpr int BLK = 32;                                    // observations per MMA block (instruction N)
+  static constexpr int TO = KB == 1 ? 128 : (KB == 2 ? 64 : 32);    // observations per pipeline stage
+  static constexpr int NBLK = TO / BLK;
+  static constexpr int SLAB_BYTES = BLK * 32;                        // one slice x one K block of a 32-observation block: 4 groups x 2 chunks x 128 B
+  static constexpr int BLOCK_BYTES = KB * NS * SLAB_BYTES;           // [kb][slice][group][chunk][8 rows][16 B]
+  static constexpr int SLICE_BYTES = NBLK * BLOCK_BYTES;
+  static constexpr int META_BYTES = TO * 8;                         // y per observation (unused by the binary-logistic epilogue)
+  static constexpr int STAGE_BYTES = SLICE_BYTES + META_BYTES;
+  static constexpr int STAGES = KB == 4 ? 3 : 4;                    // KB = 4: 96 KB of Theta slices share the shared memory
+  static constexpr int ACC_COLS = NS * BLK;                         // TMEM columns of one accumulator set
+  static constexpr bool A_TMEM = (2 * ACC_COLS + NS * KB * 8) <= 512;
+  static constexpr int A_COL0 = 2 * ACC_COLS;
+  static constexpr int A_SMEM_BYTES = A_TMEM ? 0 : NS * KB * 4096;
+  static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
+};
+
+template <int NS, int KB>
+__host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
+  using G = I8Geom<NS, KB>;
+  size_t b = 128 + (size_t)G::STAGES * G::STAGE_BYTES + G::A_SMEM_BYTES +
+             (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
+  return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
+}
+
+// ---- slicing -----------------------------------------------------------------------------------------
+#define I8_EMAX 480
+// smallest exponent e (clamped) with m < 2^e
+__device__ __forceinline__ int i8_exponent(double m) {
+  if (!(m > 0.0)) return 0;
+  const int e = ilogb(m) + 1;
+  return max(-I8_EMAX, min(I8_EMAX, e));
+}
+// |u| <= 1  ->  u = sum_s s[s] 2^(-6 - 7 s) + O(2^(-7 NS + 1)), every step exact in FP64
+template <int NS>
+__device__ __forceinline__ void i8_slices(double u, int (&s)[NS]) {
+  double r = u * 64.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double q = rint(r);
+    s[i] = (int)q;
+    r = (r - q) * 128.0;
+  }
+}
+
+// Tile-major int8 copy of X (+ y and the row exponents), built once per model: tile t of TO observations is
+// stored exactly as a pipeline stage sits in shared memory:
+//   [block b = obs / 32][k block kb][slice s][group g = (obs % 32) / 8][chunk c = (k % 32) / 16][row = obs % 8][16 bytes k % 16]
+//   then meta[TO]
+// i.e. 128-byte core matrices (8 rows x 16 B) in the canonical K-major no-swizzle operand layout of tcgen05.mma
+// (leading byte offset 128 between the two K chunks, stride byte offset 256 between row groups).  Inside a block and
+// a K block the slices are CONSECUTIVE row groups, so slices 0 .. NS-1-j of a block form ONE B operand with
+// N = 32 (NS - j) rows: a single MMA multiplies Theta slice j with all of them, and because slice s lands
+// 32 s columns further right, its product falls on the accumulator columns of diagonal s + j.
+// column maxima (as the bit patterns of non-negative doubles, which order like integers) + non-finite check
+__global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ X, long long n, long long ld,
+                                                       unsigned long long* __restrict__ colmax_bits, int* __restrict__ bad) {
+  const int j = blockIdx.x;
+  double m = 0.0;
+  bool nf = false;
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.y * blockDim.x) {
+    const double a = fabs(X[(size_t)j * ld + i]);
+    if (!(a < 0x1p480)) nf = true;  // NaN, Inf or beyond the exponent window
+    else m = fmax(m, a);
+  }
+  if (nf) atomicOr(bad, 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FM_FULL, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&colmax_bits[j], (unsigned long long)__double_as_longlong(m));
+}
+// column exponents: x'_ij = x_ij 2^-cexp[j] in (-1, 1); theta'_j = theta_j 2^cexp[j] keeps every product unchanged
+__global__ void i8_colexp_kernel(const unsigned long long* __restrict__ colmax_bits, int p_x, int* __restrict__ cexp) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < p_x) cexp[j] = i8_exponent(__longlong_as_double((long long)colmax_bits[j]));
+}
+// sxy[j] = sum_i (y_i - 1/2) x_ij, fixed-order reduction (one CTA per column): the linear part of the binary
+// logistic log-likelihood, sum_i [y_i eta_i - eta_i / 2] = theta . sxy, leaves the per-evaluation epilogue
+__global__ void __launch_bounds__(1024) i8_sxy_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n,
+                                                     long long ld, double* __restrict__ sxy) {
+  __shared__ double red[1024];
+  const int j = blockIdx.x, t = threadIdx.x;
+  double hi = 0.0, lo = 0.0;  // compensated (two-sum) partial
+  for (long long i = t; i < n; i += 1024) {
+    const double v = (y[i] - 0.5) * X[(size_t)j * ld + i];
+    const double s = hi + v, bb = s - hi;
+    lo += (hi - (s - bb)) + (v - bb);
+    hi = s;
+  }
+  red[t] = hi + lo;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t == 0) sxy[j] = red[0];
+}
+
+template <int NS, int KB>
+__global__ void pack_i8_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n, long long ld,
+                               int p_x, const int* __restrict__ cexp, unsigned char* __restrict__ Xq) {
+  using G = I8Geom<NS, KB>;
+  const long long tile = blockIdx.x;
+  const int t = threadIdx.x;  // blockDim.x == TO
+  const long long row = tile * G::TO + t;
+  unsigned char* dst = Xq + (size_t)tile * G::STAGE_BYTES;
+  const bool valid = row < n;
+  unsigned char* grp = dst + (size_t)(t / G::BLK) * G::BLOCK_BYTES + ((t % G::BLK) / 8) * 256 + (t % 8) * 16;
+  for (int kb = 0; kb < KB; kb++)
+    for (int c = 0; c < 2; c++) {
+      uint32_t w[NS][4];
+#pragma unroll
+      for (int i = 0; i < NS; i++) w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const int j = kb * 32 + c * 16 + q;
+        const double u = (valid && j < p_x) ? scalbn(X[(size_t)j * ld + row], -cexp[j]) : 0.0;
+        int s[NS];
+        i8_slices<NS>(u, s);
+#pragma unroll
+        for (int i = 0; i < NS; i++) w[i][q / 4] |= (uint32_t)(uint8_t)(int8_t)s[i] << (8 * (q % 4));
+      }
+#pragma unroll
+      for (int i = 0; i < NS; i++)
+        *reinterpret_cast<uint4*>(grp + (size_t)(kb * NS + i) * G::SLAB_BYTES + c * 128) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+    }
+  *reinterpret_cast<double*>(dst + G::SLICE_BYTES + t * 8) = valid ? y[row] : 0.0;
+}
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+// D[tmem] (+)= A * B, int8 x int8 -> int32; A from tensor memory or shared memory, B from shared memory
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_x8(uint32_t taddr, const uint32_t (&w)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(w[0]), "r"(w[1]),
+               "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+template <int CH>
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&v)[CH]) {
+  static_assert(CH == 4 || CH == 8, "4 or 8 columns per load");
+  if (CH == 8)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4 % CH]), "=r"(v[5 % CH]), "=r"(v[6 % CH]), "=r"(v[7 % CH])
+                 : "r"(taddr)
+                 : "memory");
+  else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// wait for this thread's tcgen05.ld's; the registers are threaded through so no use can be scheduled above it
+template <int NS, int CH>
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&a)[NS][CH]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int d = 0; d < NS; d++)
+#pragma unroll
+    for (int e = 0; e < CH; e++) asm volatile("" : "+r"(a[d][e]));
+}
+// mbarrier wait for the single-thread roles: back off instead of spinning in the issue slots the epilogue needs
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
+}
+
+// t = sum_d a_d 2^(7 (NS - 1 - d)), exact: adjacent diagonals are merged in int32 (|a_d| <= (d+1) * 32 KB * 4096 < 2^24),
+// up to three merged pairs in int64, then ONE conversion (I2F.F64.S64, off the FP64 pipe) per group
+template <int NS, int CH>
+__device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e) {
+  int v[(NS + 1) / 2];
+#pragma unroll
+  for (int p = 0; p < NS / 2; p++) v[p] = (int)a[2 * p][e] * 128 + (int)a[2 * p + 1][e];
+  if (NS & 1) v[NS / 2] = (int)a[NS - 1][e];
+  if (NS <= 6) {  // 32 x 32 -> 64-bit multiply-adds (IMAD.WIDE)
+    constexpr int NV = (NS + 1) / 2;
+    long long w = v[NV - 1];
+#pragma unroll
+    for (int p = NV - 2; p >= 0; p--) w += (long long)v[p] * (int)(1u << (7 * (NS - 2 - 2 * p)));
+    return __ll2double_rn(w);
+  } else {  // 7, 8: two groups
+    const long long hi = (long long)v[0] * 16384LL + v[1];
+    const long long lo = (long long)v[2] * ((NS & 1) ? 128LL : 16384LL) + v[3];
+    return fma(__ll2double_rn(hi), (NS & 1) ? 2097152.0 : 268435456.0, __ll2double_rn(lo));
+  }
+}
+
+// Binary logistic regression without the per-observation response: with z = +-eta,
+//   sum_i [min(z_i, 0) - log1p(exp(-|z_i|))] = theta . sxy - sum_i [ |eta_i| / 2 + log1p(exp(-|eta_i|)) ]
+// (y_i eta_i - max(eta_i, 0) = (y_i - 1/2) eta_i - |eta_i| / 2), so the epilogue only accumulates the even function
+// of eta: 19 FP64 instructions, no select, no load of y.  eta is finite here (non-finite Theta never gets this far).
+__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(eta), lo = __double2loint(eta);
+  // |eta| clamped near 64 on the high word alone (>= 64 -> [64, 64 + 2^-14]: table entry 2048, tiny remainder)
+  const double a = __hiloint2double(min(hi & 0x7fffffff, 0x40500000), lo);
+  const double MAGIC = 6755399441055744.0;
+  const double t = fma(a, (double)FM_SP_H, MAGIC);
+  const int k = __double2loint(t);
+  const double d = fma(t - MAGIC, -1.0 / FM_SP_H, a);
+  const double2 sg = tab[k];
+  double q = -0x1.6c175d75f692ap-10;  // same polynomials as fm_softplus_tab_core (softplus.h)
+  q = fma(q, d, 0x1.1111ad1af8af9p-7);
+  q = fma(q, d, -0x1.5555555538138p-5);
+  q = fma(q, d, 0x1.555555551ad1ap-3);
+  q = fma(q, d, -0x1.0000000000000p-1);
+  q = fma(q, d, 0x1.0000000000000p+0);
+  const double v = (sg.x * d) * -q;
+  double L = -0x1.555b6df3e4efdp-3;
+  L = fma(L, v, 0x1.99a091298881fp-3);
+  L = fma(L, v, -0x1.fffffff6b5a52p-3);
+  L = fma(L, v, 0x1.555555500646bp-2);
+  L = fma(L, v, -0x1.0000000000008p-1);
+  L = fma(L, v, 0x1.0000000000005p+0);
+  acc_abs = fma(0.5, fabs(eta), acc_abs);
+  acc_g = fma(v, L, acc_g + sg.y);
+}
+
+template <int FAMILY, bool YBIN, int NS, int KB, int EW, int CH>
+__global__ void __launch_bounds__((EW + 2) * 32, 1)
+tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
+                       TiledBuffers tb, const int* __restrict__ err) {
+  using G = I8Geom<NS, KB>;
+  static_assert(NS >= 2 && NS <= 8, "2..8 slices");
+  static_assert(EW == 8 || EW == 16, "2 or 4 epilogue warps per TMEM lane quarter");
+  constexpr int NTHREADS = (EW + 2) * 32;
+  constexpr int CW = G::BLK / (EW / 4);  // columns (observations) of a block owned by one epilogue warp
+  static_assert(CW % CH == 0, "whole chunks");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + G::STAGES;
+  uint64_t* acc_full = empty + G::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned char* stage0 = smem_raw + 128;
+  unsigned char* sA = stage0 + (size_t)G::STAGES * G::STAGE_BYTES;
+  double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
+  double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sp_tab) +
+                                          (FAMILY == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W_TMA = EW, W_MMA = EW + 1;
+  if (err[0] != 0) return;
+  const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
+  const long long ntiles = (mp.n + G::TO - 1) / G::TO;
+  const long long first = slice, step = tb.gx;
+  const int p_x = mp.p_x;
+
+  if (tid == 0) {
+    for (int s = 0; s < G::STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1 + EW);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], EW);
+    }
+    mbar_fence_init();
+  }
+  if (warp == W_MMA) {  // the allocating warp also frees
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
+    const double2* gt = reinterpret_cast<const double2*>(mp.sp_tab);
+    for (int e = tid; e < FM_SP_ENTRIES; e += NTHREADS) sp_tab[e] = gt[e];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- this thread's chain: exponent, intercept; threads 0..127 also slice Theta into the A operand ----
+  const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
+  const int lchain = tid & (I8_CHAINS - 1);
+  const int col = chain_block * I8_CHAINS + lchain;
+  const double* th = nullptr;
+  if (warp < EW && col < tb.ncols) th = col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
+  double thmax = 0.0, b0 = 0.0, lin = 0.0;
+  bool th_nan = false, th_big = false;
+  if (th) {
+    for (int j = 0; j < p_x; j++) {
+      const double v = th[icpt + j];
+      const double a = fabs(scalbn(v, mp.i8_cexp[j]));  // theta'_j = theta_j 2^cexp[j]
+      if (a != a) th_nan = true;
+      else if (!(a < 0x1p480)) th_big = true;
+      thmax = fmax(thmax, a);
+      if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) lin = fma(v, mp.i8_sxy[j], lin);
+    }
+    if (icpt) b0 = th[0];
+  }
+  const bool th_bad = th_nan || th_big;
+  const int eth = th_bad ? 0 : i8_exponent(thmax);
+  const double csc = __hiloint2double((1023 - G::SHIFT + eth) << 20, 0);  // eta = t * 2^(eth - SHIFT)
+  if (tid < I8_CHAINS) {
+    for (int kb = 0; kb < KB; kb++) {
+      uint32_t w[NS][8];
+#pragma unroll
+      for (int i = 0; i < NS; i++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) w[i][q] = 0u;
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int j = kb * 32 + q;
+        const double u = (th && !th_bad && j < p_x) ? scalbn(th[icpt + j], mp.i8_cexp[j] - eth) : 0.0;
+        int s[NS];
+        i8_slices<NS>(u, s);
+#pragma unroll
+        for (int i = 0; i < NS; i++) w[i][q / 4] |= (uint32_t)(uint8_t)(int8_t)s[i] << (8 * (q % 4));
+      }
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        if (G::A_TMEM) {
+          tc_st_x8(tmem + G::A_COL0 + (i * KB + kb) * 8 + ((uint32_t)(warp * 32) << 16), w[i]);
+        } else {
+          unsigned char* p = sA + (size_t)(i * KB + kb) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
+          *reinterpret_cast<uint4*>(p) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+          *reinterpret_cast<uint4*>(p + 128) = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
+        }
+      }
+    }
+    if (G::A_TMEM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == W_TMA) {
+    // ===== producer: one bulk copy per stage =====
+    if (lane == 0) {
+      long long it = 0;
+      for (long long tile = first; tile < ntiles; tile += step, it++) {
+        const int s = (int)(it % G::STAGES);
+        const uint32_t ph = (uint32_t)((it / G::STAGES) & 1);
+        mbar_wait_sleep(&empty[s], ph ^ 1u, 256);
+        mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
+        bulk_g2s(stage0 + (size_t)s * G::STAGE_BYTES, mp.Xq + (size_t)tile * G::STAGE_BYTES, (uint32_t)G::STAGE_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===== MMA issuer: NS * KB instructions per block of 32 observations (N = 32 (NS - j)) =====
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, K-major, N >> 3, M >> 4
+      constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_CHAINS >> 4) << 24);
+      const uint32_t sA_addr = smem_u32(sA);
+      uint32_t blk = 0;
+      long long it = 0;
+      for (long long tile = first; tile < ntiles; tile += step, it++) {
+        const int s = (int)(it % G::STAGES);
+        mbar_wait_sleep(&full[s], (uint32_t)((it / G::STAGES) & 1), 64);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(stage0 + (size_t)s * G::STAGE_BYTES);
+#pragma unroll 1
+        for (int b = 0; b < G::NBLK; b++, blk++) {
+          const uint32_t buf = blk & 1u;
+          mbar_wait_sleep(&acc_empty[buf], ((blk >> 1) & 1u) ^ 1u, 64);
+          tc_fence_after();
+          const uint32_t bblk = sbase + (uint32_t)b * G::BLOCK_BYTES;
+          const uint32_t dbase = tmem + buf * G::ACC_COLS;
+#pragma unroll
+          for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {  // Theta slice j times X slices 0 .. NS-1-j at once: diagonals j .. NS-1
+              const uint32_t idesc = IDESC0 | ((uint32_t)((G::BLK * (NS - j)) >> 3) << 17);
+              const uint64_t bdesc = tc_smem_desc(bblk + (uint32_t)(kb * NS) * G::SLAB_BYTES, 128u, 256u);
+              const uint32_t accum = (j > 0 || kb > 0) ? 1u : 0u;
+              if (G::A_TMEM) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::A_COL0 + (j * KB + kb) * 8, bdesc, idesc, accum);
+              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)(j * KB + kb) * 4096u, 128u, 256u), bdesc, idesc, accum);
+            }
+          }
+          tc_commit(&acc_full[buf]);
+        }
+        tc_commit(&empty[s]);  // the stage's slices are free once every MMA that reads them has retired
+      }
+    }
+  } else {
+    // ===== epilogue: thread = chain (TMEM lane); the EW / 4 warps of a lane quarter split the 32 columns =====
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    double acc = 0.0, acc2 = 0.0;
+    uint32_t blk = 0;
+    long long it = 0;
+    for (long long tile = first; tile < ntiles; tile += step, it++) {
+      const int s = (int)(it % G::STAGES);
+      mbar_wait(&full[s], (uint32_t)((it / G::STAGES) & 1));
+      const double* ymeta = reinterpret_cast<const double*>(stage0 + (size_t)s * G::STAGE_BYTES + G::SLICE_BYTES);
+      const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
+#pragma unroll 1
+      for (int b = 0; b < G::NBLK; b++, blk++) {
+        const uint32_t buf = blk & 1u;
+        mbar_wait(&acc_full[buf], (blk >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < CW / CH; cc++) {
+          const int col0 = h * CW + cc * CH;
+          uint32_t a[NS][CH];
+#pragma unroll
+          for (int d = 0; d < NS; d++) tc_ld<CH>(tmem + buf * G::ACC_COLS + d * G::BLK + col0 + lane_base, a[d]);
+          tc_wait_ld<NS, CH>(a);
+          if (cc == CW / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          const int obs0 = b * G::BLK + col0;
+          if (obs0 + CH <= valid) {
+#pragma unroll
+            for (int e = 0; e < CH; e++) {
+              const double t = i8_assemble<NS, CH>(a, e);
+              if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
+                const double r = ymeta[obs0 + e] - fma(t, csc, b0);  // warp-uniform address: broadcast
+                acc = fma(r, r, acc);
+              } else if (YBIN) {
+                i8_logistic_even(t * csc, acc, acc2, sp_tab);
+              } else {
+                acc += tile_term<FAMILY, false>(t * csc, ymeta[obs0 + e], sp_tab);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < CH; e++) {
+              if (obs0 + e < valid) {
+                const double t = i8_assemble<NS, CH>(a, e);
+                if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
+                  const double r = ymeta[obs0 + e] - fma(t, csc, b0);
+                  acc = fma(r, r, acc);
+                } else if (YBIN) {
+                  i8_logistic_even(t * csc, acc, acc2, sp_tab);
+                } else {
+                  acc += tile_term<FAMILY, false>(t * csc, ymeta[obs0 + e], sp_tab);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    red[h * I8_CHAINS + q * 32 + lane] = acc + acc2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < I8_CHAINS && col < tb.ncols) {
+    double v = red[tid];
+#pragma unroll
+    for (int hh = 1; hh < EW / 4; hh++) v += red[hh * I8_CHAINS + tid];  // fixed order
+    if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) v = (slice == 0 ? lin : 0.0) - v;  // theta . sxy enters once per chain
+    // non-finite parameters never reach the integer path: NaN propagates (the reference's `undefined` abort),
+    // +-Inf / beyond 2^480 gives the rejected-proposal value
+    if (th_nan) v = NAN;
+    else if (th_big) v = (FAMILY == FMCMC_FAMILY_LOGISTIC) ? -INFINITY : INFINITY;
+    tb.partial[(size_t)slice * tb.ncols + col] = v;
+  }
+  if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}

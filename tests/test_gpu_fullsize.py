@@ -3,8 +3,8 @@ per chain-step at these sizes, so it is not the checker here):
 
   * split additivity   f(full data) == f(first half) + f(second half) (+ the prior counted once)
   * permutation invariance of the observations
-  * agreement of three independent device code paths (DFMA lane<->chain kernel, DMMA kernel, the
-    plain one-CTA-per-theta logpost kernel)
+  * agreement of four independent device code paths (DFMA lane<->chain kernel, DMMA kernel, split-integer
+    tcgen05 kernel, the plain one-CTA-per-theta logpost kernel)
   * bit-for-bit determinism, and independence of the result from how chains are sharded
 
 Tolerance: 1e-12 relative on every log-posterior (north_star's FP64 band); decisions identical."""
@@ -49,10 +49,17 @@ def test_cfg3_logistic_full_size_properties(cfg3_data):
     full = DeviceModel(fm.ll_logistic(X, y))
     o3 = _first_rows(full, spec, init, C, path=3)
     o2 = _first_rows(full, spec, init, C, path=2)
-    assert o3["report"].path == 3 and o2["report"].path == 2
+    o4 = _first_rows(full, spec, init, C, path=4)   # the default for > 128 chains (auto-selection: cfg5 test below)
+    assert o3["report"].path == 3 and o2["report"].path == 2 and o4["report"].path == 4
     f3, f2 = o3["logpost"], o2["logpost"]           # [C][2]: f(initial), f(first proposal)
     assert _rel(f3, f2) <= RTOL                     # DMMA kernel == DFMA kernel
-    assert np.array_equal(o3["draws"], o2["draws"])  # same Philox proposals
+    assert _rel(o4["logpost"], f3) <= RTOL          # tcgen05 int8-slice kernel == DMMA kernel
+    assert np.array_equal(o3["draws"], o2["draws"]) and np.array_equal(o4["draws"], o3["draws"])  # same Philox proposals
+    # path 4: per-chain exponents and a fixed slice order => independent of how chains are grouped into CTAs / calls
+    lo4 = _first_rows(full, spec, init[:300], 300, path=4)
+    hi4 = _first_rows(full, spec, init[300:], C - 300, path=4, chain_offset=300)
+    assert np.array_equal(np.concatenate([lo4["logpost"], hi4["logpost"]]), o4["logpost"])
+    assert np.array_equal(np.concatenate([lo4["ans"], hi4["ans"]]), o4["ans"])
     direct = full.logpost(init[:64])                # third code path: logpost_kernel
     assert _rel(f3[:64, 0], direct) <= RTOL
 
@@ -89,7 +96,7 @@ def test_cfg3_logistic_full_size_properties(cfg3_data):
 
 
 def test_cfg3_decisions_agree_between_device_kernels(cfg3_data):
-    """20 MH rows of 1024 kernel_adapt chains at full n: the DFMA and DMMA kernels make the same accept/reject
+    """20 MH rows of 1024 kernel_adapt chains at full n: the DFMA, DMMA and tcgen05 kernels make the same accept/reject
     decisions from the same Philox streams (a flipped decision would show as an O(1) difference)."""
     import fmcmc_b200 as fm
     from fmcmc_b200.device import DeviceModel
@@ -99,16 +106,17 @@ def test_cfg3_decisions_agree_between_device_kernels(cfg3_data):
     init = np.random.default_rng(4).normal(0, 0.1, (C, p))
     spec = dict(type=A.KERNEL_ADAPT, k=p, mu=0.0, warmup=5, freq=1, eps=1e-4)
     outs = []
-    for path in (2, 3):
+    for path in (2, 3, 4):
         m = DeviceModel(fm.ll_logistic(X, y))
         outs.append(_first_rows(m, spec, init, C, rows=T, path=path))
         m.close()
     acc = [np.any(o["ans"][:, 1:] != o["ans"][:, :-1], axis=2) for o in outs]
-    assert np.array_equal(acc[0], acc[1])
+    assert np.array_equal(acc[0], acc[1]) and np.array_equal(acc[0], acc[2])
     assert acc[0].mean() > 0.05
     scale = np.abs(outs[0]["ans"]).max(axis=(0, 1))
-    assert np.max(np.abs(outs[0]["ans"] - outs[1]["ans"]).max(axis=(0, 1)) / scale) <= 1e-11
-    assert _rel(outs[1]["logpost"], outs[0]["logpost"]) <= RTOL
+    for other in (1, 2):
+        assert np.max(np.abs(outs[0]["ans"] - outs[other]["ans"]).max(axis=(0, 1)) / scale) <= 1e-11
+        assert _rel(outs[other]["logpost"], outs[0]["logpost"]) <= RTOL
 
 
 def test_cfg5_gaussian_full_size_properties():
@@ -139,10 +147,13 @@ def test_cfg5_gaussian_full_size_properties():
 
     full = model_of(Xd, yd)
     o = _first_rows(full, spec, init, C)
-    assert o["report"].path == 3
+    assert o["report"].path == 4                    # > 128 chains: the split-integer tcgen05 kernel is the default
     f = o["logpost"][:, 0]
     again = _first_rows(full, spec, init, C)
     assert np.array_equal(again["logpost"], o["logpost"]) and np.array_equal(again["ans"], o["ans"])
+    o3 = _first_rows(full, spec, init, C, path=3)   # the FP64 DMMA kernel on the same inputs
+    assert o3["report"].path == 3
+    assert np.array_equal(o3["ans"], o["ans"]) and _rel(o["logpost"], o3["logpost"]) <= RTOL
     full.close()
     # closed form from the sufficient statistics, FP64 on the device via torch (plumbing only)
     th = torch.from_numpy(init).cuda()

@@ -1,0 +1,139 @@
+"""Path 4 — the split-integer tcgen05 likelihood kernel (fmcmc_b200/csrc/tiled_i8.cuh) — against the CPU oracle.
+
+Same fed-stream contract as the FP64 paths (every accept/reject decision identical, samples within 1e-12
+relative): the int8 slicing of X and Theta is exact until the FP64 reassembly, and the truncated slice pairs
+leave an error far below the band."""
+import numpy as np
+import pytest
+
+from fmcmc_b200 import _abi as A
+from gpu_util import assert_parity, run_both
+from test_gpu_parity import _kernels, _logistic_family
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _gaussian_family(rng, n, p):
+    from fmcmc_b200 import ll_gaussian_lm
+    X = rng.standard_normal((n, p))
+    y = 1.0 + X @ rng.standard_normal(p) + rng.normal(0, 2.0, n)
+    return ll_gaussian_lm(X, y, intercept=True, guard=True), p + 2
+
+
+@pytest.mark.parametrize("family", ["logistic", "gaussian"])
+@pytest.mark.parametrize("kname", ["normal", "normal_reflective", "adapt", "ram", "nmirror", "unif"])
+def test_i8_path_parity(oracle, family, kname):
+    """Ragged n (tail tile), chains not a multiple of the 128-chain block, every kernel class (RAM adds the
+    second likelihood column block and, because its adaptation consumes f itself, runs on 7 slices)."""
+    rng = np.random.default_rng(33)
+    n, p = 2 * 128 * 3 + 77, 7
+    if family == "logistic":
+        fam, k = _logistic_family(rng, n, p), p
+        init = rng.normal(0, 0.1, (70, k))
+    else:
+        fam, k = _gaussian_family(rng, n, p)
+        init = np.c_[rng.normal(0, 0.1, (70, k - 1)), np.full(70, 3.0)]
+    spec = dict(_kernels(k)[kname])
+    if family == "logistic":
+        for key in ("lb", "ub"):
+            if key in spec:
+                spec[key] = -A.DBL_MAX if key == "lb" else A.DBL_MAX
+    if "scale" in spec:
+        spec["scale"] = 0.05
+    g, o, _ = run_both(oracle, fam, spec, init, 140, 70, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, f"{family}/{kname}")
+
+
+def test_i8_many_chain_blocks(oracle):
+    """600 chains => 5 chain blocks of 128; p_x = 32 (the bench's shape: one K block, Theta slices in TMEM)."""
+    rng = np.random.default_rng(44)
+    fam = _logistic_family(rng, 1500, 32)
+    spec = dict(type=A.KERNEL_NORMAL, k=32, mu=0.0, scale=0.03)
+    g, o, _ = run_both(oracle, fam, spec, rng.normal(0, 0.1, (600, 32)), 40, 600, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL)
+
+
+@pytest.mark.parametrize("family,p", [("gaussian", 127), ("gaussian", 50), ("logistic", 100), ("logistic", 33)])
+def test_i8_wide_design_matrix(oracle, family, p):
+    """p_x > 32: 2 / 4 K blocks per slice pair; at 4 the Theta slices live in shared memory (SS form of the MMA)."""
+    rng = np.random.default_rng(55)
+    n, C = 1000 + 13, 150
+    if family == "logistic":
+        fam, k = _logistic_family(rng, n, p), p
+        init = rng.normal(0, 0.05, (C, k))
+        spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.02)
+    else:
+        fam, k = _gaussian_family(rng, n, p)
+        init = np.c_[rng.normal(0, 0.1, (C, k - 1)), np.full(C, 3.0)]
+        lb = np.full(k, -A.DBL_MAX); lb[-1] = 0.0
+        spec = dict(type=A.KERNEL_NMIRROR, k=k, mu=0.0, scale=0.05, warmup=30, arate=0.4, lb=lb, ub=A.DBL_MAX,
+                    nadapt=np.array([10, 20, 30]))
+    g, o, _ = run_both(oracle, fam, spec, init, 60, C, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, f"{family}/p={p}")
+
+
+def test_i8_badly_scaled_columns(oracle):
+    """Rows / chains whose entries span many orders of magnitude: the per-row and per-chain exponents keep the
+    absolute error of eta at ~2^-47 of |x|max |theta|max, which is what the 1e-12 band on the log-posterior needs."""
+    rng = np.random.default_rng(77)
+    n, p, C = 900, 12, 40
+    from fmcmc_b200 import ll_logistic
+    X = rng.standard_normal((n, p)) * np.logspace(-6, 3, p)
+    X[:, 0] = 1.0
+    beta = rng.standard_normal(p) / np.logspace(-6, 3, p)
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
+    fam = ll_logistic(X, y, prior_sd=2.0)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.02 / np.logspace(-6, 3, p))
+    init = beta + rng.normal(0, 0.01, (C, p)) / np.logspace(-6, 3, p)
+    g, o, _ = run_both(oracle, fam, spec, init, 80, C, rng=rng, path=4)
+    assert_parity(g[0], o[0], RTOL)
+
+
+def test_i8_nonbinary_response_and_nan(oracle):
+    """y outside {0, 1} contributes nothing (sum(logp[y == 1]) + sum(logq[y == 0])); a NaN parameter aborts like
+    R/mcmc.R:758-765."""
+    from fmcmc_b200 import ll_logistic, _lib
+    from fmcmc_b200.device import DeviceModel
+    rng = np.random.default_rng(88)
+    n, p, C = 700, 5, 9
+    X = rng.standard_normal((n, p)); X[:, 0] = 1.0
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    y[::17] = 0.5
+    fam = ll_logistic(X, y, prior_sd=2.0)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.05)
+    g, o, _ = run_both(oracle, fam, spec, rng.normal(0, 0.1, (C, p)), 60, C, rng=rng, path=4)
+    assert_parity(g[0], o[0], RTOL)
+    m = DeviceModel(fam)
+    m.set_path(4)
+    init = rng.normal(0, 0.1, (C, p))
+    init[3, 2] = np.nan
+    with pytest.raises(_lib.FmcmcError) as ei:
+        m.run(spec, 10, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
+    m.close()
+    assert "undefined" in str(ei.value)
+
+
+def test_i8_matches_fp64_kernel_at_scale(oracle):
+    """n = 200 000, p = 32, 256 chains (too slow for the oracle): the log-posteriors of the tcgen05 path and the
+    FP64 DMMA path agree to 1e-13 relative and the chains take identical decisions."""
+    from fmcmc_b200.device import DeviceModel
+    rng = np.random.default_rng(99)
+    n, p, C, T = 200_000, 32, 256, 30
+    fam = _logistic_family(rng, n, p)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.004)
+    init = rng.normal(0, 0.05, (C, p))
+    outs = {}
+    for path in (3, 4):
+        m = DeviceModel(fam)
+        m.set_path(path)
+        outs[path] = m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=5))
+        assert outs[path]["report"].path == path
+        m.close()
+    a, b = outs[4], outs[3]
+    assert np.array_equal(a["ans"], b["ans"])
+    err = np.max(np.abs(a["logpost"] - b["logpost"]) / np.abs(b["logpost"]))
+    assert err < 1e-13, err

@@ -192,7 +192,7 @@ def test_tiled_wide_design_matrix(oracle, family, p):
         lb = np.full(k, -A.DBL_MAX); lb[-1] = 0.0
         spec = dict(type=A.KERNEL_NMIRROR, k=k, mu=0.0, scale=0.05, warmup=30, arate=0.4, lb=lb, ub=A.DBL_MAX,
                     nadapt=np.array([10, 20, 30]))
-    g, o, _ = run_both(oracle, fam, spec, init, 60, C, rng=rng)
+    g, o, _ = run_both(oracle, fam, spec, init, 60, C, rng=rng, path=3)
     assert g[0]["report"].path == 3
     assert_parity(g[0], o[0], RTOL, f"{family}/p={p}")
 
