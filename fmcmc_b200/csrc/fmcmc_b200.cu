@@ -606,7 +606,7 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   i8_colmax_kernel<<<dim3((unsigned)mp.p_x, ychunks), 256, 0, m->stream>>>(mp.X, mp.n, mp.ld, colmax, m->xq_bad.as<int>());
   i8_colexp_kernel<<<(mp.p_x + 127) / 128, 128, 0, m->stream>>>(colmax, mp.p_x, cexp);
   i8_sxy_kernel<<<(unsigned)mp.p_x, 1024, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, sxy);
-#define I8_CASE(N, K) if (NS == N && KB == K) pack_i8_kernel<N, K><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, mp.p_x, cexp, xq);
+#define I8_CASE(N, K) if (NS == N && KB == K) pack_i8_kernel<N, K><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
   e = cudaGetLastError();
@@ -901,6 +901,9 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     if (gx > ntiles) gx = (int)ntiles;
     tb.gx = gx;
     tb.cb = chain_blocks;
+#ifdef FMCMC_I8_TUNE_HOOKS
+    if (const char* v = getenv("FMCMC_I8_TUNE")) tb.tune = atoi(v);
+#endif
     const bool sharded = m->shard_world > 1;
     if (sharded) {  // observation sharding: partial sums live in the exchange buffer, one block per step parity
       if (path != 3 || gx != m->sm_count || tb.ncols > m->shard_max_cols) {

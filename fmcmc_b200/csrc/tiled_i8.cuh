@@ -44,9 +44,7 @@ struct I8Geom {
   static constexpr int SLAB_BYTES = BLK * 32;                        // one slice x one K block of a 32-observation block: 4 groups x 2 chunks x 128 B
   static constexpr int BLOCK_BYTES = KB * NS * SLAB_BYTES;           // [kb][slice][group][chunk][8 rows][16 B]
   static constexpr int SLICE_BYTES = NBLK * BLOCK_BYTES;
-  static constexpr int META_BYTES = TO * 8;                         // y per observation (unused by the binary-logistic epilogue)
-  static constexpr int STAGE_BYTES = SLICE_BYTES + META_BYTES;
-  static constexpr int STAGES = KB == 4 ? 3 : 4;                    // KB = 4: 96 KB of Theta slices share the shared memory
+  static constexpr int STAGE_BYTES = SLICE_BYTES;                   // a stage is pure MMA operand: only the tensor pipe holds it
   static constexpr int ACC_COLS = NS * BLK;                         // TMEM columns of one accumulator set
   static constexpr bool A_TMEM = (2 * ACC_COLS + NS * KB * 8) <= 512;
   static constexpr int A_COL0 = 2 * ACC_COLS;
@@ -54,10 +52,21 @@ struct I8Geom {
   static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
 };
 
+// pipeline depth: as many stages as fit beside the Theta slices (KB = 4: 96 KB) and the softplus table, at most 6.
+// The bulk copies have ~1.5 us of latency and a K = 128 stage is consumed in ~0.8 us: 3 stages starved the MMAs
+// (profiles/r01_i8_findings.md)
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_stages(int family) {
+  using G = I8Geom<NS, KB>;
+  const int fixed = 256 + G::A_SMEM_BYTES + (family == FMCMC_FAMILY_LOGISTIC ? FM_SP_ENTRIES * 16 : 0) +
+                    (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
+  const int fit = (232448 - fixed) / G::STAGE_BYTES;
+  return fit > 6 ? 6 : fit;
+}
 template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
   using G = I8Geom<NS, KB>;
-  size_t b = 128 + (size_t)G::STAGES * G::STAGE_BYTES + G::A_SMEM_BYTES +
+  size_t b = 256 + (size_t)i8_stages<NS, KB>(family) * G::STAGE_BYTES + G::A_SMEM_BYTES +
              (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
@@ -135,8 +144,8 @@ __global__ void __launch_bounds__(1024) i8_sxy_kernel(const double* __restrict__
 }
 
 template <int NS, int KB>
-__global__ void pack_i8_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n, long long ld,
-                               int p_x, const int* __restrict__ cexp, unsigned char* __restrict__ Xq) {
+__global__ void pack_i8_kernel(const double* __restrict__ X, long long n, long long ld, int p_x,
+                               const int* __restrict__ cexp, unsigned char* __restrict__ Xq) {
   using G = I8Geom<NS, KB>;
   const long long tile = blockIdx.x;
   const int t = threadIdx.x;  // blockDim.x == TO
@@ -162,7 +171,6 @@ __global__ void pack_i8_kernel(const double* __restrict__ X, const double* __res
       for (int i = 0; i < NS; i++)
         *reinterpret_cast<uint4*>(grp + (size_t)(kb * NS + i) * G::SLAB_BYTES + c * 128) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
     }
-  *reinterpret_cast<double*>(dst + G::SLICE_BYTES + t * 8) = valid ? y[row] : 0.0;
 }
 
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------------
@@ -218,6 +226,14 @@ __device__ __forceinline__ void tc_wait_ld(uint32_t (&a)[NS][CH]) {
   for (int d = 0; d < NS; d++)
 #pragma unroll
     for (int e = 0; e < CH; e++) asm volatile("" : "+r"(a[d][e]));
+}
+// one lane of a CONVERGED warp: ptxas then keeps descriptors / addresses in uniform registers and issues the
+// tcgen05 / TMA instruction directly (inside an `if (lane == 0)` region it wraps every UTCIMMA in an
+// ELECT + R2UR loop, ~80 clk per instruction - profiles/r01_i8_findings.md)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 // mbarrier wait for the single-thread roles: back off instead of spinning in the issue slots the epilogue needs
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
@@ -296,12 +312,14 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   static_assert(CW % CH == 0, "whole chunks");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty = full + G::STAGES;
-  uint64_t* acc_full = empty + G::STAGES;
+  constexpr int STAGES = i8_stages<NS, KB>(FAMILY);
+  static_assert(STAGES >= 2 && 2 * STAGES + 4 <= 31, "barriers live in the first 256 bytes");
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  unsigned char* stage0 = smem_raw + 128;
-  unsigned char* sA = stage0 + (size_t)G::STAGES * G::STAGE_BYTES;
+  unsigned char* stage0 = smem_raw + 256;
+  unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
   double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
   double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sp_tab) +
                                           (FAMILY == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0));
@@ -314,9 +332,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const int p_x = mp.p_x;
 
   if (tid == 0) {
-    for (int s = 0; s < G::STAGES; s++) {
+    for (int s = 0; s < STAGES; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1 + EW);
+      mbar_init(&empty[s], 1);  // released by the MMA warp's tcgen05.commit alone
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&acc_full[b], 1);
@@ -394,37 +412,39 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   tc_fence_after();
 
   if (warp == W_TMA) {
-    // ===== producer: one bulk copy per stage =====
-    if (lane == 0) {
-      long long it = 0;
-      for (long long tile = first; tile < ntiles; tile += step, it++) {
-        const int s = (int)(it % G::STAGES);
-        const uint32_t ph = (uint32_t)((it / G::STAGES) & 1);
-        mbar_wait_sleep(&empty[s], ph ^ 1u, 256);
+    // ===== producer: one bulk copy per stage (whole warp in the loop, one elected lane issues) =====
+    long long it = 0;
+    for (long long tile = first; tile < ntiles; tile += step, it++) {
+      const int s = (int)(it % STAGES);
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      mbar_wait_sleep(&empty[s], ph ^ 1u, 256);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
         bulk_g2s(stage0 + (size_t)s * G::STAGE_BYTES, mp.Xq + (size_t)tile * G::STAGE_BYTES, (uint32_t)G::STAGE_BYTES, &full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == W_MMA) {
-    // ===== MMA issuer: NS * KB instructions per block of 32 observations (N = 32 (NS - j)) =====
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, K-major, N >> 3, M >> 4
-      constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_CHAINS >> 4) << 24);
-      const uint32_t sA_addr = smem_u32(sA);
-      uint32_t blk = 0;
-      long long it = 0;
-      for (long long tile = first; tile < ntiles; tile += step, it++) {
-        const int s = (int)(it % G::STAGES);
-        mbar_wait_sleep(&full[s], (uint32_t)((it / G::STAGES) & 1), 64);
-        tc_fence_after();
-        const uint32_t sbase = smem_u32(stage0 + (size_t)s * G::STAGE_BYTES);
+    // ===== MMA issuer: NS * KB instructions per block of 32 observations (N = 32 (NS - j)); whole warp in the
+    // loop, one elected lane issues =====
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, K-major, N >> 3, M >> 4
+    constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_CHAINS >> 4) << 24);
+    const uint32_t sA_addr = smem_u32(sA);
+    uint32_t blk = 0;
+    long long it = 0;
+    for (long long tile = first; tile < ntiles; tile += step, it++) {
+      const int s = (int)(it % STAGES);
+      mbar_wait_sleep(&full[s], (uint32_t)((it / STAGES) & 1), 32);
+      tc_fence_after();
+      const uint32_t sbase = smem_u32(stage0 + (size_t)s * G::STAGE_BYTES);
 #pragma unroll 1
-        for (int b = 0; b < G::NBLK; b++, blk++) {
-          const uint32_t buf = blk & 1u;
-          mbar_wait_sleep(&acc_empty[buf], ((blk >> 1) & 1u) ^ 1u, 64);
-          tc_fence_after();
-          const uint32_t bblk = sbase + (uint32_t)b * G::BLOCK_BYTES;
-          const uint32_t dbase = tmem + buf * G::ACC_COLS;
+      for (int b = 0; b < G::NBLK; b++, blk++) {
+        const uint32_t buf = blk & 1u;
+        mbar_wait_sleep(&acc_empty[buf], ((blk >> 1) & 1u) ^ 1u, 32);
+        tc_fence_after();
+        const uint32_t bblk = sbase + (uint32_t)b * G::BLOCK_BYTES;
+        const uint32_t dbase = tmem + buf * G::ACC_COLS;
+        if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < KB; kb++) {
 #pragma unroll
@@ -438,8 +458,10 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           }
           tc_commit(&acc_full[buf]);
         }
-        tc_commit(&empty[s]);  // the stage's slices are free once every MMA that reads them has retired
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(&empty[s]);  // the stage's slices are free once every MMA that reads them has retired
+      __syncwarp();
     }
   } else {
     // ===== epilogue: thread = chain (TMEM lane); the EW / 4 warps of a lane quarter split the 32 columns =====
@@ -449,9 +471,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     uint32_t blk = 0;
     long long it = 0;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
-      const int s = (int)(it % G::STAGES);
-      mbar_wait(&full[s], (uint32_t)((it / G::STAGES) & 1));
-      const double* ymeta = reinterpret_cast<const double*>(stage0 + (size_t)s * G::STAGE_BYTES + G::SLICE_BYTES);
+      const double* ymeta = mp.y + tile * G::TO;  // L1-resident broadcast loads (Gaussian / non-binary logistic only)
       const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
 #pragma unroll 1
       for (int b = 0; b < G::NBLK; b++, blk++) {
@@ -462,8 +482,18 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
         for (int cc = 0; cc < CW / CH; cc++) {
           const int col0 = h * CW + cc * CH;
           uint32_t a[NS][CH];
+#ifdef FMCMC_I8_TUNE_HOOKS  // profiling experiments only (profiles/r01_i8_findings.md): results are garbage
+          if (tb.tune & 1) {
 #pragma unroll
-          for (int d = 0; d < NS; d++) tc_ld<CH>(tmem + buf * G::ACC_COLS + d * G::BLK + col0 + lane_base, a[d]);
+            for (int d = 0; d < NS; d++)
+#pragma unroll
+              for (int e = 0; e < CH; e++) a[d][e] = (uint32_t)(lane * 37 + d * 11 + e + (int)blk);
+          } else
+#endif
+          {
+#pragma unroll
+            for (int d = 0; d < NS; d++) tc_ld<CH>(tmem + buf * G::ACC_COLS + d * G::BLK + col0 + lane_base, a[d]);
+          }
           tc_wait_ld<NS, CH>(a);
           if (cc == CW / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
             tc_fence_before();
@@ -471,17 +501,23 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
           const int obs0 = b * G::BLK + col0;
+#ifdef FMCMC_I8_TUNE_HOOKS
+          if (tb.tune & 2) {
+#pragma unroll
+            for (int e = 0; e < CH; e++) acc += (double)(int)(a[0][e] ^ a[NS - 1][e]);
+          } else
+#endif
           if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
               const double t = i8_assemble<NS, CH>(a, e);
               if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
-                const double r = ymeta[obs0 + e] - fma(t, csc, b0);  // warp-uniform address: broadcast
+                const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
                 i8_logistic_even(t * csc, acc, acc2, sp_tab);
               } else {
-                acc += tile_term<FAMILY, false>(t * csc, ymeta[obs0 + e], sp_tab);
+                acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
             }
           } else {
@@ -490,20 +526,18 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
               if (obs0 + e < valid) {
                 const double t = i8_assemble<NS, CH>(a, e);
                 if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
-                  const double r = ymeta[obs0 + e] - fma(t, csc, b0);
+                  const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
                   i8_logistic_even(t * csc, acc, acc2, sp_tab);
                 } else {
-                  acc += tile_term<FAMILY, false>(t * csc, ymeta[obs0 + e], sp_tab);
+                  acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
               }
             }
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
     }
     red[h * I8_CHAINS + q * 32 + lane] = acc + acc2;
   }

@@ -14,14 +14,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 }
 
 // fp_iters: DFMA loop length per FP64 warp (0 = no FP64 work); mma_count: MMAs issued by the tensor thread (0 = none)
-__global__ void __launch_bounds__(288, 1) k(double* out, int fp_iters, int mma_count, int N, int a_tmem, long long* cyc, int R) {
+__global__ void __launch_bounds__(320, 1) k(double* out, int fp_iters, int mma_count, int N, int a_tmem, long long* cyc, int R) {
   extern __shared__ __align__(128) unsigned char smem[];  // A: 4 KB, B: 8 KB (zeros are fine)
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int e = tid; e < 12288 / 4; e += 288) reinterpret_cast<uint32_t*>(smem)[e] = 0x01010101u * (e & 3);
+  for (int e = tid; e < 12288 / 4; e += 320) reinterpret_cast<uint32_t*>(smem)[e] = 0x01010101u * (e & 3);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -41,12 +42,14 @@ __global__ void __launch_bounds__(288, 1) k(double* out, int fp_iters, int mma_c
       a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     out[blockIdx.x * 256 + tid] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-  } else if (tid == 256 && mma_count > 0) {
+  } else if ((tid == 256 || (tid == 288 && R < 0)) && mma_count > 0) {
+    const int second = tid == 288;  // R < 0: two issuing threads (warps 8 and 9), |R| accumulators each, own barrier
+    const int RR = R < 0 ? -R : R;
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t da = make_desc(smem_u32(smem), 128, 256), db = make_desc(smem_u32(smem + 4096), 128, 256);
     const long long t0 = clock64();
     for (int i = 0; i < mma_count; i++) {
-      const uint32_t d = tmem + (uint32_t)((i % R) * N);  // R independent accumulators
+      const uint32_t d = tmem + (uint32_t)(((i & (RR - 1)) + second * RR) * N);  // RR (power of two) independent accumulators per issuing thread
       if (a_tmem)
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
                      "r"(tmem + 504), "l"(db), "r"(idesc), "r"(1u)
@@ -56,14 +59,14 @@ __global__ void __launch_bounds__(288, 1) k(double* out, int fp_iters, int mma_c
                      "l"(da), "l"(db), "r"(idesc), "r"(1u)
                      : "memory");
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[second])) : "memory");
     uint32_t ok = 0;
     while (!ok)
       asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                    : "=r"(ok)
-                   : "r"(smem_u32(&bar)), "r"(0u)
+                   : "r"(smem_u32(&bars[second])), "r"(0u)
                    : "memory");
-    if (blockIdx.x == 0) cyc[0] = clock64() - t0;
+    if (blockIdx.x == 0 && !second) cyc[0] = clock64() - t0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -79,13 +82,13 @@ int main() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  auto run = [&](int fp_iters, int mma_count, int N, int a_tmem, const char* name, int R = 1) {
+  auto run = [&](int fp_iters, int mma_count, int N, int a_tmem, const char* name, int R = 2) {
     float best = 1e30f;
     long long hc = 0;
     for (int rep = 0; rep < 3; rep++) {
       cudaMemset(cyc, 0, 8);
       cudaEventRecord(e0);
-      k<<<148, 288, 16384>>>(out, fp_iters, mma_count, N, a_tmem, cyc, R);
+      k<<<148, 320, 16384>>>(out, fp_iters, mma_count, N, a_tmem, cyc, R);
       cudaEventRecord(e1);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
@@ -96,7 +99,7 @@ int main() {
     }
     const double tf = 148.0 * 256 * 8.0 * fp_iters * 2 / (best * 1e-3) / 1e12;
     printf("%-46s %8.3f ms  DFMA %6.2f TF/s   %8.1f clk/MMA (%lld clk for %d MMAs, %.0f int8 MAC/clk/SM)\n", name, best, tf,
-           mma_count ? (double)hc / mma_count : 0.0, hc, mma_count, mma_count ? 128.0 * N * 32 * mma_count / (double)hc : 0.0);
+           mma_count ? (double)hc / mma_count / (R < 0 ? 2 : 1) : 0.0, hc, mma_count * (R < 0 ? 2 : 1), mma_count ? 128.0 * N * 32 * mma_count * (R < 0 ? 2 : 1) / (double)hc : 0.0);
   };
   const int F = 200000;
   run(F, 0, 32, 0, "DFMA only");
@@ -107,10 +110,11 @@ int main() {
       run(0, 40000, N, a_tmem, nm);
     }
   for (int N : {32, 64, 96, 128, 192})
-    for (int R : {1, 2, 4, 8}) {
-      if (R * N > 496) continue;
+    for (int R : {1, 2, 4, 8, -1, -2}) {
+      const int RR = R < 0 ? -2 * R : R;
+      if (RR * N > 496) continue;
       char nm[96];
-      snprintf(nm, sizeof nm, "MMA only, N=%d, A from TMEM, %d accumulators", N, R);
+      snprintf(nm, sizeof nm, "MMA only, N=%d, A TMEM, %d accumulators x %d issuing thread(s)", N, R < 0 ? -R : R, R < 0 ? 2 : 1);
       run(0, 40000, N, 1, nm, R);
     }
   for (int a_tmem = 0; a_tmem < 2; a_tmem++)
