@@ -1,35 +1,42 @@
 // tiled_i8.cuh — observation-tiled likelihood kernel, split-integer tensor-core variant (path 4).
 //
 // Same contract and grid as tiled_loglik_mma_kernel (tiled_mma.cuh): a CTA owns one observation slice and
-// one block of chains and writes partial[slice][chain].  What changes is where the X.Theta contraction runs.
+// one block of 128 chains and writes partial[slice][chain].  What changes is where the X.Theta contraction runs.
 // The FP64 pipe is the binding roof of paths 2 / 3, and 32 of its 51 instruction slots per
 // evaluation are the dot product.  tcgen05 has no FP64 kind, but B200's 5th-generation tensor cores multiply
 // int8 with exact int32 accumulation (tcgen05.mma kind::i8, SASS UTCIMMA), so the product is computed
 // EXACTLY on integer slices of the operands (Ozaki splitting) and only reassembled in FP64:
 //
-//   row i of X:     x_ij   = 2^ex_i  * sum_s  sx_s[i][j] * 2^(-6 - 7 s),   sx_s in [-64, 64]   (once per model)
-//   chain c:        th_cj  = 2^eth_c * sum_s  sth_s[c][j] * 2^(-6 - 7 s)                        (once per launch)
-//   eta_ic = 2^(ex_i + eth_c - 12) * sum_d 2^(-7 d) * a_d,     a_d = sum_{s + s' = d} sum_j sx_s[i][j] sth_s'[c][j]
+//   column j of X:  x_ij   = 2^cexp_j * sum_s sx_s[i][j] 2^(-6 - 7 s),   sx_s in [-64, 64]          (once per model)
+//   chain c:        th_cj 2^cexp_j = 2^eth_c * sum_s sth_s[c][j] 2^(-6 - 7 s)                         (once per launch)
+//   eta_ic = 2^(eth_c - 12) * sum_d 2^(-7 d) a_d,     a_d = sum_{s + s' = d} sum_j sx_s[i][j] sth_s'[c][j]
 //
-// a_d (d = 0 .. NS-1) are int32 accumulators in tensor memory, one tcgen05.mma per slice pair (NS (NS+1) / 2
-// instructions of M = 128 chains x N = 32 observations x K = 32 per block).  Dropping the pairs with
-// s + s' >= NS leaves an absolute error of ~2^(-7 NS - 5) * 2^(ex + eth) in eta (NS = 6: ~1e-12 |x|max |th|max —
-// the size of the FP64 rounding error of the 32-term dot product is ~1e-15; the log-posterior, a sum over n
-// terms with unbiased errors, stays ~1e-15 relative; tests/test_gpu_i8.py measures it).  Everything is integer
-// until the reassembly, so results are bit-reproducible and independent of how chains are grouped into CTAs
-// (per-row and per-chain exponents, no block-wide scaling).
+// a_d (d = 0 .. NS-1) are int32 accumulators in tensor memory.  Dropping the pairs with s + s' >= NS leaves an
+// absolute error of ~2^(-7 NS - 5) max_j|theta_j 2^cexp_j| in eta — relative to the largest single term of the dot
+// product, thanks to the column exponents (NS = 6: ~1e-12; the FP64 rounding error of a 32-term dot product is
+// ~1e-15).  Summed over n observations with unbiased signs the log-posterior stays ~1e-13 .. 1e-15 relative;
+// kernel_ram, whose adaptation consumes f itself, runs on 7 slices (fmcmc_run).  Everything is integer until the
+// reassembly, so results are bit-reproducible and independent of how chains are grouped into CTAs / calls / GPUs
+// (per-column and per-chain exponents only, no block-wide scaling).
 //
 // Mapping: TMEM lane = chain (A operand = Theta slices, written once per launch into tensor memory with
 // tcgen05.st when they fit, else shared memory), TMEM column = observation (B operand = the X slice tile,
-// streamed from HBM by one cp.async.bulk per stage in exactly the core-matrix layout the MMA reads).  An epilogue
-// thread owns one chain: it reads the NS accumulators of an observation with tcgen05.ld, reassembles eta with
-// 6 FP64 instructions (pairs of diagonals are merged in int32 first), runs the family epilogue and adds to a
-// private sum — no cross-lane reduction.  Warp roles: 8 epilogue warps (two per TMEM lane quarter, splitting
-// the 32 columns), 1 TMA producer, 1 MMA issuer; accumulators are double-buffered in TMEM so the tensor pipe
-// works on block t+1 while the FP64 pipe finishes block t.
+// streamed from HBM by one cp.async.bulk per stage in exactly the core-matrix layout the MMA reads).
+// One MMA per (Theta slice j, K block) multiplies the slice with X slices 0 .. NS-1-j AT ONCE (they are consecutive
+// row groups of the B operand, N = 32 (NS - j)); the product with X slice s lands 32 s columns to the right, i.e.
+// on diagonal s + j: NS instructions per 32-observation block instead of NS (NS + 1) / 2 (a UTCIMMA costs ~80 clk
+// to issue whatever its N - profiles/r01_i8_findings.md).
+// An epilogue thread owns one chain: it reads the NS accumulators of an observation with tcgen05.ld, merges them
+// exactly (int32 pairs -> int64, ONE I2F.F64.S64), scales (1 FP64 instruction), runs the family epilogue and adds
+// to a private sum — no cross-lane reduction.  Warp roles: 16 epilogue warps (four per TMEM lane quarter, 8 of the
+// 32 columns each), 1 TMA producer, 1 MMA issuer (whole warp in the loop, elect.sync around the issue);
+// accumulators are double-buffered in TMEM.  On B200 the FP64 pipe and the tensor pipe share their datapath
+// (DFMA drops to 3 % of its rate while UTCIMMAs run), so the kernel's time is tensor time PLUS FP64 time; the
+// double buffer hides latencies only.
 //
-// FP64-pipe slots per evaluation: 6 (reassembly) + 19 (logistic epilogue) = 25 against 51 on path 3; Gaussian:
-// 6 + 2 against 2 p_x + 2.
+// FP64-pipe slots per evaluation: 19 (binary logistic: 1 scale + 18 table-driven softplus; the linear term
+// theta . X'(y - 1/2) is a per-chain dot product with a vector computed once per model) against 51 on path 3;
+// Gaussian: 3 against 2 p_x + 2.
 #pragma once
 #include "tiled.cuh"
 
