@@ -388,12 +388,16 @@ def main():
     model.run(spec, W + 1, C, initial=init, stream=stream(run_idx), istate=istate.copy(), dstate=dstate.copy(),
               chain_offset=chain_offset, outputs=True, want_draws=True)
     run_idx += 1
-    barrier()
-    e2e_t0 = time.perf_counter()
-    m2 = model.run(spec, K + 1, C, initial=init, stream=stream(run_idx), istate=istate.copy(), dstate=dstate.copy(),
-                   chain_offset=chain_offset, outputs=True, want_draws=True)
-    torch.cuda.synchronize()
-    e2e_sec = time.perf_counter() - e2e_t0
+    e2e_runs = []
+    for _ in range(1 if wl.key == "cfg5" else 3):      # median of 3 host-side timings (page faults / host jitter); cfg5: 1 (seconds each)
+        ist_in, dst_in = istate.copy(), dstate.copy()
+        barrier()
+        e2e_t0 = time.perf_counter()
+        m2 = model.run(spec, K + 1, C, initial=init, stream=stream(run_idx), istate=ist_in, dstate=dst_in,
+                       chain_offset=chain_offset, outputs=True, want_draws=True)
+        torch.cuda.synchronize()
+        e2e_runs.append(time.perf_counter() - e2e_t0)
+    e2e_sec = float(np.median(e2e_runs))
     run_idx += 1
     last = m2["ans"][:, -1, :]
     h2d, d2h = int(m2["report"].h2d_bytes), int(m2["report"].d2h_bytes)

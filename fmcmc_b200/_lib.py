@@ -9,7 +9,7 @@ import subprocess
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfmcmcb200.so")
+SO_PATH = os.environ.get("FMCMC_B200_LIB") or os.path.join(_HERE, "libfmcmcb200.so")   # env override: profiling builds only
 _lib = None
 
 

@@ -257,18 +257,24 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
 }
 
 // t = sum_d a_d 2^(7 (NS - 1 - d)), exact: adjacent diagonals are merged in int32 (|a_d| <= (d+1) * 32 KB * 4096 < 2^24),
-// up to three merged pairs in int64, then ONE conversion (I2F.F64.S64, off the FP64 pipe) per group
+// up to three merged pairs in int64 (32 x 32 -> 64-bit multiply-adds), then ONE conversion per group.
+// (Measured alternatives, clk per warp-evaluation of the merge alone - profiles/microbench/i8_epilogue_rate.cu:
+//  I2F.F64.S64 27.9 | magic-number int64 30.1 | int32 pairs + 3 I2F.S32 + 2 DFMA 28.8 | 3 magic32 + 2 DFMA 30.9 |
+//  6 magic32 + 5 DFMA 42.3.)
 template <int NS, int CH>
-__device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e) {
+__device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e, int tune = 0) {
   int v[(NS + 1) / 2];
 #pragma unroll
   for (int p = 0; p < NS / 2; p++) v[p] = (int)a[2 * p][e] * 128 + (int)a[2 * p + 1][e];
   if (NS & 1) v[NS / 2] = (int)a[NS - 1][e];
-  if (NS <= 6) {  // 32 x 32 -> 64-bit multiply-adds (IMAD.WIDE)
+  if (NS <= 6) {
     constexpr int NV = (NS + 1) / 2;
     long long w = v[NV - 1];
 #pragma unroll
     for (int p = NV - 2; p >= 0; p--) w += (long long)v[p] * (int)(1u << (7 * (NS - 2 - 2 * p)));
+#ifdef FMCMC_I8_TUNE_HOOKS
+    if (tune & 8) return __hiloint2double(0x43300000 | (int)((w >> 32) & 0xfffff), (int)w) - 4503599627370496.0;  // no XU op (value is garbage)
+#endif
     return __ll2double_rn(w);
   } else {  // 7, 8: two groups
     const long long hi = (long long)v[0] * 16384LL + v[1];
@@ -277,33 +283,40 @@ __device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e
   }
 }
 
-// Binary logistic regression without the per-observation response: with z = +-eta,
-//   sum_i [min(z_i, 0) - log1p(exp(-|z_i|))] = theta . sxy - sum_i [ |eta_i| / 2 + log1p(exp(-|eta_i|)) ]
-// (y_i eta_i - max(eta_i, 0) = (y_i - 1/2) eta_i - |eta_i| / 2), so the epilogue only accumulates the even function
-// of eta: 19 FP64 instructions, no select, no load of y.  eta is finite here (non-finite Theta never gets this far).
-__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab) {
+// polynomial coefficients of fm_softplus_tab_core (softplus.h) + range-reduction constants in the constant bank: FP64
+// instructions take c[bank][offset] operands directly, literals cost a UMOV / IMAD.MOV pair per use
+__constant__ double I8_K[16] = {
+    -0x1.6c175d75f692ap-10, 0x1.1111ad1af8af9p-7, -0x1.5555555538138p-5, 0x1.555555551ad1ap-3, -0x1.0000000000000p-1,
+    0x1.0000000000000p+0,                                                  // q = expm1(-d) / (-d)
+    -0x1.555b6df3e4efdp-3, 0x1.99a091298881fp-3, -0x1.fffffff6b5a52p-3, 0x1.555555500646bp-2, -0x1.0000000000008p-1,
+    0x1.0000000000005p+0,                                                  // L = log1p(v) / v
+    6755399441055744.0, (double)FM_SP_H, -1.0 / FM_SP_H, 0.5};
+__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab, int tune = 0) {
   const int hi = __double2hiint(eta), lo = __double2loint(eta);
   // |eta| clamped near 64 on the high word alone (>= 64 -> [64, 64 + 2^-14]: table entry 2048, tiny remainder)
   const double a = __hiloint2double(min(hi & 0x7fffffff, 0x40500000), lo);
-  const double MAGIC = 6755399441055744.0;
-  const double t = fma(a, (double)FM_SP_H, MAGIC);
+  const double t = fma(a, I8_K[13], I8_K[12]);   // low word of t = round(32 a)
   const int k = __double2loint(t);
-  const double d = fma(t - MAGIC, -1.0 / FM_SP_H, a);
+  const double d = fma(t - I8_K[12], I8_K[14], a);
+#ifdef FMCMC_I8_TUNE_HOOKS
+  const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
+#else
   const double2 sg = tab[k];
-  double q = -0x1.6c175d75f692ap-10;  // same polynomials as fm_softplus_tab_core (softplus.h)
-  q = fma(q, d, 0x1.1111ad1af8af9p-7);
-  q = fma(q, d, -0x1.5555555538138p-5);
-  q = fma(q, d, 0x1.555555551ad1ap-3);
-  q = fma(q, d, -0x1.0000000000000p-1);
-  q = fma(q, d, 0x1.0000000000000p+0);
+#endif
+  double q = I8_K[0];
+  q = fma(q, d, I8_K[1]);
+  q = fma(q, d, I8_K[2]);
+  q = fma(q, d, I8_K[3]);
+  q = fma(q, d, I8_K[4]);
+  q = fma(q, d, I8_K[5]);
   const double v = (sg.x * d) * -q;
-  double L = -0x1.555b6df3e4efdp-3;
-  L = fma(L, v, 0x1.99a091298881fp-3);
-  L = fma(L, v, -0x1.fffffff6b5a52p-3);
-  L = fma(L, v, 0x1.555555500646bp-2);
-  L = fma(L, v, -0x1.0000000000008p-1);
-  L = fma(L, v, 0x1.0000000000005p+0);
-  acc_abs = fma(0.5, fabs(eta), acc_abs);
+  double L = I8_K[6];
+  L = fma(L, v, I8_K[7]);
+  L = fma(L, v, I8_K[8]);
+  L = fma(L, v, I8_K[9]);
+  L = fma(L, v, I8_K[10]);
+  L = fma(L, v, I8_K[11]);
+  acc_abs = fma(I8_K[15], fabs(eta), acc_abs);
   acc_g = fma(v, L, acc_g + sg.y);
 }
 
@@ -517,12 +530,12 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
-              const double t = i8_assemble<NS, CH>(a, e);
+              const double t = i8_assemble<NS, CH>(a, e, tb.tune);
               if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even(t * csc, acc, acc2, sp_tab);
+                i8_logistic_even(t * csc, acc, acc2, sp_tab, tb.tune);
               } else {
                 acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
@@ -531,12 +544,12 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll
             for (int e = 0; e < CH; e++) {
               if (obs0 + e < valid) {
-                const double t = i8_assemble<NS, CH>(a, e);
+                const double t = i8_assemble<NS, CH>(a, e, tb.tune);
                 if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even(t * csc, acc, acc2, sp_tab);
+                  i8_logistic_even(t * csc, acc, acc2, sp_tab, tb.tune);
                 } else {
                   acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
