@@ -484,7 +484,8 @@ def main():
             "e2e": {"value": C * cw * K / e2e_sec, "unit": "chain-steps/s",
                     "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                     "call": "fmcmc_run via the Python mirror with host numpy buffers (initial pinned): H2D initial + "
-                            "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows"},
+                            "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows; median of the timed calls",
+                    "timed_calls_s": e2e_runs},
             "gpu_launches": launches,
             "wall_ms_per_step": 1e3 * t_wall / K,
             "roofline": None, "roofline_other": None,
