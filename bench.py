@@ -311,6 +311,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: fmcmc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries ONE JSON line, not NCCL's version banner
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
