@@ -52,6 +52,7 @@ struct ModelParams {
   const int* i8_cexp;       // [p_x] column exponents of the slicing
   const double* i8_sxy;     // [p_x] sum_i (y_i - 1/2) x_ij (binary logistic)
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
+  const double* sp_tab4; // logistic: the 128-per-unit table of the split-integer kernel (softplus.h, FM_SP4_*)
 };
 
 // Per-run device buffers shared by both paths.

@@ -70,7 +70,7 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group, sp_tab, Xt, Xq, xq_bad, xq_aux;
+  DevBuf X, y, group, sp_tab, sp_tab4, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
   int i8_slices = 0;      // int8 slices per operand of path 4: 0 = 6, or 7 for kernel_ram whose adaptation consumes f itself
@@ -229,6 +229,11 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
     MC(ensure(m->sp_tab, tab.size() * 8));
     MC(cudaMemcpy(m->sp_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
     mp.sp_tab = m->sp_tab.as<double>();
+    std::vector<double> tab4(2 * (size_t)FM_SP4_ENTRIES);  // finer table of the split-integer kernel (path 4)
+    fm_softplus_table4_fill(tab4.data());
+    MC(ensure(m->sp_tab4, tab4.size() * 8));
+    MC(cudaMemcpy(m->sp_tab4.p, tab4.data(), tab4.size() * 8, cudaMemcpyHostToDevice));
+    mp.sp_tab4 = m->sp_tab4.as<double>();
   }
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
@@ -253,7 +258,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->sp_tab4, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,

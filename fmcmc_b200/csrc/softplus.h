@@ -180,3 +180,44 @@ FM_HD double fm_softplus_tab(double a, const double* tab) {
   const double d = fma(t - MAGIC, -1.0 / FM_SP_H, a);
   return fm_softplus_tab_core(d, tab[2 * k], tab[2 * k + 1]);
 }
+
+// ---- finer table for the split-integer kernel (tiled_i8.cuh), where every FP64 instruction of the epilogue counts ----
+// a = k/128 + d, |d| <= 1/256, a clamped to 40 (log1p(exp(-40)) = 4.2e-18, below half an ulp of any sum it enters):
+// 5121 entries = 80 KB of shared memory, and plain degree-4 Taylor polynomials are exact enough
+//   expm1(-d) / (-d) = 1 - d/2 + d^2/6 - d^3/24 + d^4/120      (next term d^5/720 <= 1.3e-15)
+//   log1p(v) / v     = 1 - v/2 + v^2/3 - v^3/4 + v^4/5          (|v| <= 2e-3: next term 5e-15, times |v| in the result)
+// 13 FP64 instructions + one LDS.128 against 15 for the 32-per-unit table.
+#define FM_SP4_H 128
+#define FM_SP4_AMAX 40
+#define FM_SP4_ENTRIES (FM_SP4_AMAX * FM_SP4_H + 1)
+static inline void fm_softplus_table4_fill(double* tab) {
+  for (int k = 0; k < FM_SP4_ENTRIES; k++) {
+    const long double x = (long double)k / FM_SP4_H;
+    const long double E = expl(-x);
+    tab[2 * k] = (double)(E / (1.0L + E));
+    tab[2 * k + 1] = (double)log1pl(E);
+  }
+}
+FM_HD double fm_softplus_tab4_core(double d, double S, double G) {
+  double q = 1.0 / 120.0;
+  q = fma(q, d, -1.0 / 24.0);
+  q = fma(q, d, 1.0 / 6.0);
+  q = fma(q, d, -0.5);
+  q = fma(q, d, 1.0);
+  const double v = (S * d) * -q;
+  double L = 0.2;
+  L = fma(L, v, -0.25);
+  L = fma(L, v, 1.0 / 3.0);
+  L = fma(L, v, -0.5);
+  L = fma(L, v, 1.0);
+  return fma(v, L, G);
+}
+// reference composition (host tests)
+FM_HD double fm_softplus_tab4(double a, const double* tab) {
+  a = (fm_hi_word(a) >= 0x40440000) ? (double)FM_SP4_AMAX : a;  // >= 40, +inf, NaN -> 40
+  const double MAGIC = 6755399441055744.0;
+  const double t = fma(a, (double)FM_SP4_H, MAGIC);
+  const int32_t k = (int32_t)(uint32_t)fm_double_to_bits(t);
+  const double d = fma(t - MAGIC, -1.0 / FM_SP4_H, a);
+  return fm_softplus_tab4_core(d, tab[2 * k], tab[2 * k + 1]);
+}

@@ -34,7 +34,7 @@
 // (DFMA drops to 3 % of its rate while UTCIMMAs run), so the kernel's time is tensor time PLUS FP64 time; the
 // double buffer hides latencies only.
 //
-// FP64-pipe slots per evaluation: 19 (binary logistic: 1 scale + 18 table-driven softplus; the linear term
+// FP64-pipe slots per evaluation: 17 (binary logistic: 1 scale + 16 table-driven softplus on a 128-per-unit table; the linear term
 // theta . X'(y - 1/2) is a per-chain dot product with a vector computed once per model) against 51 on path 3;
 // Gaussian: 3 against 2 p_x + 2.
 #pragma once
@@ -59,13 +59,21 @@ struct I8Geom {
   static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
 };
 
+// softplus table of the logistic epilogue: the 128-per-unit table (80 KB, degree-4 polynomials) unless the Theta slices
+// already take 96 KB of shared memory (K = 128), then the 32-per-unit one (32 KB, degree 5)
+template <int KB>
+__host__ __device__ constexpr bool i8_fine_table() { return KB < 4; }
+template <int KB>
+__host__ __device__ constexpr int i8_table_bytes(int family) {
+  return family == FMCMC_FAMILY_LOGISTIC ? (i8_fine_table<KB>() ? FM_SP4_ENTRIES : FM_SP_ENTRIES) * 16 : 0;
+}
 // pipeline depth: as many stages as fit beside the Theta slices (KB = 4: 96 KB) and the softplus table, at most 6.
 // The bulk copies have ~1.5 us of latency and a K = 128 stage is consumed in ~0.8 us: 3 stages starved the MMAs
 // (profiles/r01_i8_findings.md)
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_stages(int family) {
   using G = I8Geom<NS, KB>;
-  const int fixed = 256 + G::A_SMEM_BYTES + (family == FMCMC_FAMILY_LOGISTIC ? FM_SP_ENTRIES * 16 : 0) +
+  const int fixed = 256 + G::A_SMEM_BYTES + i8_table_bytes<KB>(family) +
                     (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
   const int fit = (232448 - fixed) / G::STAGE_BYTES;
   return fit > 6 ? 6 : fit;
@@ -74,7 +82,7 @@ template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
   using G = I8Geom<NS, KB>;
   size_t b = 256 + (size_t)i8_stages<NS, KB>(family) * G::STAGE_BYTES + G::A_SMEM_BYTES +
-             (family == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
+             (size_t)i8_table_bytes<KB>(family) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
 
@@ -283,41 +291,77 @@ __device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e
   }
 }
 
-// polynomial coefficients of fm_softplus_tab_core (softplus.h) + range-reduction constants in the constant bank: FP64
-// instructions take c[bank][offset] operands directly, literals cost a UMOV / IMAD.MOV pair per use
-__constant__ double I8_K[16] = {
+// log1p(exp(-|eta|)) = G + v L from the softplus table in shared memory (softplus.h: fm_softplus_tab4_core for the
+// 128-per-unit table, fm_softplus_tab_core for the 32-per-unit one): returns v, L and G apart so the caller can fold them
+// into its running sums.  Coefficients and range-reduction constants sit in the constant bank (FP64 instructions take
+// c[bank][offset] operands; literals cost a UMOV / IMAD.MOV pair per use).
+__constant__ double I8_KF[12] = {1.0 / 120.0, -1.0 / 24.0, 1.0 / 6.0, -0.5, 1.0,     // q = expm1(-d) / (-d), |d| <= 1/256
+                                 0.2, -0.25, 1.0 / 3.0,                                 // L = log1p(v) / v (then -0.5, 1.0 = K[3], K[4])
+                                 6755399441055744.0, (double)FM_SP4_H, -1.0 / FM_SP4_H, 0.5};
+__constant__ double I8_KC[16] = {
     -0x1.6c175d75f692ap-10, 0x1.1111ad1af8af9p-7, -0x1.5555555538138p-5, 0x1.555555551ad1ap-3, -0x1.0000000000000p-1,
-    0x1.0000000000000p+0,                                                  // q = expm1(-d) / (-d)
+    0x1.0000000000000p+0,                                                  // q, |d| <= 1/64
     -0x1.555b6df3e4efdp-3, 0x1.99a091298881fp-3, -0x1.fffffff6b5a52p-3, 0x1.555555500646bp-2, -0x1.0000000000008p-1,
-    0x1.0000000000005p+0,                                                  // L = log1p(v) / v
+    0x1.0000000000005p+0,                                                  // L
     6755399441055744.0, (double)FM_SP_H, -1.0 / FM_SP_H, 0.5};
-__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab, int tune = 0) {
+template <bool FINE>
+__device__ __forceinline__ void i8_softplus_parts(double eta, const double2* __restrict__ tab, double& v, double& L, double& G, int tune) {
   const int hi = __double2hiint(eta), lo = __double2loint(eta);
-  // |eta| clamped near 64 on the high word alone (>= 64 -> [64, 64 + 2^-14]: table entry 2048, tiny remainder)
-  const double a = __hiloint2double(min(hi & 0x7fffffff, 0x40500000), lo);
-  const double t = fma(a, I8_K[13], I8_K[12]);   // low word of t = round(32 a)
+  // |eta| clamped on the high word alone: >= 40 -> [40, 40 + 2^-15] (entry 5120) / >= 64 -> [64, 64 + 2^-14] (entry 2048)
+  const double a = __hiloint2double(min(hi & 0x7fffffff, FINE ? 0x40440000 : 0x40500000), lo);
+  const double MAGIC = FINE ? I8_KF[8] : I8_KC[12];
+  const double t = fma(a, FINE ? I8_KF[9] : I8_KC[13], MAGIC);   // low word of t = round(H a)
   const int k = __double2loint(t);
-  const double d = fma(t - I8_K[12], I8_K[14], a);
+  const double d = fma(t - MAGIC, FINE ? I8_KF[10] : I8_KC[14], a);
 #ifdef FMCMC_I8_TUNE_HOOKS
   const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
 #else
   const double2 sg = tab[k];
 #endif
-  double q = I8_K[0];
-  q = fma(q, d, I8_K[1]);
-  q = fma(q, d, I8_K[2]);
-  q = fma(q, d, I8_K[3]);
-  q = fma(q, d, I8_K[4]);
-  q = fma(q, d, I8_K[5]);
-  const double v = (sg.x * d) * -q;
-  double L = I8_K[6];
-  L = fma(L, v, I8_K[7]);
-  L = fma(L, v, I8_K[8]);
-  L = fma(L, v, I8_K[9]);
-  L = fma(L, v, I8_K[10]);
-  L = fma(L, v, I8_K[11]);
-  acc_abs = fma(I8_K[15], fabs(eta), acc_abs);
-  acc_g = fma(v, L, acc_g + sg.y);
+  if (FINE) {
+    double q = I8_KF[0];
+    q = fma(q, d, I8_KF[1]);
+    q = fma(q, d, I8_KF[2]);
+    q = fma(q, d, I8_KF[3]);
+    q = fma(q, d, I8_KF[4]);
+    v = (sg.x * d) * -q;
+    L = I8_KF[5];
+    L = fma(L, v, I8_KF[6]);
+    L = fma(L, v, I8_KF[7]);
+    L = fma(L, v, I8_KF[3]);
+    L = fma(L, v, I8_KF[4]);
+  } else {
+    double q = I8_KC[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) q = fma(q, d, I8_KC[i]);
+    v = (sg.x * d) * -q;
+    L = I8_KC[6];
+#pragma unroll
+    for (int i = 7; i < 12; i++) L = fma(L, v, I8_KC[i]);
+  }
+  G = sg.y;
+}
+// Binary logistic regression without the per-observation response: with z = +-eta,
+//   sum_i [min(z_i, 0) - log1p(exp(-|z_i|))] = theta . sxy - sum_i [ |eta_i| / 2 + log1p(exp(-|eta_i|)) ]
+// (y_i eta_i - max(eta_i, 0) = (y_i - 1/2) eta_i - |eta_i| / 2), so the epilogue only accumulates the even function
+// of eta: 17 FP64 instructions (19 with the coarse table), no select, no load of y.  eta is finite here (non-finite
+// Theta never gets this far).
+template <bool FINE>
+__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab, int tune = 0) {
+  double v, L, G;
+  i8_softplus_parts<FINE>(eta, tab, v, L, G, tune);
+  acc_abs = fma(0.5, fabs(eta), acc_abs);
+  acc_g = fma(v, L, acc_g + G);
+}
+// general response (sum(logp[y == 1]) + sum(logq[y == 0]), anything else contributes nothing), NaN propagated like
+// logistic_term_tab (families.cuh)
+template <bool FINE>
+__device__ __forceinline__ double i8_logistic_term(double eta, double y, const double2* __restrict__ tab) {
+  double v, L, G;
+  i8_softplus_parts<FINE>(eta, tab, v, L, G, 0);
+  const double z = (y == 1.0) ? eta : -eta;
+  const double r = fm_min0(z) - fma(v, L, G);
+  return (y == 1.0 || y == 0.0) ? r : 0.0;
 }
 
 template <int FAMILY, bool YBIN, int NS, int KB, int EW, int CH>
@@ -342,7 +386,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
   double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
   double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sp_tab) +
-                                          (FAMILY == FMCMC_FAMILY_LOGISTIC ? (size_t)FM_SP_ENTRIES * 16 : 0));
+                                          (size_t)i8_table_bytes<KB>(FAMILY));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W_TMA = EW, W_MMA = EW + 1;
   if (err[0] != 0) return;
@@ -367,8 +411,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
-    const double2* gt = reinterpret_cast<const double2*>(mp.sp_tab);
-    for (int e = tid; e < FM_SP_ENTRIES; e += NTHREADS) sp_tab[e] = gt[e];
+    constexpr bool FINE = i8_fine_table<KB>();
+    const double2* gt = reinterpret_cast<const double2*>(FINE ? mp.sp_tab4 : mp.sp_tab);
+    for (int e = tid; e < (FINE ? FM_SP4_ENTRIES : FM_SP_ENTRIES); e += NTHREADS) sp_tab[e] = gt[e];
   }
   tc_fence_before();
   __syncthreads();
@@ -535,9 +580,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even(t * csc, acc, acc2, sp_tab, tb.tune);
+                i8_logistic_even<i8_fine_table<KB>()>(t * csc, acc, acc2, sp_tab, tb.tune);
               } else {
-                acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
+                acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
             }
           } else {
@@ -549,9 +594,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even(t * csc, acc, acc2, sp_tab, tb.tune);
+                  i8_logistic_even<i8_fine_table<KB>()>(t * csc, acc, acc2, sp_tab, tb.tune);
                 } else {
-                  acc += tile_term<FAMILY, false>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
+                  acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
               }
             }

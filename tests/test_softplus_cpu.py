@@ -43,6 +43,29 @@ def test_softplus_host_build_vs_mpmath():
     assert e.max() < 2.5 and e.mean() < 0.6, (e.max(), e.mean())
 
 
+def test_softplus_fine_table_vs_mpmath():
+    """The 128-per-unit table + degree-4 Taylor core of the split-integer kernel's epilogue (softplus.h, FM_SP4_*)."""
+    src = '#include "%s/fmcmc_b200/csrc/softplus.h"\n' % ROOT + \
+          'extern "C" void sp4_eval(const double* a, double* o, long n) { static double tab[2 * FM_SP4_ENTRIES]; ' \
+          'fm_softplus_table4_fill(tab); for (long i = 0; i < n; i++) o[i] = fm_softplus_tab4(a[i], tab); }\n'
+    with tempfile.TemporaryDirectory() as td:
+        cpp, so = os.path.join(td, "sp4.cpp"), os.path.join(td, "libsp4.so")
+        open(cpp, "w").write(src)
+        subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
+        L = C.CDLL(so)
+        rng = np.random.default_rng(3)
+        a = np.concatenate([rng.uniform(0, 39.9, 6000), rng.uniform(0, 2, 3000), 10 ** rng.uniform(-300, 1.5, 1000),
+                            np.arange(0, 5120) / 128.0 + 1.0 / 256.0 - 1e-9, [0.0, 1e-17, 36.7, 39.99]])
+        o = np.empty_like(a)
+        L.sp4_eval(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_long(a.size))
+        e = ulp_err(o, a)
+        assert e.max() < 1.5 and e.mean() < 0.45, (e.max(), e.mean())
+        big = np.array([40.0, 41.5, 64.0, 700.0, 1e300, np.inf])            # clamped: absolute error below 4.3e-18
+        ob = np.empty_like(big)
+        L.sp4_eval(big.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p), C.c_long(big.size))
+        assert np.all(np.abs(ob - np.log1p(np.exp(-big))) < 4.3e-18)
+
+
 @pytest.mark.gpu
 def test_softplus_device_vs_mpmath():
     import fmcmc_b200 as fm
