@@ -73,7 +73,7 @@ struct fmcmc_model {
   DevBuf X, y, group, sp_tab, sp_tab4, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
-  int i8_slices = 0;      // int8 slices per operand of path 4: 0 = 6, or 7 for kernel_ram whose adaptation consumes f itself
+  int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (6; 7 for kernel_ram and for n < 65536)
                           // (FMCMC_I8_SLICES = 6 | 7 overrides; tiled_i8.cuh has the error bound)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -824,7 +824,10 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     set_err(err, errlen, "the observation-tiled paths support gaussian_lm / logistic with p_x <= 32 (path 2) or <= 128 (paths 3, 4); got family %d, p_x %d", mp.family, mp.p_x);
     return FMCMC_EUNSUP;
   }
-  const int i8_NS = m->i8_slices ? m->i8_slices : (is_ram ? 7 : 6), i8_KB = i8_kblocks(mp.p_x);
+  // 6 slices leave ~1e-12 |theta x|max in eta: averaged over >= 65536 observations the log-posterior is ~1e-14 relative.
+  // kernel_ram (its adaptation consumes f itself) and short data (less averaging, and the tensor work is negligible
+  // there anyway) run on 7 slices: ~1e-14 in eta, ~1e-15 relative in f.
+  const int i8_NS = m->i8_slices ? m->i8_slices : ((is_ram || mp.n_total < 65536) ? 7 : 6), i8_KB = i8_kblocks(mp.p_x);
   if (path == 4) {  // int8 slice tiles of X (once per model); X with non-finite entries cannot be sliced
     cudaError_t pe = ensure_packed_i8(m, i8_NS, i8_KB);
     if (pe == cudaErrorNotSupported) {

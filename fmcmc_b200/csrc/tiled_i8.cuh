@@ -53,16 +53,19 @@ struct I8Geom {
   static constexpr int SLICE_BYTES = NBLK * BLOCK_BYTES;
   static constexpr int STAGE_BYTES = SLICE_BYTES;                   // a stage is pure MMA operand: only the tensor pipe holds it
   static constexpr int ACC_COLS = NS * BLK;                         // TMEM columns of one accumulator set
-  static constexpr bool A_TMEM = (2 * ACC_COLS + NS * KB * 8) <= 512;
+  // A operand (Theta slices): as many K blocks as fit tensor memory next to the two accumulator sets (8 columns per
+  // slice and K block), the rest in shared memory - every MMA whose A comes from shared memory re-reads 4 KB
   static constexpr int A_COL0 = 2 * ACC_COLS;
-  static constexpr int A_SMEM_BYTES = A_TMEM ? 0 : NS * KB * 4096;
+  static constexpr int A_TKB = ((512 - A_COL0) / (NS * 8)) < KB ? ((512 - A_COL0) / (NS * 8)) : KB;
+  static constexpr int A_SKB = KB - A_TKB;
+  static constexpr int A_SMEM_BYTES = NS * A_SKB * 4096;
   static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
 };
 
-// softplus table of the logistic epilogue: the 128-per-unit table (80 KB, degree-4 polynomials) unless the Theta slices
-// already take 96 KB of shared memory (K = 128), then the 32-per-unit one (32 KB, degree 5)
+// softplus table of the logistic epilogue: the 128-per-unit table (80 KB, degree-4 polynomials); the 32-per-unit one
+// (32 KB, degree 5) is kept as the fallback should a geometry leave too little shared memory
 template <int KB>
-__host__ __device__ constexpr bool i8_fine_table() { return KB < 4; }
+__host__ __device__ constexpr bool i8_fine_table() { return true; }
 template <int KB>
 __host__ __device__ constexpr int i8_table_bytes(int family) {
   return family == FMCMC_FAMILY_LOGISTIC ? (i8_fine_table<KB>() ? FM_SP4_ENTRIES : FM_SP_ENTRIES) * 16 : 0;
@@ -460,17 +463,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       }
 #pragma unroll
       for (int i = 0; i < NS; i++) {
-        if (G::A_TMEM) {
-          tc_st_x8(tmem + G::A_COL0 + (i * KB + kb) * 8 + ((uint32_t)(warp * 32) << 16), w[i]);
+        if (kb < G::A_TKB) {
+          tc_st_x8(tmem + G::A_COL0 + (i * G::A_TKB + kb) * 8 + ((uint32_t)(warp * 32) << 16), w[i]);
         } else {
-          unsigned char* p = sA + (size_t)(i * KB + kb) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
+          unsigned char* p = sA + (size_t)(i * G::A_SKB + (kb - G::A_TKB)) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
           *reinterpret_cast<uint4*>(p) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
           *reinterpret_cast<uint4*>(p + 128) = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
         }
       }
     }
-    if (G::A_TMEM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (G::A_TKB > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (G::A_SKB > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -517,8 +520,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
               const uint32_t idesc = IDESC0 | ((uint32_t)((G::BLK * (NS - j)) >> 3) << 17);
               const uint64_t bdesc = tc_smem_desc(bblk + (uint32_t)(kb * NS) * G::SLAB_BYTES, 128u, 256u);
               const uint32_t accum = (j > 0 || kb > 0) ? 1u : 0u;
-              if (G::A_TMEM) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::A_COL0 + (j * KB + kb) * 8, bdesc, idesc, accum);
-              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)(j * KB + kb) * 4096u, 128u, 256u), bdesc, idesc, accum);
+              if (kb < G::A_TKB) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::A_COL0 + (j * G::A_TKB + kb) * 8, bdesc, idesc, accum);
+              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)(j * G::A_SKB + (kb - G::A_TKB)) * 4096u, 128u, 256u), bdesc, idesc, accum);
             }
           }
           tc_commit(&acc_full[buf]);
