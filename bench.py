@@ -214,6 +214,14 @@ class Workload:
             self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 3, 0, 2
             self.label = (f"lifeexpect hier_normal (smoke x female cells, k=7) n=1000 x {self.chains} chains/GPU, kernel_ram "
                           "(BASELINE configs[3]); on-chip data, latency-bound")
+        elif key == "cfg2":          # BASELINE configs[1]: README model, 4 chains, kernel_normal_reflective, convergence_gelman
+            self.family, self.n, self.p_x, self.k = "gaussian", 1000, 1, 3
+            self.chains = args.chains or 4
+            self.kernel_name = "kernel_normal_reflective(scale=.1, lb=(-5, 0, 0), ub=5) (README.md:378-382)"
+            self.kwarm = 0
+            self.flops_per_eval, self.transc_per_eval, self.fp64_instr_per_eval = 6, 0, 3
+            self.label = (f"README Gaussian LM shape n=1000 k=3 x {self.chains} chains, kernel_normal_reflective + "
+                          "convergence_gelman(200) auto-stop (BASELINE configs[1]); on-chip data, latency-bound")
         elif key == "cfg1":          # BASELINE configs[0]: README model shape, 1 chain, kernel_normal(scale=.1)
             self.family, self.n, self.p_x, self.k = "gaussian", 1000, 1, 3
             self.chains = args.chains or 1
@@ -247,6 +255,14 @@ class Workload:
             kern = fm.kernel_ram(lb=[np.nan] * 5 + [1e-3, 1e-3])
             init = np.tile([75.0] * 5 + [5.0, 5.0], (C, 1)) + rng.normal(0, 0.5, (C, k))
             return fam, None, kern, init, None
+        if self.key == "cfg2":
+            rng = np.random.default_rng(1000)
+            X = rng.standard_normal(self.n)
+            y = 3.0 + 2.0 * X + rng.normal(0, 4.0, self.n)
+            fam = fm.ll_gaussian_lm(X.reshape(-1, 1), y, intercept=True, guard=True)
+            kern = fm.kernel_normal_reflective(scale=0.1, lb=[-5.0, 0.0, 0.0], ub=5.0)
+            init = np.tile([0.0, 0.0, float(np.std(y, ddof=1))], (C, 1)) + np.abs(rng.normal(0, 0.2, (C, k)))
+            return fam, None, kern, np.clip(init, [-5, 0, 0.01], 5.0), None
         if self.key == "cfg1":
             X = rng.standard_normal(self.n)
             y = 3.0 + 2.0 * X + rng.normal(0, 4.0, self.n)
@@ -279,7 +295,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg1", "few"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "cfg4", "cfg2", "cfg1", "few"],
                     help="cfg3 = BASELINE configs[2] (default, the metric's configuration); cfg5 = configs[4] per-GPU share")
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
     ap.add_argument("--nobs", dest="n", type=int, default=None, help="observations (cfg5: default 1e7; few: default 1e6)")
@@ -291,7 +307,7 @@ def main():
                     help="prime abs_iter instead of running the kernel's 500 warm-up rows (profiling runs)")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {"cfg3": 100, "cfg5": 5, "cfg4": 1000, "cfg1": 10000, "few": 1000}[args.workload]
+        args.steps = {"cfg3": 100, "cfg5": 5, "cfg4": 1000, "cfg2": 5000, "cfg1": 10000, "few": 1000}[args.workload]
     args.steps = max(args.steps, 2)
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -426,6 +442,19 @@ def main():
     except Exception as e:  # the R-hat of a short window may be degenerate; never fail the bench on it
         mpsrf = f"unavailable: {e}"
 
+    # ---- cfg2: the whole public call with the convergence checker (bulks of 200 rows, R-hat on the device after each) ----
+    autostop = None
+    if wl.key == "cfg2" and rank == 0:
+        msgs = []
+        chk = fm.convergence_gelman(200)
+        a0 = time.perf_counter()
+        res = fm.MCMC(init0, fam, 5000, nchains=C, kernel=wl.make(fm, A, torch, local, rank)[2], conv_checker=chk, seed=11)
+        a_sec = time.perf_counter() - a0
+        rows = res.niter()
+        autostop = {"rows_per_chain_until_converged": rows, "wall_ms": 1e3 * a_sec,
+                    "chain_steps_per_s": C * rows / a_sec, "threshold": 1.1, "freq": 200,
+                    "call": "MCMC(initial, ll_gaussian_lm, 5000, nchains=4, kernel_normal_reflective, conv_checker=convergence_gelman(200))"}
+
     # ---- max over ranks ------------------------------------------------------------------------------------------
     t = torch.tensor([dev_ms, hot_ms, e2e_sec, t_wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -491,6 +520,7 @@ def main():
             "wall_ms_per_step": 1e3 * t_wall / K,
             "roofline": None, "roofline_other": None,
             "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * cw},
+            "autostop": autostop,
             "clocks": clocks,
         }
         # The many-chain kernel is bound by the FP64 pipe (DFMA / DMMA share one 64-lane datapath per SM; tcgen05 has

@@ -224,7 +224,7 @@ typedef struct fmcmc_run_report {
   int64_t n_accept;      /* accepted proposals over all chains               */
   int64_t n_launches;    /* CUDA kernels launched by this call               */
   double  device_ms;     /* CUDA-event time of the stepping kernels          */
-  int32_t path;          /* 1 = chain-resident fused kernel, 2 = observation-tiled (DFMA), 3 = (DMMA) */
+  int32_t path;          /* 1 = chain-resident fused kernel, 2 = observation-tiled (DFMA), 3 = (DMMA), 4 = (tcgen05 int8 slices) */
   int32_t reserved;
   double  hot_ms;        /* summed CUDA-event time of the dominant kernel's launches ... */
   int64_t hot_launches;  /* ... and how many of them were timed (path 2: tiled_loglik)   */
@@ -263,7 +263,10 @@ int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec
 int64_t fmcmc_rows_kept(int64_t nsteps, int64_t burnin, int64_t thin);
 
 /* Force a stepping path (0 = auto, 1 = chain-resident, 2 = observation-tiled DFMA kernel,
- * 3 = observation-tiled FP64 tensor-core (DMMA) kernel). */
+ * 3 = observation-tiled FP64 tensor-core (DMMA) kernel, 4 = observation-tiled split-integer kernel: X.Theta
+ * exact on int8 slices on the tcgen05 tensor cores, FP64 pipe for the log-density only).  Auto picks 1 for data
+ * that fits on chip, 2 for p_x <= 16, 4 for more than 128 likelihood columns (chains), else 3; 4 falls back to 3
+ * when X holds non-finite values.  No equivalent in the reference (one CPU code path). */
 int fmcmc_set_path(fmcmc_model* m, int path);
 
 /* Evaluate the family's log-posterior for `nchains` parameter vectors
