@@ -356,6 +356,48 @@ __device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, do
   acc_abs = fma(0.5, fabs(eta), acc_abs);
   acc_g = fma(v, L, acc_g + G);
 }
+// The same with the scaling folded in: eta = t csc with t the integer-valued double from the reassembly and csc a power
+// of two, so |eta| is never formed.  Adding |t| csc to 1.5 * 2^(52 - log2 H) rounds it to a multiple of 1 / H (k in the low
+// word), the remainder d = |t| csc - k / H is one more fma, and sum |eta| is csc * sum |t| (scaled once per chain at the
+// end): 16 FP64 instructions.  hi_clamp = high word of AMAX / csc.
+template <bool FINE>
+__device__ __forceinline__ void i8_logistic_even_t(double t, double csc, int hi_clamp, double& acc_abs_t, double& acc_g,
+                                                   const double2* __restrict__ tab, int tune = 0) {
+  const double MAGICH = FINE ? 52776558133248.0 : 211106232532992.0;  // 1.5 * 2^45 (H = 128) / 1.5 * 2^47 (H = 32)
+  const double tc = __hiloint2double(min(__double2hiint(t) & 0x7fffffff, hi_clamp), __double2loint(t));  // |t|, clamped
+  const double t2 = fma(tc, csc, MAGICH);
+  const int k = __double2loint(t2);
+  const double d = fma(tc, csc, MAGICH - t2);
+#ifdef FMCMC_I8_TUNE_HOOKS
+  const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
+#else
+  const double2 sg = tab[k];
+#endif
+  double v, L;
+  if (FINE) {
+    double q = I8_KF[0];
+    q = fma(q, d, I8_KF[1]);
+    q = fma(q, d, I8_KF[2]);
+    q = fma(q, d, I8_KF[3]);
+    q = fma(q, d, I8_KF[4]);
+    v = (sg.x * d) * -q;
+    L = I8_KF[5];
+    L = fma(L, v, I8_KF[6]);
+    L = fma(L, v, I8_KF[7]);
+    L = fma(L, v, I8_KF[3]);
+    L = fma(L, v, I8_KF[4]);
+  } else {
+    double q = I8_KC[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++) q = fma(q, d, I8_KC[i]);
+    v = (sg.x * d) * -q;
+    L = I8_KC[6];
+#pragma unroll
+    for (int i = 7; i < 12; i++) L = fma(L, v, I8_KC[i]);
+  }
+  acc_abs_t += fabs(t);
+  acc_g = fma(v, L, acc_g + sg.y);
+}
 // general response (sum(logp[y == 1]) + sum(logq[y == 0]), anything else contributes nothing), NaN propagated like
 // logistic_term_tab (families.cuh)
 template <bool FINE>
@@ -445,6 +487,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const bool th_bad = th_nan || th_big;
   const int eth = th_bad ? 0 : i8_exponent(thmax);
   const double csc = __hiloint2double((1023 - G::SHIFT + eth) << 20, 0);  // eta = t * 2^(eth - SHIFT)
+  // high word of AMAX / csc (AMAX = 40 = 1.25 * 2^5 with the fine softplus table, 64 = 2^6 with the coarse one)
+  const int hi_clamp = (i8_fine_table<KB>() ? 0x40440000 : 0x40500000) + ((G::SHIFT - eth) << 20);
   if (tid < I8_CHAINS) {
     for (int kb = 0; kb < KB; kb++) {
       uint32_t w[NS][8];
@@ -583,7 +627,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even<i8_fine_table<KB>()>(t * csc, acc, acc2, sp_tab, tb.tune);
+                i8_logistic_even_t<i8_fine_table<KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
               } else {
                 acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
@@ -597,7 +641,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even<i8_fine_table<KB>()>(t * csc, acc, acc2, sp_tab, tb.tune);
+                  i8_logistic_even_t<i8_fine_table<KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
                 } else {
                   acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
@@ -607,7 +651,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
         }
       }
     }
-    red[h * I8_CHAINS + q * 32 + lane] = acc + acc2;
+    // binary logistic: acc holds sum |t|; sum(|eta| / 2 + g) = (csc / 2) sum |t| + sum g
+    red[h * I8_CHAINS + q * 32 + lane] = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) ? fma(0.5 * csc, acc, acc2) : acc + acc2;
   }
   tc_fence_before();
   __syncthreads();

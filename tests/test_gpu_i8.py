@@ -139,20 +139,22 @@ def test_i8_matches_fp64_kernel_at_scale(oracle):
     assert err < 1e-13, err
 
 
-def test_i8_falls_back_on_nonfinite_design_matrix(oracle):
-    """An Inf in X cannot be sliced: the auto-selected path silently falls back to the FP64 DMMA kernel (same results as the
-    oracle), forcing path 4 is an error."""
+def test_i8_falls_back_on_unsliceable_design_matrix(oracle):
+    """An entry beyond the exponent window (|x| >= 2^480; likewise Inf / NaN) cannot be sliced: the auto-selected path
+    silently falls back to the FP64 DMMA kernel (same results as the oracle), forcing path 4 is an error."""
     from fmcmc_b200 import ll_gaussian_lm, _lib
     from fmcmc_b200.device import DeviceModel
     rng = np.random.default_rng(12)
     n, p, C = 700, 20, 140
     X = rng.standard_normal((n, p))
     y = 1.0 + X @ rng.standard_normal(p) + rng.normal(0, 2.0, n)
-    X[17, 3] = np.inf                                   # every mean is +-Inf / NaN for that row: f = -Inf (guarded)
+    X[17, 3] = 1e200                                    # its coefficient is pinned at 0, so every mean stays finite
     fam = ll_gaussian_lm(X, y, intercept=True, guard=True)
     k = p + 2
-    spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.05)
+    fixed = np.zeros(k, dtype=bool); fixed[4] = True    # parameter 0 = intercept, 1 + j = coefficient of column j
+    spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.05, fixed=fixed)
     init = np.c_[rng.normal(0, 0.1, (C, k - 1)), np.full(C, 3.0)]
+    init[:, 4] = 0.0
     g, o, _ = run_both(oracle, fam, spec, init, 20, C, rng=rng)
     assert g[0]["report"].path == 3
     assert_parity(g[0], o[0], RTOL)
