@@ -360,13 +360,17 @@ __device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, do
 // of two, so |eta| is never formed.  Adding |t| csc to 1.5 * 2^(52 - log2 H) rounds it to a multiple of 1 / H (k in the low
 // word), the remainder d = |t| csc - k / H is one more fma, and sum |eta| is csc * sum |t| (scaled once per chain at the
 // end): 16 FP64 instructions.  hi_clamp = high word of AMAX / csc.
-template <bool FINE>
+// SAFE = false (the warp's chains all have |theta'|max < 2^20 / KB, hence |eta| < 2^25): no clamp of the argument at all -
+// round(H |eta|) then fits the low word of t2, the table INDEX is clamped (one unsigned min; beyond AMAX the entry is
+// G(AMAX) = 4e-18 with a remainder |d| <= 1 / 2H, i.e. the right answer to 4e-18), and |t| enters the two fmas through the
+// free source modifier.  SAFE = true clamps |t| itself on its high word (AMAX / csc = hi_clamp) for arbitrary magnitudes.
+template <bool FINE, bool SAFE>
 __device__ __forceinline__ void i8_logistic_even_t(double t, double csc, int hi_clamp, double& acc_abs_t, double& acc_g,
                                                    const double2* __restrict__ tab, int tune = 0) {
   const double MAGICH = FINE ? 52776558133248.0 : 211106232532992.0;  // 1.5 * 2^45 (H = 128) / 1.5 * 2^47 (H = 32)
-  const double tc = __hiloint2double(min(__double2hiint(t) & 0x7fffffff, hi_clamp), __double2loint(t));  // |t|, clamped
+  const double tc = SAFE ? __hiloint2double(min(__double2hiint(t) & 0x7fffffff, hi_clamp), __double2loint(t)) : fabs(t);
   const double t2 = fma(tc, csc, MAGICH);
-  const int k = __double2loint(t2);
+  const int k = SAFE ? __double2loint(t2) : (int)min((unsigned)__double2loint(t2), (unsigned)(FINE ? FM_SP4_ENTRIES : FM_SP_ENTRIES) - 1u);
   const double d = fma(tc, csc, MAGICH - t2);
 #ifdef FMCMC_I8_TUNE_HOOKS
   const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
@@ -489,6 +493,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const double csc = __hiloint2double((1023 - G::SHIFT + eth) << 20, 0);  // eta = t * 2^(eth - SHIFT)
   // high word of AMAX / csc (AMAX = 40 = 1.25 * 2^5 with the fine softplus table, 64 = 2^6 with the coarse one)
   const int hi_clamp = (i8_fine_table<KB>() ? 0x40440000 : 0x40500000) + ((G::SHIFT - eth) << 20);
+  // |eta| <= 32 KB max|theta'| < 2^(5 + log2 KB + eth): below 2^25 for every chain of the warp, the unclamped epilogue applies
+  const bool eta_small = __all_sync(FM_FULL, eth + 5 + (KB == 1 ? 0 : (KB == 2 ? 1 : 2)) <= 25);
   if (tid < I8_CHAINS) {
     for (int kb = 0; kb < KB; kb++) {
       uint32_t w[NS][8];
@@ -619,7 +625,11 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             for (int e = 0; e < CH; e++) acc += (double)(int)(a[0][e] ^ a[NS - 1][e]);
           } else
 #endif
-          if (obs0 + CH <= valid) {
+          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && eta_small && obs0 + CH <= valid) {  // the hot loop of cfg3
+#pragma unroll
+            for (int e = 0; e < CH; e++)
+              i8_logistic_even_t<i8_fine_table<KB>(), false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+          } else if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
               const double t = i8_assemble<NS, CH>(a, e, tb.tune);
@@ -627,7 +637,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even_t<i8_fine_table<KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                i8_logistic_even_t<i8_fine_table<KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
               } else {
                 acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
@@ -641,7 +651,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even_t<i8_fine_table<KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                  i8_logistic_even_t<i8_fine_table<KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
                 } else {
                   acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }

@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(1024, 1) k(double* out, const double* gtab, in
     for (int e = 0; e < CH; e++) {
       if (MODE == 0) {            // the real thing
         const double t = i8_assemble<6, CH>(a, e);
-        i8_logistic_even_t<true>(t, csc, 0x40440000 + (45 << 20), acc, acc2, tab);
+        i8_logistic_even_t<true, false>(t, csc, 0x40440000 + (45 << 20), acc, acc2, tab);
       } else if (MODE == 1) {     // FP64 part only: the argument comes from a cheap int -> double trick
         const double t = __hiloint2double(0x43300000, (int)a[0][e]) - 4503599627370496.0;
-        i8_logistic_even_t<true>(t, 9.5367431640625e-07, 0x40440000 + (20 << 20), acc, acc2, tab);
+        i8_logistic_even_t<true, false>(t, 9.5367431640625e-07, 0x40440000 + (20 << 20), acc, acc2, tab);
       } else if (MODE == 2) {     // integer merge + conversion only (the kernel's form)
         acc += i8_assemble<6, CH>(a, e);
       } else {

@@ -164,3 +164,21 @@ def test_i8_falls_back_on_unsliceable_design_matrix(oracle):
         m.run(spec, 5, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
     m.close()
     assert "finite" in str(ei.value)
+
+
+def test_i8_large_linear_predictors(oracle):
+    """|eta| far beyond the softplus table (40): moderate magnitudes take the unclamped epilogue (index clamp only), chains
+    with |theta| >= 2^20 switch their warp to the clamped one; both must reproduce the oracle (terms ~ -|eta| or ~ 0)."""
+    from fmcmc_b200 import ll_logistic
+    rng = np.random.default_rng(21)
+    n, p, C = 900, 10, 150
+    X = rng.standard_normal((n, p)); X[:, 0] = 1.0
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    fam = ll_logistic(X, y, prior_sd=2.0)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.5)
+    init = rng.normal(0, 30.0, (C, p))                  # |eta| ~ 100
+    init[7] *= 1e5                                      # |theta| ~ 3e6 > 2^20: clamped variant for that warp
+    init[140] *= 1e9
+    g, o, _ = run_both(oracle, fam, spec, init, 25, C, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL)
