@@ -490,7 +490,7 @@ def main():
         achieved_tf = flops / (hot_ms * 1e-3) / 1e12
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
-        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (16 if wl.family == "logistic" else 3)
+        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (14 if wl.family == "logistic" else 3)
         pipe_util = evals * fp64_instr / 32.0 / (hot_ms * 1e-3) / pipe_slots
         kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 4: "tiled_loglik_i8_kernel", 1: "mh_resident_kernel"}[path]
         line = {

@@ -53,6 +53,7 @@ struct ModelParams {
   const double* i8_sxy;     // [p_x] sum_i (y_i - 1/2) x_ij (binary logistic)
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
   const double* sp_tab4; // logistic: the 128-per-unit table of the split-integer kernel (softplus.h, FM_SP4_*)
+  const double* sp_tab8; // logistic: its 256-per-unit table (FM_SP8_*)
 };
 
 // Per-run device buffers shared by both paths.

@@ -62,30 +62,33 @@ struct I8Geom {
   static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
 };
 
-// softplus table of the logistic epilogue: the 128-per-unit table (80 KB, degree-4 polynomials); the 32-per-unit one
-// (32 KB, degree 5) is kept as the fallback should a geometry leave too little shared memory
-template <int KB>
-__host__ __device__ constexpr bool i8_fine_table() { return true; }
-template <int KB>
-__host__ __device__ constexpr int i8_table_bytes(int family) {
-  return family == FMCMC_FAMILY_LOGISTIC ? (i8_fine_table<KB>() ? FM_SP4_ENTRIES : FM_SP_ENTRIES) * 16 : 0;
+// softplus table of the logistic epilogue (softplus.h): level 2 = 256 entries per unit (160 KB, cubic polynomials, 11 FP64
+// instructions) when it leaves room for two pipeline stages, else level 1 = 128 per unit (80 KB, degree 4, 13)
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_smem_fixed(int table_bytes) {
+  return 256 + I8Geom<NS, KB>::A_SMEM_BYTES + table_bytes + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
 }
-// pipeline depth: as many stages as fit beside the Theta slices (KB = 4: 96 KB) and the softplus table, at most 6.
-// The bulk copies have ~1.5 us of latency and a K = 128 stage is consumed in ~0.8 us: 3 stages starved the MMAs
-// (profiles/r01_i8_findings.md)
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_table_level() {
+  return (232448 - i8_smem_fixed<NS, KB>(FM_SP8_ENTRIES * 16)) / I8Geom<NS, KB>::STAGE_BYTES >= 2 ? 2 : 1;
+}
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_table_entries() { return i8_table_level<NS, KB>() == 2 ? FM_SP8_ENTRIES : FM_SP4_ENTRIES; }
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_table_bytes(int family) {
+  return family == FMCMC_FAMILY_LOGISTIC ? i8_table_entries<NS, KB>() * 16 : 0;
+}
+// pipeline depth: as many stages as fit beside the Theta slices and the softplus table, at most 6.
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_stages(int family) {
-  using G = I8Geom<NS, KB>;
-  const int fixed = 256 + G::A_SMEM_BYTES + i8_table_bytes<KB>(family) +
-                    (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
-  const int fit = (232448 - fixed) / G::STAGE_BYTES;
+  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family))) / I8Geom<NS, KB>::STAGE_BYTES;
   return fit > 6 ? 6 : fit;
 }
 template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
   using G = I8Geom<NS, KB>;
   size_t b = 256 + (size_t)i8_stages<NS, KB>(family) * G::STAGE_BYTES + G::A_SMEM_BYTES +
-             (size_t)i8_table_bytes<KB>(family) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
+             (size_t)i8_table_bytes<NS, KB>(family) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
 
@@ -294,83 +297,61 @@ __device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e
   }
 }
 
-// log1p(exp(-|eta|)) = G + v L from the softplus table in shared memory (softplus.h: fm_softplus_tab4_core for the
-// 128-per-unit table, fm_softplus_tab_core for the 32-per-unit one): returns v, L and G apart so the caller can fold them
-// into its running sums.  Coefficients and range-reduction constants sit in the constant bank (FP64 instructions take
-// c[bank][offset] operands; literals cost a UMOV / IMAD.MOV pair per use).
-__constant__ double I8_KF[12] = {1.0 / 120.0, -1.0 / 24.0, 1.0 / 6.0, -0.5, 1.0,     // q = expm1(-d) / (-d), |d| <= 1/256
-                                 0.2, -0.25, 1.0 / 3.0,                                 // L = log1p(v) / v (then -0.5, 1.0 = K[3], K[4])
-                                 6755399441055744.0, (double)FM_SP4_H, -1.0 / FM_SP4_H, 0.5};
-__constant__ double I8_KC[16] = {
-    -0x1.6c175d75f692ap-10, 0x1.1111ad1af8af9p-7, -0x1.5555555538138p-5, 0x1.555555551ad1ap-3, -0x1.0000000000000p-1,
-    0x1.0000000000000p+0,                                                  // q, |d| <= 1/64
-    -0x1.555b6df3e4efdp-3, 0x1.99a091298881fp-3, -0x1.fffffff6b5a52p-3, 0x1.555555500646bp-2, -0x1.0000000000008p-1,
-    0x1.0000000000005p+0,                                                  // L
-    6755399441055744.0, (double)FM_SP_H, -1.0 / FM_SP_H, 0.5};
-template <bool FINE>
-__device__ __forceinline__ void i8_softplus_parts(double eta, const double2* __restrict__ tab, double& v, double& L, double& G, int tune) {
-  const int hi = __double2hiint(eta), lo = __double2loint(eta);
-  // |eta| clamped on the high word alone: >= 40 -> [40, 40 + 2^-15] (entry 5120) / >= 64 -> [64, 64 + 2^-14] (entry 2048)
-  const double a = __hiloint2double(min(hi & 0x7fffffff, FINE ? 0x40440000 : 0x40500000), lo);
-  const double MAGIC = FINE ? I8_KF[8] : I8_KC[12];
-  const double t = fma(a, FINE ? I8_KF[9] : I8_KC[13], MAGIC);   // low word of t = round(H a)
-  const int k = __double2loint(t);
-  const double d = fma(t - MAGIC, FINE ? I8_KF[10] : I8_KC[14], a);
-#ifdef FMCMC_I8_TUNE_HOOKS
-  const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
-#else
-  const double2 sg = tab[k];
-#endif
-  if (FINE) {
-    double q = I8_KF[0];
-    q = fma(q, d, I8_KF[1]);
-    q = fma(q, d, I8_KF[2]);
-    q = fma(q, d, I8_KF[3]);
-    q = fma(q, d, I8_KF[4]);
-    v = (sg.x * d) * -q;
-    L = I8_KF[5];
-    L = fma(L, v, I8_KF[6]);
-    L = fma(L, v, I8_KF[7]);
-    L = fma(L, v, I8_KF[3]);
-    L = fma(L, v, I8_KF[4]);
+// Polynomial cores of the softplus tables (softplus.h: fm_softplus_tab4_core / fm_softplus_tab8_core) with the coefficients
+// in the constant bank (FP64 instructions take c[bank][offset] operands; literals cost a UMOV / IMAD.MOV pair per use).
+// Given the remainder d and the table entry S: v = S expm1(-d) and L = log1p(v) / v, so that log1p(exp(-a)) = G + v L.
+__constant__ double I8_K1[8] = {1.0 / 120.0, -1.0 / 24.0, 1.0 / 6.0, -0.5, 1.0, 0.2, -0.25, 1.0 / 3.0};   // level 1: Taylor, degree 4
+__constant__ double I8_K2[8] = {-0x1.5555582d82db0p-5, 0x1.55555999999f5p-3, -0x1.fffffffffffd2p-2, 0x1.fffffffffff77p-1,
+                                -0x1.00000b2f503bap-2, 0x1.555562c14f2f7p-2, -0x1.ffffffffffe89p-2, 0x1.fffffffffff1fp-1};  // level 2: cubic
+template <int TL>
+__device__ __forceinline__ void i8_softplus_core(double d, double S, double& v, double& L) {
+  if (TL == 2) {
+    double q = I8_K2[0];
+    q = fma(q, d, I8_K2[1]);
+    q = fma(q, d, I8_K2[2]);
+    q = fma(q, d, I8_K2[3]);
+    v = (S * d) * -q;
+    L = I8_K2[4];
+    L = fma(L, v, I8_K2[5]);
+    L = fma(L, v, I8_K2[6]);
+    L = fma(L, v, I8_K2[7]);
   } else {
-    double q = I8_KC[0];
-#pragma unroll
-    for (int i = 1; i < 6; i++) q = fma(q, d, I8_KC[i]);
-    v = (sg.x * d) * -q;
-    L = I8_KC[6];
-#pragma unroll
-    for (int i = 7; i < 12; i++) L = fma(L, v, I8_KC[i]);
+    double q = I8_K1[0];
+    q = fma(q, d, I8_K1[1]);
+    q = fma(q, d, I8_K1[2]);
+    q = fma(q, d, I8_K1[3]);
+    q = fma(q, d, I8_K1[4]);
+    v = (S * d) * -q;
+    L = I8_K1[5];
+    L = fma(L, v, I8_K1[6]);
+    L = fma(L, v, I8_K1[7]);
+    L = fma(L, v, I8_K1[3]);
+    L = fma(L, v, I8_K1[4]);
   }
-  G = sg.y;
 }
+// 1.5 * 2^(52 - log2 H): adding a >= 0 to it rounds a to a multiple of 1 / H and leaves round(H a) in the low word
+template <int TL>
+__device__ __forceinline__ constexpr double i8_magic_h() { return TL == 2 ? 26388279066624.0 : 52776558133248.0; }
+
 // Binary logistic regression without the per-observation response: with z = +-eta,
 //   sum_i [min(z_i, 0) - log1p(exp(-|z_i|))] = theta . sxy - sum_i [ |eta_i| / 2 + log1p(exp(-|eta_i|)) ]
-// (y_i eta_i - max(eta_i, 0) = (y_i - 1/2) eta_i - |eta_i| / 2), so the epilogue only accumulates the even function
-// of eta: 17 FP64 instructions (19 with the coarse table), no select, no load of y.  eta is finite here (non-finite
-// Theta never gets this far).
-template <bool FINE>
-__device__ __forceinline__ void i8_logistic_even(double eta, double& acc_abs, double& acc_g, const double2* __restrict__ tab, int tune = 0) {
-  double v, L, G;
-  i8_softplus_parts<FINE>(eta, tab, v, L, G, tune);
-  acc_abs = fma(0.5, fabs(eta), acc_abs);
-  acc_g = fma(v, L, acc_g + G);
-}
-// The same with the scaling folded in: eta = t csc with t the integer-valued double from the reassembly and csc a power
-// of two, so |eta| is never formed.  Adding |t| csc to 1.5 * 2^(52 - log2 H) rounds it to a multiple of 1 / H (k in the low
-// word), the remainder d = |t| csc - k / H is one more fma, and sum |eta| is csc * sum |t| (scaled once per chain at the
-// end): 16 FP64 instructions.  hi_clamp = high word of AMAX / csc.
+// (y_i eta_i - max(eta_i, 0) = (y_i - 1/2) eta_i - |eta_i| / 2), so the epilogue only accumulates the even function of
+// eta; no select, no load of y.  The scaling is folded in: eta = t csc with t the integer-valued double from the
+// reassembly and csc a power of two, so |eta| is never formed - adding |t| csc to the magic constant rounds it to a multiple
+// of 1 / H (k in the low word), the remainder d = |t| csc - k / H is one more fma, and sum |eta| = csc sum |t| (scaled once
+// per chain at the end).  14 FP64 instructions with the level-2 table, 16 with level 1.
 // SAFE = false (the warp's chains all have |theta'|max < 2^20 / KB, hence |eta| < 2^25): no clamp of the argument at all -
-// round(H |eta|) then fits the low word of t2, the table INDEX is clamped (one unsigned min; beyond AMAX the entry is
+// round(H |eta|) then fits the low word, the table INDEX is clamped (one unsigned min; beyond AMAX the entry is
 // G(AMAX) = 4e-18 with a remainder |d| <= 1 / 2H, i.e. the right answer to 4e-18), and |t| enters the two fmas through the
 // free source modifier.  SAFE = true clamps |t| itself on its high word (AMAX / csc = hi_clamp) for arbitrary magnitudes.
-template <bool FINE, bool SAFE>
+template <int TL, bool SAFE>
 __device__ __forceinline__ void i8_logistic_even_t(double t, double csc, int hi_clamp, double& acc_abs_t, double& acc_g,
                                                    const double2* __restrict__ tab, int tune = 0) {
-  const double MAGICH = FINE ? 52776558133248.0 : 211106232532992.0;  // 1.5 * 2^45 (H = 128) / 1.5 * 2^47 (H = 32)
+  constexpr double MAGICH = i8_magic_h<TL>();
+  constexpr unsigned KMAX = (TL == 2 ? FM_SP8_ENTRIES : FM_SP4_ENTRIES) - 1u;
   const double tc = SAFE ? __hiloint2double(min(__double2hiint(t) & 0x7fffffff, hi_clamp), __double2loint(t)) : fabs(t);
   const double t2 = fma(tc, csc, MAGICH);
-  const int k = SAFE ? __double2loint(t2) : (int)min((unsigned)__double2loint(t2), (unsigned)(FINE ? FM_SP4_ENTRIES : FM_SP_ENTRIES) - 1u);
+  const int k = SAFE ? __double2loint(t2) : (int)min((unsigned)__double2loint(t2), KMAX);
   const double d = fma(tc, csc, MAGICH - t2);
 #ifdef FMCMC_I8_TUNE_HOOKS
   const double2 sg = (tune & 4) ? make_double2(d * 0.25, d) : tab[k];
@@ -378,38 +359,24 @@ __device__ __forceinline__ void i8_logistic_even_t(double t, double csc, int hi_
   const double2 sg = tab[k];
 #endif
   double v, L;
-  if (FINE) {
-    double q = I8_KF[0];
-    q = fma(q, d, I8_KF[1]);
-    q = fma(q, d, I8_KF[2]);
-    q = fma(q, d, I8_KF[3]);
-    q = fma(q, d, I8_KF[4]);
-    v = (sg.x * d) * -q;
-    L = I8_KF[5];
-    L = fma(L, v, I8_KF[6]);
-    L = fma(L, v, I8_KF[7]);
-    L = fma(L, v, I8_KF[3]);
-    L = fma(L, v, I8_KF[4]);
-  } else {
-    double q = I8_KC[0];
-#pragma unroll
-    for (int i = 1; i < 6; i++) q = fma(q, d, I8_KC[i]);
-    v = (sg.x * d) * -q;
-    L = I8_KC[6];
-#pragma unroll
-    for (int i = 7; i < 12; i++) L = fma(L, v, I8_KC[i]);
-  }
+  i8_softplus_core<TL>(d, sg.x, v, L);
   acc_abs_t += fabs(t);
   acc_g = fma(v, L, acc_g + sg.y);
 }
 // general response (sum(logp[y == 1]) + sum(logq[y == 0]), anything else contributes nothing), NaN propagated like
 // logistic_term_tab (families.cuh)
-template <bool FINE>
+template <int TL>
 __device__ __forceinline__ double i8_logistic_term(double eta, double y, const double2* __restrict__ tab) {
-  double v, L, G;
-  i8_softplus_parts<FINE>(eta, tab, v, L, G, 0);
+  constexpr double MAGICH = i8_magic_h<TL>();
+  // |eta| clamped on the high word alone: >= 40 -> [40, 40 + 2^-15], the last table entry with a tiny remainder
+  const double a = __hiloint2double(min(__double2hiint(eta) & 0x7fffffff, 0x40440000), __double2loint(eta));
+  const double t2 = a + MAGICH;
+  const double d = a + (MAGICH - t2);
+  const double2 sg = tab[__double2loint(t2)];
+  double v, L;
+  i8_softplus_core<TL>(d, sg.x, v, L);
   const double z = (y == 1.0) ? eta : -eta;
-  const double r = fm_min0(z) - fma(v, L, G);
+  const double r = fm_min0(z) - fma(v, L, sg.y);
   return (y == 1.0 || y == 0.0) ? r : 0.0;
 }
 
@@ -435,7 +402,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
   double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
   double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sp_tab) +
-                                          (size_t)i8_table_bytes<KB>(FAMILY));
+                                          (size_t)i8_table_bytes<NS, KB>(FAMILY));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W_TMA = EW, W_MMA = EW + 1;
   if (err[0] != 0) return;
@@ -460,9 +427,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
-    constexpr bool FINE = i8_fine_table<KB>();
-    const double2* gt = reinterpret_cast<const double2*>(FINE ? mp.sp_tab4 : mp.sp_tab);
-    for (int e = tid; e < (FINE ? FM_SP4_ENTRIES : FM_SP_ENTRIES); e += NTHREADS) sp_tab[e] = gt[e];
+    const double2* gt = reinterpret_cast<const double2*>(i8_table_level<NS, KB>() == 2 ? mp.sp_tab8 : mp.sp_tab4);
+    for (int e = tid; e < i8_table_entries<NS, KB>(); e += NTHREADS) sp_tab[e] = gt[e];
   }
   tc_fence_before();
   __syncthreads();
@@ -491,8 +457,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const bool th_bad = th_nan || th_big;
   const int eth = th_bad ? 0 : i8_exponent(thmax);
   const double csc = __hiloint2double((1023 - G::SHIFT + eth) << 20, 0);  // eta = t * 2^(eth - SHIFT)
-  // high word of AMAX / csc (AMAX = 40 = 1.25 * 2^5 with the fine softplus table, 64 = 2^6 with the coarse one)
-  const int hi_clamp = (i8_fine_table<KB>() ? 0x40440000 : 0x40500000) + ((G::SHIFT - eth) << 20);
+  // high word of AMAX / csc (AMAX = 40 = 1.25 * 2^5)
+  const int hi_clamp = (0x40440000) + ((G::SHIFT - eth) << 20);
   // |eta| <= 32 KB max|theta'| < 2^(5 + log2 KB + eth): below 2^25 for every chain of the warp, the unclamped epilogue applies
   const bool eta_small = __all_sync(FM_FULL, eth + 5 + (KB == 1 ? 0 : (KB == 2 ? 1 : 2)) <= 25);
   if (tid < I8_CHAINS) {
@@ -628,7 +594,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && eta_small && obs0 + CH <= valid) {  // the hot loop of cfg3
 #pragma unroll
             for (int e = 0; e < CH; e++)
-              i8_logistic_even_t<i8_fine_table<KB>(), false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+              i8_logistic_even_t<i8_table_level<NS, KB>(), false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
           } else if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
@@ -637,9 +603,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even_t<i8_fine_table<KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                i8_logistic_even_t<i8_table_level<NS, KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
               } else {
-                acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
+                acc += i8_logistic_term<i8_table_level<NS, KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
             }
           } else {
@@ -651,9 +617,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even_t<i8_fine_table<KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                  i8_logistic_even_t<i8_table_level<NS, KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
                 } else {
-                  acc += i8_logistic_term<i8_fine_table<KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
+                  acc += i8_logistic_term<i8_table_level<NS, KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
               }
             }

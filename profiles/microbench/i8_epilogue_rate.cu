@@ -1,5 +1,5 @@
 // i8_epilogue_rate.cu — how fast can the SM run path 4's per-evaluation instruction stream (integer merge + I2F +
-// 16 FP64 softplus).  NOTE: synthesising the six accumulator words costs ~6 integer instructions (~12 clk) per
+// 14 FP64 softplus).  NOTE: synthesising the six accumulator words costs ~6 integer instructions (~12 clk) per
 // evaluation here that the kernel does not pay (its words come from tcgen05.ld). when nothing else is in the way (no TMEM, no MMA, no barriers)?  W warps per SM, CH evaluations
 // interleaved per warp, inputs synthesised in registers.  Reports clk per warp-evaluation per scheduler; the FP64
 // pipe alone needs 38 (19 instructions x 2 clk).
@@ -30,8 +30,8 @@ __device__ __forceinline__ double merge_variant(const uint32_t (&a)[6][CH], int 
 
 template <int CH, int MODE>
 __global__ void __launch_bounds__(1024, 1) k(double* out, const double* gtab, int iters, long long* cyc) {
-  extern __shared__ double2 tab[];   // FM_SP4_ENTRIES (fine table)
-  for (int e = threadIdx.x; e < FM_SP4_ENTRIES; e += blockDim.x) tab[e] = reinterpret_cast<const double2*>(gtab)[e];
+  extern __shared__ double2 tab[];   // FM_SP8_ENTRIES (fine table)
+  for (int e = threadIdx.x; e < FM_SP8_ENTRIES; e += blockDim.x) tab[e] = reinterpret_cast<const double2*>(gtab)[e];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const double csc = 1.0 / 35184372088832.0;  // 2^-45: eta = t * csc of order 1
@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(1024, 1) k(double* out, const double* gtab, in
     for (int e = 0; e < CH; e++) {
       if (MODE == 0) {            // the real thing
         const double t = i8_assemble<6, CH>(a, e);
-        i8_logistic_even_t<true, false>(t, csc, 0x40440000 + (45 << 20), acc, acc2, tab);
+        i8_logistic_even_t<2, false>(t, csc, 0x40440000 + (45 << 20), acc, acc2, tab);
       } else if (MODE == 1) {     // FP64 part only: the argument comes from a cheap int -> double trick
         const double t = __hiloint2double(0x43300000, (int)a[0][e]) - 4503599627370496.0;
-        i8_logistic_even_t<true, false>(t, 9.5367431640625e-07, 0x40440000 + (20 << 20), acc, acc2, tab);
+        i8_logistic_even_t<2, false>(t, 9.5367431640625e-07, 0x40440000 + (20 << 20), acc, acc2, tab);
       } else if (MODE == 2) {     // integer merge + conversion only (the kernel's form)
         acc += i8_assemble<6, CH>(a, e);
       } else {
@@ -72,16 +72,16 @@ int main() {
   long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 8);
   cudaMalloc(&cyc, 8);
-  double* htab = new double[2 * FM_SP4_ENTRIES];
-  fm_softplus_table4_fill(htab);
-  cudaMalloc(&gtab, 2 * FM_SP4_ENTRIES * 8);
-  cudaMemcpy(gtab, htab, 2 * FM_SP4_ENTRIES * 8, cudaMemcpyHostToDevice);
+  double* htab = new double[2 * FM_SP8_ENTRIES];
+  fm_softplus_table8_fill(htab);
+  cudaMalloc(&gtab, 2 * FM_SP8_ENTRIES * 8);
+  cudaMemcpy(gtab, htab, 2 * FM_SP8_ENTRIES * 8, cudaMemcpyHostToDevice);
   const int iters = 2000;
   auto run = [&](auto kern, int warps, int CH, const char* name) {
     long long hc = 0;
     for (int rep = 0; rep < 2; rep++) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SP4_ENTRIES * 16);
-      kern<<<148, warps * 32, FM_SP4_ENTRIES * 16>>>(out, gtab, iters, cyc);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FM_SP8_ENTRIES * 16);
+      kern<<<148, warps * 32, FM_SP8_ENTRIES * 16>>>(out, gtab, iters, cyc);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
       cudaMemcpy(&hc, cyc, 8, cudaMemcpyDeviceToHost);
@@ -92,8 +92,8 @@ int main() {
   for (int warps : {8, 16}) {
     run(k<8, 0>, warps, 8, "merge + I2F + softplus (the epilogue)");
     run(k<4, 0>, warps, 4, "merge + I2F + softplus (the epilogue)");
-    run(k<8, 1>, warps, 8, "softplus only (16 FP64 + LDS + 3 int)");
-    run(k<4, 1>, warps, 4, "softplus only (16 FP64 + LDS + 3 int)");
+    run(k<8, 1>, warps, 8, "softplus only (14 FP64 + LDS + 3 int)");
+    run(k<4, 1>, warps, 4, "softplus only (14 FP64 + LDS + 3 int)");
     run(k<8, 2>, warps, 8, "merge only: int32 pairs, int64, I2F.S64 (kernel)");
     if (warps == 16) {
       run(k<8, 11>, warps, 8, "merge only: int32 pairs, 3 magic32, 2 DFMA");

@@ -66,6 +66,27 @@ def test_softplus_fine_table_vs_mpmath():
         assert np.all(np.abs(ob - np.log1p(np.exp(-big))) < 4.3e-18)
 
 
+def test_softplus_finest_table_vs_mpmath():
+    """The 256-per-unit table + cubic near-minimax cores (softplus.h, FM_SP8_*) of the split-integer kernel at p <= 64."""
+    src = '#include "%s/fmcmc_b200/csrc/softplus.h"\n' % ROOT + \
+          'extern "C" void sp8_eval(const double* a, double* o, long n) { static double tab[2 * FM_SP8_ENTRIES]; ' \
+          'fm_softplus_table8_fill(tab); for (long i = 0; i < n; i++) o[i] = fm_softplus_tab8(a[i], tab); }\n'
+    with tempfile.TemporaryDirectory() as td:
+        cpp, so = os.path.join(td, "sp8.cpp"), os.path.join(td, "libsp8.so")
+        open(cpp, "w").write(src)
+        subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
+        L = C.CDLL(so)
+        rng = np.random.default_rng(4)
+        a = np.concatenate([rng.uniform(0, 39.9, 6000), rng.uniform(0, 2, 3000), 10 ** rng.uniform(-300, 1.5, 1000),
+                            np.arange(0, 10240) / 256.0 + 1.0 / 512.0 - 1e-9, np.arange(0, 10240) / 256.0 - 1.0 / 512.0 + 1e-9,
+                            [0.0, 1e-17, 36.7, 39.99]])
+        a = np.abs(a)
+        o = np.empty_like(a)
+        L.sp8_eval(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_long(a.size))
+        e = ulp_err(o, a)
+        assert e.max() < 2.0 and e.mean() < 0.5, (e.max(), e.mean())
+
+
 @pytest.mark.gpu
 def test_softplus_device_vs_mpmath():
     import fmcmc_b200 as fm
