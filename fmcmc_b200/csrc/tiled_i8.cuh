@@ -387,17 +387,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   using G = I8Geom<NS, KB>;
   static_assert(NS >= 2 && NS <= 8, "2..8 slices");
   static_assert(EW == 8 || EW == 16, "2 or 4 epilogue warps per TMEM lane quarter");
-  constexpr int NTHREADS = (EW + 2) * 32;
   constexpr int CW = G::BLK / (EW / 4);  // columns (observations) of a block owned by one epilogue warp
   static_assert(CW % CH == 0, "whole chunks");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   constexpr int STAGES = i8_stages<NS, KB>(FAMILY);
-  static_assert(STAGES >= 2 && 2 * STAGES + 4 <= 31, "barriers live in the first 256 bytes");
+  static_assert(STAGES >= 2 && 2 * STAGES + 5 <= 31, "barriers live in the first 256 bytes");
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* tab_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_bar + 1);
   unsigned char* stage0 = smem_raw + 256;
   unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
   double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
@@ -420,15 +420,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], EW);
     }
+    mbar_init(tab_bar, 1);
     mbar_fence_init();
+    if (FAMILY == FMCMC_FAMILY_LOGISTIC) {  // softplus table: one bulk copy (up to 160 KB), overlapped with the Theta slicing
+      constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_bytes<NS, KB>(FAMILY);
+      mbar_expect_tx(tab_bar, TAB_BYTES);
+      bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? mp.sp_tab8 : mp.sp_tab4, TAB_BYTES, tab_bar);
+    }
   }
   if (warp == W_MMA) {  // the allocating warp also frees
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (FAMILY == FMCMC_FAMILY_LOGISTIC) {
-    const double2* gt = reinterpret_cast<const double2*>(i8_table_level<NS, KB>() == 2 ? mp.sp_tab8 : mp.sp_tab4);
-    for (int e = tid; e < i8_table_entries<NS, KB>(); e += NTHREADS) sp_tab[e] = gt[e];
   }
   tc_fence_before();
   __syncthreads();
@@ -551,6 +553,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     // ===== epilogue: thread = chain (TMEM lane); the EW / 4 warps of a lane quarter split the 32 columns =====
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (FAMILY == FMCMC_FAMILY_LOGISTIC) mbar_wait(tab_bar, 0u);  // the softplus table has landed
     double acc = 0.0, acc2 = 0.0;
     uint32_t blk = 0;
     long long it = 0;
