@@ -76,6 +76,8 @@ struct fmcmc_model {
   int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (6; 7 for kernel_ram and for n < 65536)
                           // (FMCMC_I8_SLICES = 6 | 7 overrides; tiled_i8.cuh has the error bound)
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;        // output rows leave the device while later rows are still being computed
+  std::vector<cudaEvent_t> chunk_ev;         // "kept rows of chunk q are final" (recorded on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
   int smem_optin = 0;
@@ -176,6 +178,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 #define MC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "CUDA error %s (%s)", cudaGetErrorString(e_), #call); fmcmc_model_free(m); return FMCMC_ECUDA; } } while (0)
   MC(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  MC(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   MC(cudaEventCreate(&m->ev0));
   MC(cudaEventCreate(&m->ev1));
   MC(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -277,6 +280,8 @@ extern "C" void fmcmc_model_free(fmcmc_model* m) {
   for (auto& e : m->hot_ev) cudaEventDestroy(e);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  for (auto& e : m->chunk_ev) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -447,6 +452,17 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, double* __res
     else { j = (int)(e % k); r = (e / k) % keep; c = e / ((long long)k * keep); }
     const long long srow = burnin + (r + 1) * thin - 1;
     dst[e] = src[((size_t)srow * C + c) * k + j];
+  }
+}
+// kept rows [r0, r1) only, into the same [C][keep][k] layout (streamed outputs)
+__global__ void gather_rows_range_kernel(const double* __restrict__ src, double* __restrict__ dst, int C, int k,
+                                         long long keep, long long r0, long long r1, long long burnin, long long thin) {
+  const long long nr = r1 - r0, total = (long long)C * nr * k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % k);
+    const long long r = r0 + (e / k) % nr, c = e / ((long long)k * nr);
+    const long long srow = burnin + (r + 1) * thin - 1;
+    dst[((size_t)c * keep + r) * k + j] = src[((size_t)srow * C + c) * k + j];
   }
 }
 __global__ void append_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rowlen,
@@ -847,6 +863,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     }
   }
   long long launches = 0;
+  long long stream_chunk = 0, stream_nchunks = 0;   // streamed outputs (tiled paths): kept rows per chunk, chunks
   int hot_timed = 0;
   CU_CHECK(cudaEventRecord(m->ev0, m->stream));
   if (path == 1) {
@@ -964,9 +981,38 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       m->hot_ev.resize(2 * FM_HOT_EVENTS);
       for (auto& e : m->hot_ev) CU_CHECK(cudaEventCreate(&e));
     }
+    // Streamed outputs: the stepping launches are all queued first; while the GPU works through them the host copies
+    // the kept rows of finished chunks (gather on a second stream + strided D2H) - only the last chunk's copy is exposed.
+    {
+      const bool want_out = !(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0 && !(run->flags & FMCMC_RUN_COLMAJOR) &&
+                            (ans_out || draws_out || logpost_out);
+      const size_t row_bytes = (size_t)C * k * 8 * ((ans_out ? 1 : 0) + ((draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) ? 1 : 0)) +
+                               (logpost_out ? (size_t)C * 8 : 0);
+      if (want_out && row_bytes * (size_t)keep >= ((size_t)8 << 20)) {
+        stream_chunk = (long long)std::max<size_t>(1, ((size_t)4 << 20) / std::max<size_t>(row_bytes, 1));
+        stream_nchunks = (keep + stream_chunk - 1) / stream_chunk;
+        if (stream_nchunks < 2) stream_chunk = stream_nchunks = 0;
+      }
+      if (stream_nchunks) {
+        if (ans_out) CU_CHECK(ensure(m->out_ans, (size_t)C * keep * k * 8));
+        if (draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) CU_CHECK(ensure(m->out_draws, (size_t)C * keep * k * 8));
+        if (logpost_out) CU_CHECK(ensure(m->out_lp, (size_t)C * keep * 8));
+        while ((long long)m->chunk_ev.size() < stream_nchunks) {
+          cudaEvent_t cev;
+          CU_CHECK(cudaEventCreateWithFlags(&cev, cudaEventDisableTiming));
+          m->chunk_ev.push_back(cev);
+        }
+      }
+    }
+    long long next_chunk = 0;
     for (long long row = 1; row <= T + 1; row++) {
       { cudaError_t he = head_launch(row); if (he != cudaSuccess) { set_err(err, errlen, "CUDA error %s (tiled_head)", cudaGetErrorString(he)); return FMCMC_ECUDA; } }
       launches += 1;
+      if (next_chunk < stream_nchunks) {  // head(row) finalises source row row - 2 (0-based): is chunk `next_chunk` complete?
+        const long long r1 = std::min<long long>(keep, (next_chunk + 1) * stream_chunk);
+        const long long last_src = run->burnin + r1 * run->thin - 1;
+        if (row - 2 >= last_src) { cudaEventRecord(m->chunk_ev[next_chunk], m->stream); next_chunk++; }
+      }
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
         const bool timed = hot_timed < FM_HOT_EVENTS;
         if (sharded) {
@@ -998,6 +1044,34 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     CU_CHECK(cudaGetLastError());
   }
   CU_CHECK(cudaEventRecord(m->ev1, m->stream));
+
+  if (stream_nchunks) {  // overlap: chunk q leaves while the rows after it are still being computed
+    const int gb = m->sm_count;
+    const bool want_draws = draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS);
+    for (long long q = 0; q < stream_nchunks; q++) {
+      const long long r0 = q * stream_chunk, r1 = std::min<long long>(keep, r0 + stream_chunk);
+      CU_CHECK(cudaStreamWaitEvent(m->copy_stream, m->chunk_ev[q], 0));
+      const size_t pitch = (size_t)keep * k * 8, width = (size_t)(r1 - r0) * k * 8, off = (size_t)r0 * k;
+      if (ans_out) {
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin);
+        CU_CHECK(cudaMemcpy2DAsync(ans_out + off, pitch, m->out_ans.as<double>() + off, pitch, width, C, cudaMemcpyDeviceToHost, m->copy_stream));
+        launches += 1;
+      }
+      if (want_draws) {
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin);
+        CU_CHECK(cudaMemcpy2DAsync(draws_out + off, pitch, m->out_draws.as<double>() + off, pitch, width, C, cudaMemcpyDeviceToHost, m->copy_stream));
+        launches += 1;
+      }
+      if (logpost_out) {
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, r0, r1, run->burnin, run->thin);
+        CU_CHECK(cudaMemcpy2DAsync(logpost_out + r0, (size_t)keep * 8, m->out_lp.as<double>() + r0, (size_t)keep * 8, (size_t)(r1 - r0) * 8, C,
+                                   cudaMemcpyDeviceToHost, m->copy_stream));
+        launches += 1;
+      }
+      CU_CHECK(cudaStreamSynchronize(m->copy_stream));
+    }
+    d2h += (long long)C * keep * k * 8 * ((ans_out ? 1 : 0) + (want_draws ? 1 : 0)) + (logpost_out ? (long long)C * keep * 8 : 0);
+  }
 
   // ---- error check, outputs -----------------------------------------------------------------
   int herr[4] = {0, 0, 0, 0};
@@ -1063,7 +1137,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     }
     m->store_rows += keep;
   }
-  if (!(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0) {
+  if (!(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0 && !stream_nchunks) {
     const int colmajor = (run->flags & FMCMC_RUN_COLMAJOR) ? 1 : 0;
     if (ans_out) {
       CU_CHECK(ensure(m->out_ans, (size_t)C * keep * k * 8));
