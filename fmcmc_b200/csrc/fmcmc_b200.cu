@@ -954,8 +954,11 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const dim3 lgrid = path >= 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
-    const size_t mat_bytes = adaptive ? (size_t)4 * kf * kf * 8 : 0;
-    const int mat_doubles = (mat_bytes && mat_bytes <= (size_t)40 * 1024) ? 4 * kf * kf : 0;
+    // kernel_adapt factorises in 2 kf^2 doubles of shared memory (A, L), kernel_ram needs 4 kf^2: at k = 32 that is 16 KB per
+    // warp instead of 32, so three CTAs instead of one share an SM and 1 024 chains are one wave of the head kernel, not two
+    const int mat_mats = ks->type == FMCMC_KERNEL_ADAPT ? 2 : 4;
+    const size_t mat_bytes = adaptive ? (size_t)mat_mats * kf * kf * 8 : 0;
+    const int mat_doubles = (mat_bytes && mat_bytes <= (size_t)40 * 1024) ? mat_mats * kf * kf : 0;
     const size_t hsmem = (size_t)TL_HEAD_WARPS * (4 * k + mat_doubles) * 8;
     const int kclass = kernel_class(ks->type);
     auto head_launch = [&](long long row) -> cudaError_t {
