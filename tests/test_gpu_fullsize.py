@@ -177,3 +177,46 @@ def test_cfg5_gaussian_full_size_properties():
     fb = _first_rows(b, spec, init, C)["logpost"][:, 0]
     b.close()
     assert _rel(fa + fb, f) <= RTOL
+
+
+def test_cfg3_full_n_against_the_oracle(oracle, cfg3_data):
+    """BASELINE configs[2] at its full n = 1e6, p = 32 against the CPU oracle itself (not only device paths against each
+    other): 160 chains (more than one 128-chain block, so the default split-integer tcgen05 path runs, 6 slices) x 5 fed-stream
+    rows - every decision identical, log-posteriors and samples within 1e-12.  800 oracle chain-steps over 1e6 observations:
+    seconds on the host threads."""
+    import fmcmc_b200 as fm
+    from gpu_util import assert_parity, run_both
+    X, y = cfg3_data
+    p = X.shape[1]
+    C, T = 160, 5
+    rng = np.random.default_rng(17)
+    init = rng.normal(0, 0.1, (C, p))
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.004)
+    g, o, _ = run_both(oracle, fm.ll_logistic(X, y), spec, init, T, C, rng=rng)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, "cfg3 full n")
+    acc = np.any(g[0]["ans"][:, 1:] != g[0]["ans"][:, :-1], axis=2)
+    assert 0.02 < acc.mean() < 0.98                 # the comparison saw both accepted and rejected proposals
+
+
+def test_cfg5_shape_against_the_oracle(oracle):
+    """BASELINE configs[4]'s geometry (Gaussian, 127 columns + sd: four K blocks, Theta slices split between tensor and
+    shared memory, 6 slices) at n = 300 000 against the CPU oracle: decisions identical, samples and log-posteriors 1e-12."""
+    import fmcmc_b200 as fm
+    from gpu_util import assert_parity, run_both
+    rng = np.random.default_rng(23)
+    n, p, C, T = 300_000, 127, 160, 4
+    X = np.empty((n, p), order="F")
+    X[:, 0] = 1.0
+    for j in range(1, p):
+        X[:, j] = rng.standard_normal(n)
+    beta = rng.standard_normal(p)
+    y = X @ beta + 2.0 * rng.standard_normal(n)
+    fam = fm.ll_gaussian_lm(X, y, intercept=False, guard=True)
+    k = p + 1
+    lb = np.full(k, -A.DBL_MAX); lb[-1] = 0.0
+    spec = dict(type=A.KERNEL_NORMAL_REFLECTIVE, k=k, mu=0.0, scale=2e-4, lb=lb, ub=A.DBL_MAX)
+    init = np.c_[beta + rng.normal(0, 1e-3, (C, p)), rng.uniform(1.5, 2.5, C)]
+    g, o, _ = run_both(oracle, fam, spec, init, T, C, rng=rng)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, "cfg5 shape")
