@@ -268,3 +268,18 @@ def test_logpost_matches_oracle(oracle, readme_data):
     f = np.isfinite(ref)
     np.testing.assert_allclose(got[f], ref[f], rtol=1e-13)
     assert np.array_equal(got[~f], ref[~f])
+
+
+@pytest.mark.parametrize("burnin,thin", [(0, 1), (37, 3)])
+def test_streamed_outputs_match_oracle(oracle, burnin, thin):
+    """Outputs above 8 MB leave the device chunk by chunk while later rows are still being computed (fmcmc_run, tiled
+    paths): same rows, same order, burnin / thin included (R/mcmc.R:786-813), checked against the oracle."""
+    rng = np.random.default_rng(71)
+    n, p, C, T = 2500, 8, 600, 400
+    fam = _logistic_family(rng, n, p)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.05)
+    g, o, _ = run_both(oracle, fam, spec, rng.normal(0, 0.1, (C, p)), T, C, rng=rng, burnin=burnin, thin=thin)
+    keep = (T - burnin) // thin
+    assert g[0]["report"].path in (2, 3, 4) and g[0]["ans"].shape == (C, keep, p)
+    assert g[0]["ans"].nbytes * 2 >= 8 << 20                     # large enough to take the streamed path
+    assert_parity(g[0], o[0], RTOL, f"streamed outputs burnin={burnin} thin={thin}")
