@@ -312,6 +312,11 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries exactly ONE JSON line: anything a library writes to file descriptor 1 meanwhile (NCCL prints its version
+    # banner there) is sent to stderr; the descriptor is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -327,7 +332,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: fmcmc_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries ONE JSON line, not NCCL's version banner
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -568,7 +572,10 @@ def main():
                                     "sample": f"{chains_s} chains x {rows_s - 1} MH steps over the full n={n}, "
                                               f"{sec:.1f} s wall on {threads} host threads (C restatement of the "
                                               "reference loop; R is not installed)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     model.close()
     if world > 1:
         dist.destroy_process_group()
