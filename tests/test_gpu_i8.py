@@ -182,3 +182,24 @@ def test_i8_large_linear_predictors(oracle):
     g, o, _ = run_both(oracle, fam, spec, init, 25, C, rng=rng, path=4)
     assert g[0]["report"].path == 4
     assert_parity(g[0], o[0], RTOL)
+
+
+@pytest.mark.parametrize("family", ["logistic", "gaussian"])
+def test_i8_tiny_problem(oracle, family):
+    """Forced path 4 far below its intended regime: fewer observations than one 128-row tile, one covariate (31 of the 32
+    K columns are padding), 3 chains in a 128-lane block."""
+    rng = np.random.default_rng(5)
+    n, p, C = 50, 1, 3
+    if family == "logistic":
+        from fmcmc_b200 import ll_logistic
+        X = rng.standard_normal((n, p))
+        y = (rng.random(n) < 1 / (1 + np.exp(-1.5 * X[:, 0]))).astype(np.float64)
+        fam, k = ll_logistic(X, y, prior_sd=2.0), p
+        init = rng.normal(0, 0.3, (C, k))
+    else:
+        fam, k = _gaussian_family(rng, n, p)
+        init = np.c_[rng.normal(0, 0.3, (C, k - 1)), np.full(C, 2.0)]
+    spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.2)
+    g, o, _ = run_both(oracle, fam, spec, init, 200, C, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, family)
