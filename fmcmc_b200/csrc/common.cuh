@@ -51,9 +51,10 @@ struct ModelParams {
   const unsigned char* Xq;  // tile-major int8 slices of X (+ y) for the tcgen05 kernel (tiled_i8.cuh), or null
   const int* i8_cexp;       // [p_x] column exponents of the slicing
   const double* i8_sxy;     // [p_x] sum_i (y_i - 1/2) x_ij (binary logistic)
+  const double* i8_cmax;    // [p_x] max_i |x_ij|, then [1] max_i sum_j x_ij^2 (bounds on |eta| for the un-clamped epilogue)
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
   const double* sp_tab4; // logistic: the 128-per-unit table of the split-integer kernel (softplus.h, FM_SP4_*)
-  const double* sp_tab8; // logistic: its 256-per-unit table (FM_SP8_*)
+  const double* sp_tab8; // logistic: its 256-per-unit table: (tau, T) of log(2 cosh(a / 2)) (softplus.h, fm_lcosh_table8_fill)
 };
 
 // Per-run device buffers shared by both paths.

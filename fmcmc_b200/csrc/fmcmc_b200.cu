@@ -238,7 +238,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
     MC(cudaMemcpy(m->sp_tab4.p, tab4.data(), tab4.size() * 8, cudaMemcpyHostToDevice));
     mp.sp_tab4 = m->sp_tab4.as<double>();
     std::vector<double> tab8(2 * (size_t)FM_SP8_ENTRIES);
-    fm_softplus_table8_fill(tab8.data());
+    fm_lcosh_table8_fill(tab8.data());
     MC(ensure(m->sp_tab8, tab8.size() * 8));
     MC(cudaMemcpy(m->sp_tab8.p, tab8.data(), tab8.size() * 8, cudaMemcpyHostToDevice));
     mp.sp_tab8 = m->sp_tab8.as<double>();
@@ -616,21 +616,23 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   if (e != cudaSuccess) return e;
   e = ensure(m->xq_bad, sizeof(int));
   if (e != cudaSuccess) return e;
-  // aux: [p_x] column maxima (u64 bit patterns) | [p_x] sxy (f64) | [p_x] column exponents (i32)
+  // aux: [p_x] column maxima + [1] largest squared row norm (u64 bit patterns of non-negative doubles) | [p_x] sxy (f64) |
+  // [p_x] column exponents (i32)
   const size_t px = (size_t)mp.p_x;
-  e = ensure(m->xq_aux, px * 8 + px * 8 + px * 4);
+  e = ensure(m->xq_aux, (px + 1) * 8 + px * 8 + px * 4);
   if (e != cudaSuccess) return e;
   unsigned long long* colmax = m->xq_aux.as<unsigned long long>();
-  double* sxy = reinterpret_cast<double*>(colmax + px);
+  double* sxy = reinterpret_cast<double*>(colmax + px + 1);
   int* cexp = reinterpret_cast<int*>(sxy + px);
   e = cudaMemsetAsync(m->xq_bad.p, 0, sizeof(int), m->stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(m->xq_aux.p, 0, px * 20, m->stream);
+  e = cudaMemsetAsync(m->xq_aux.p, 0, px * 20 + 8, m->stream);
   if (e != cudaSuccess) return e;
   unsigned char* xq = m->Xq.as<unsigned char>();
   const unsigned ychunks = (unsigned)std::min<long long>(64, (mp.n + 255) / 256);
   i8_colmax_kernel<<<dim3((unsigned)mp.p_x, ychunks), 256, 0, m->stream>>>(mp.X, mp.n, mp.ld, colmax, m->xq_bad.as<int>());
   i8_colexp_kernel<<<(mp.p_x + 127) / 128, 128, 0, m->stream>>>(colmax, mp.p_x, cexp);
+  i8_rownorm_kernel<<<(unsigned)std::min<long long>(4096, (mp.n + 255) / 256), 256, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, colmax + px);
   i8_sxy_kernel<<<(unsigned)mp.p_x, 1024, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, sxy);
 #define I8_CASE(N, K) if (NS == N && KB == K) pack_i8_kernel<N, K><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);
   I8_FOR_SHAPES(I8_CASE)
@@ -645,6 +647,7 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   if (bad) { m->xq_NS = -1; release(m->Xq); return cudaErrorNotSupported; }
   m->mp.i8_cexp = cexp;
   m->mp.i8_sxy = sxy;
+  m->mp.i8_cmax = reinterpret_cast<const double*>(colmax);
   m->mp.Xq = xq;
   m->xq_NS = NS;
   m->xq_KB = KB;

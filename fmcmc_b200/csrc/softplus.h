@@ -256,3 +256,40 @@ FM_HD double fm_softplus_tab8(double a, const double* tab) {
   const double d = fma(t - MAGIC, -1.0 / FM_SP8_H, a);
   return fm_softplus_tab8_core(d, tab[2 * k], tab[2 * k + 1]);
 }
+
+// ---- log(2 cosh(a / 2)) = a / 2 + log(1 + exp(-a)) on the same 256-per-unit grid (the binary-logistic epilogue of
+// tiled_i8.cuh accumulates exactly this even function of eta: tiled_i8.cuh, i8_logistic_lcosh).  h is analytic and all
+// its derivatives are polynomials in tau = h' = tanh(a/2) / 2:  with u = 1/4 - tau^2
+//   h'' = u,  h''' = -2 tau u,  h'''' = u (1/2 - 6 u) ... so the degree-4 Taylor expansion around the table point needs
+// only (tau_k, T_k = h(k/256)) from the table, 16 B per entry as before:
+//   h(k/256 + d) = T + d (tau + d u (1/2 + d (-tau/3 + d (1/24 - u/4)))),  remainder <= 0.13 d^5 / 120 = 3e-17 (|d| <= 1/512)
+// 9 FP64 instructions including the accumulation (against 11 for G + log1p(S expm1(-d)) plus one for sum |eta| / 2).
+// The last entry (a = 40) has tau = 1/2 exactly in double, hence u = 0 and h = T + d / 2 there.  Arguments beyond the table
+// are the caller's business: the kernel either proves |eta| <= 39.9 for all its chains (no clamp at all) or clamps the
+// argument and adds the excess |eta| / 2 apart (tiled_i8.cuh).
+static inline void fm_lcosh_table8_fill(double* tab) {
+  for (int k = 0; k < FM_SP8_ENTRIES; k++) {
+    const long double x = (long double)k / FM_SP8_H;
+    const long double E = expl(-x);
+    tab[2 * k] = (double)(0.5L - E / (1.0L + E));          // tau = 1/2 - sigma(-x)
+    tab[2 * k + 1] = (double)(0.5L * x + log1pl(E));       // T
+  }
+}
+FM_HD double fm_lcosh_tab8_core(double d, double tau, double T) {
+  const double u = fma(-tau, tau, 0.25);
+  const double i1 = fma(u, -0.25, 1.0 / 24.0);
+  const double i2 = fma(d, i1, tau * (-1.0 / 3.0));
+  const double i3 = fma(d, i2, 0.5);
+  const double P = u * i3;
+  const double Q = fma(d, P, tau);
+  return fma(d, Q, T);
+}
+// reference composition (host tests): 0 <= a <= 40
+FM_HD double fm_lcosh_tab8(double a, const double* tab) {
+  const double MAGICH = 26388279066624.0;  // 1.5 * 2^44: ulp = 1/256
+  const double t2 = a + MAGICH;
+  uint32_t k = (uint32_t)fm_double_to_bits(t2);
+  k = k > (uint32_t)(FM_SP8_ENTRIES - 1) ? (uint32_t)(FM_SP8_ENTRIES - 1) : k;
+  const double d = a + (MAGICH - t2);
+  return fm_lcosh_tab8_core(d, tab[2 * k], tab[2 * k + 1]);
+}

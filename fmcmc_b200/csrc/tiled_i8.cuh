@@ -142,6 +142,23 @@ __global__ void i8_colexp_kernel(const unsigned long long* __restrict__ colmax_b
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < p_x) cexp[j] = i8_exponent(__longlong_as_double((long long)colmax_bits[j]));
 }
+// largest squared row norm max_i sum_j x_ij^2 (bit pattern of a non-negative double, like colmax): with Cauchy-Schwarz the
+// second bound on |eta| of the un-clamped logistic epilogue
+__global__ void __launch_bounds__(256) i8_rownorm_kernel(const double* __restrict__ X, long long n, long long ld, int p_x,
+                                                        unsigned long long* __restrict__ rmax2_bits) {
+  double m = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int j = 0; j < p_x; j++) {
+      const double x = X[(size_t)j * ld + i];
+      s = fma(x, x, s);
+    }
+    m = fmax(m, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FM_FULL, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(rmax2_bits, (unsigned long long)__double_as_longlong(m));
+}
+
 // sxy[j] = sum_i (y_i - 1/2) x_ij, fixed-order reduction (one CTA per column): the linear part of the binary
 // logistic log-likelihood, sum_i [y_i eta_i - eta_i / 2] = theta . sxy, leaves the per-evaluation epilogue
 __global__ void __launch_bounds__(1024) i8_sxy_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n,
@@ -363,6 +380,42 @@ __device__ __forceinline__ void i8_logistic_even_t(double t, double csc, int hi_
   acc_abs_t += fabs(t);
   acc_g = fma(v, L, acc_g + sg.y);
 }
+// Level-2 table (softplus.h: fm_lcosh_table8_fill): entry k = (tau_k, T_k) of h(a) = log(2 cosh(a / 2)) = a / 2 + log1p(exp(-a)),
+// the even function the binary-logistic epilogue sums.  h(k/256 + d) = T + d (tau + d u (1/2 + d (-tau/3 + d (1/24 - u/4)))),
+// u = 1/4 - tau^2 (degree-4 Taylor; every derivative of h is a polynomial in tau): 9 FP64 instructions including the
+// accumulation, 12 with the range reduction, and no separate sum of |eta|.
+__device__ __forceinline__ double i8_lcosh_core(double d, double tau, double Tacc) {
+  const double u = fma(-tau, tau, 0.25);
+  const double i1 = fma(u, -0.25, 1.0 / 24.0);
+  const double i2 = fma(d, i1, tau * (-1.0 / 3.0));
+  const double i3 = fma(d, i2, 0.5);
+  const double P = u * i3;
+  const double Q = fma(d, P, tau);
+  return fma(d, Q, Tacc);
+}
+// FAST: the warp's chains bound |eta| <= 39.9 over ALL observations (i8 prologue: min(sum_j |theta_j| max_i |x_ij|,
+// |theta|_2 max_i |x_i|_2)), so round(256 |eta|) indexes the table as it is - no clamp of any kind: 12 FP64 + 7 (merge) +
+// address + LDS.128 per evaluation.
+__device__ __forceinline__ void i8_logistic_lcosh_fast(double t, double csc, double& acc_h, const double2* __restrict__ tab) {
+  constexpr double MAGICH = i8_magic_h<2>();
+  const double t2 = fma(fabs(t), csc, MAGICH);
+  const double d = fma(fabs(t), csc, MAGICH - t2);
+  const double2 tt = tab[__double2loint(t2)];
+  acc_h = i8_lcosh_core(d, tt.x, acc_h + tt.y);
+}
+// SAFE: arbitrary magnitudes.  |t| is clamped on its high word (AMAX / csc = hi_clamp), sum |t| is accumulated apart and
+// g = h(a_c) - a_c / 2 = log1p(exp(-a_c)) enters the second accumulator: sum h = (csc / 2) sum |t| + sum g.
+__device__ __forceinline__ void i8_logistic_lcosh_safe(double t, double csc, int hi_clamp, double& acc_abs_t, double& acc_g,
+                                                       const double2* __restrict__ tab) {
+  constexpr double MAGICH = i8_magic_h<2>();
+  const double tc = __hiloint2double(min(__double2hiint(t) & 0x7fffffff, hi_clamp), __double2loint(t));
+  const double t2 = fma(tc, csc, MAGICH);
+  const double d = fma(tc, csc, MAGICH - t2);
+  const double2 tt = tab[__double2loint(t2)];
+  const double h = i8_lcosh_core(d, tt.x, tt.y);
+  acc_abs_t += fabs(t);
+  acc_g += fma(tc, -0.5 * csc, h);
+}
 // general response (sum(logp[y == 1]) + sum(logq[y == 0]), anything else contributes nothing), NaN propagated like
 // logistic_term_tab (families.cuh)
 template <int TL>
@@ -373,11 +426,24 @@ __device__ __forceinline__ double i8_logistic_term(double eta, double y, const d
   const double t2 = a + MAGICH;
   const double d = a + (MAGICH - t2);
   const double2 sg = tab[__double2loint(t2)];
-  double v, L;
-  i8_softplus_core<TL>(d, sg.x, v, L);
+  double g;
+  if (TL == 2) {
+    g = fma(-0.5, a, i8_lcosh_core(d, sg.x, sg.y));  // log1p(exp(-a)) = h(a) - a / 2
+  } else {
+    double v, L;
+    i8_softplus_core<TL>(d, sg.x, v, L);
+    g = fma(v, L, sg.y);
+  }
   const double z = (y == 1.0) ? eta : -eta;
-  const double r = fm_min0(z) - fma(v, L, sg.y);
+  const double r = fm_min0(z) - g;
   return (y == 1.0 || y == 0.0) ? r : 0.0;
+}
+
+template <int TL>
+__device__ __forceinline__ void i8_logistic_safe(double t, double csc, int hi_clamp, double& acc_abs_t, double& acc_g,
+                                                 const double2* __restrict__ tab) {
+  if (TL == 2) i8_logistic_lcosh_safe(t, csc, hi_clamp, acc_abs_t, acc_g, tab);
+  else i8_logistic_even_t<1, true>(t, csc, hi_clamp, acc_abs_t, acc_g, tab);
 }
 
 template <int FAMILY, bool YBIN, int NS, int KB, int EW, int CH>
@@ -443,7 +509,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const int col = chain_block * I8_CHAINS + lchain;
   const double* th = nullptr;
   if (warp < EW && col < tb.ncols) th = col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
-  double thmax = 0.0, b0 = 0.0, lin = 0.0;
+  double thmax = 0.0, b0 = 0.0, lin = 0.0, eb1 = 0.0, eb2 = 0.0;
   bool th_nan = false, th_big = false;
   if (th) {
     for (int j = 0; j < p_x; j++) {
@@ -452,6 +518,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       if (a != a) th_nan = true;
       else if (!(a < 0x1p480)) th_big = true;
       thmax = fmax(thmax, a);
+      eb1 = fma(fabs(v), mp.i8_cmax[j], eb1);  // |eta_i| <= sum_j |theta_j| max_i |x_ij|
+      eb2 = fma(v, v, eb2);                    // |eta_i| <= |theta|_2 max_i |x_i|_2
       if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) lin = fma(v, mp.i8_sxy[j], lin);
     }
     if (icpt) b0 = th[0];
@@ -463,6 +531,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const int hi_clamp = (0x40440000) + ((G::SHIFT - eth) << 20);
   // |eta| <= 32 KB max|theta'| < 2^(5 + log2 KB + eth): below 2^25 for every chain of the warp, the unclamped epilogue applies
   const bool eta_small = __all_sync(FM_FULL, eth + 5 + (KB == 1 ? 0 : (KB == 2 ? 1 : 2)) <= 25);
+  // level-2 table: |eta| <= 39.9 for every observation and every chain of the warp (idle lanes: 0; NaN fails the test) -
+  // the un-clamped lcosh epilogue applies (the slicing error of eta, <= 2^-35 thmax, is far inside the 0.1 margin)
+  const bool eta_in_table = __all_sync(FM_FULL, !th_bad && fmin(eb1, sqrt(eb2 * mp.i8_cmax[p_x])) <= 39.9);
   if (tid < I8_CHAINS) {
     for (int kb = 0; kb < KB; kb++) {
       uint32_t w[NS][8];
@@ -594,10 +665,14 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             for (int e = 0; e < CH; e++) acc += (double)(int)(a[0][e] ^ a[NS - 1][e]);
           } else
 #endif
-          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && eta_small && obs0 + CH <= valid) {  // the hot loop of cfg3
+          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && eta_in_table && obs0 + CH <= valid) {
+#pragma unroll
+            for (int e = 0; e < CH; e++)  // the hot loop of cfg3
+              i8_logistic_lcosh_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+          } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 1 && eta_small && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)
-              i8_logistic_even_t<i8_table_level<NS, KB>(), false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+              i8_logistic_even_t<1, false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
           } else if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
@@ -606,7 +681,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
               } else if (YBIN) {
-                i8_logistic_even_t<i8_table_level<NS, KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                i8_logistic_safe<i8_table_level<NS, KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab);
               } else {
                 acc += i8_logistic_term<i8_table_level<NS, KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
               }
@@ -620,7 +695,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);
                 } else if (YBIN) {
-                  i8_logistic_even_t<i8_table_level<NS, KB>(), true>(t, csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+                  i8_logistic_safe<i8_table_level<NS, KB>()>(t, csc, hi_clamp, acc, acc2, sp_tab);
                 } else {
                   acc += i8_logistic_term<i8_table_level<NS, KB>()>(t * csc, __ldg(ymeta + obs0 + e), sp_tab);
                 }
