@@ -256,6 +256,38 @@ __device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&v)[CH]) {
                  : "r"(taddr)
                  : "memory");
 }
+// all NS accumulators of 8 columns (diagonal d sits 32 d columns further right) in ONE asm statement: the address reaches
+// the uniform datapath once (one R2UR) and the NS loads carry immediate offsets, instead of one R2UR per load
+template <int NS, int CH>
+__device__ __forceinline__ void tc_ld_diagonals(uint32_t taddr, uint32_t (&a)[NS][CH]) {
+  if constexpr (CH == 8 && NS == 6) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%48];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%48+32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%48+64];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%48+96];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%32,%33,%34,%35,%36,%37,%38,%39}, [%48+128];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%40,%41,%42,%43,%44,%45,%46,%47}, [%48+160];\n"
+        : "=r"(a[0][0]), "=r"(a[0][1]), "=r"(a[0][2]), "=r"(a[0][3]), "=r"(a[0][4]), "=r"(a[0][5]), "=r"(a[0][6]), "=r"(a[0][7]), "=r"(a[1][0]), "=r"(a[1][1]), "=r"(a[1][2]), "=r"(a[1][3]), "=r"(a[1][4]), "=r"(a[1][5]), "=r"(a[1][6]), "=r"(a[1][7]), "=r"(a[2][0]), "=r"(a[2][1]), "=r"(a[2][2]), "=r"(a[2][3]), "=r"(a[2][4]), "=r"(a[2][5]), "=r"(a[2][6]), "=r"(a[2][7]), "=r"(a[3][0]), "=r"(a[3][1]), "=r"(a[3][2]), "=r"(a[3][3]), "=r"(a[3][4]), "=r"(a[3][5]), "=r"(a[3][6]), "=r"(a[3][7]), "=r"(a[4][0]), "=r"(a[4][1]), "=r"(a[4][2]), "=r"(a[4][3]), "=r"(a[4][4]), "=r"(a[4][5]), "=r"(a[4][6]), "=r"(a[4][7]), "=r"(a[5][0]), "=r"(a[5][1]), "=r"(a[5][2]), "=r"(a[5][3]), "=r"(a[5][4]), "=r"(a[5][5]), "=r"(a[5][6]), "=r"(a[5][7])
+        : "r"(taddr)
+        : "memory");
+  } else if constexpr (CH == 8 && NS == 7) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%56];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%56+32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%56+64];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%24,%25,%26,%27,%28,%29,%30,%31}, [%56+96];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%32,%33,%34,%35,%36,%37,%38,%39}, [%56+128];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%40,%41,%42,%43,%44,%45,%46,%47}, [%56+160];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%48,%49,%50,%51,%52,%53,%54,%55}, [%56+192];\n"
+        : "=r"(a[0][0]), "=r"(a[0][1]), "=r"(a[0][2]), "=r"(a[0][3]), "=r"(a[0][4]), "=r"(a[0][5]), "=r"(a[0][6]), "=r"(a[0][7]), "=r"(a[1][0]), "=r"(a[1][1]), "=r"(a[1][2]), "=r"(a[1][3]), "=r"(a[1][4]), "=r"(a[1][5]), "=r"(a[1][6]), "=r"(a[1][7]), "=r"(a[2][0]), "=r"(a[2][1]), "=r"(a[2][2]), "=r"(a[2][3]), "=r"(a[2][4]), "=r"(a[2][5]), "=r"(a[2][6]), "=r"(a[2][7]), "=r"(a[3][0]), "=r"(a[3][1]), "=r"(a[3][2]), "=r"(a[3][3]), "=r"(a[3][4]), "=r"(a[3][5]), "=r"(a[3][6]), "=r"(a[3][7]), "=r"(a[4][0]), "=r"(a[4][1]), "=r"(a[4][2]), "=r"(a[4][3]), "=r"(a[4][4]), "=r"(a[4][5]), "=r"(a[4][6]), "=r"(a[4][7]), "=r"(a[5][0]), "=r"(a[5][1]), "=r"(a[5][2]), "=r"(a[5][3]), "=r"(a[5][4]), "=r"(a[5][5]), "=r"(a[5][6]), "=r"(a[5][7]), "=r"(a[6][0]), "=r"(a[6][1]), "=r"(a[6][2]), "=r"(a[6][3]), "=r"(a[6][4]), "=r"(a[6][5]), "=r"(a[6][6]), "=r"(a[6][7])
+        : "r"(taddr)
+        : "memory");
+  } else {
+#pragma unroll
+    for (int d = 0; d < NS; d++) tc_ld<CH>(taddr + d * 32, a[d]);
+  }
+}
 // wait for this thread's tcgen05.ld's; the registers are threaded through so no use can be scheduled above it
 template <int NS, int CH>
 __device__ __forceinline__ void tc_wait_ld(uint32_t (&a)[NS][CH]) {
@@ -471,6 +503,10 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                                           (size_t)i8_table_bytes<NS, KB>(FAMILY));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W_TMA = EW, W_MMA = EW + 1;
+  // the warp index through redux.sync (CREDUX writes a uniform register): ptxas then KNOWS that the role branches below are
+  // warp-uniform and keeps warp-uniform values - the TMEM addresses of the epilogue's tcgen05.ld's above all - in uniform
+  // registers (otherwise: one R2UR per load; a shuffle broadcast does not convince it)
+  const int warp_u = (int)__reduce_min_sync(FM_FULL, (unsigned)warp);
   if (err[0] != 0) return;
   const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
   const long long ntiles = (mp.n + G::TO - 1) / G::TO;
@@ -568,7 +604,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   __syncthreads();
   tc_fence_after();
 
-  if (warp == W_TMA) {
+  if (warp_u == W_TMA) {
     // ===== producer: one bulk copy per stage (whole warp in the loop, one elected lane issues) =====
     long long it = 0;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
@@ -581,7 +617,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       }
       __syncwarp();
     }
-  } else if (warp == W_MMA) {
+  } else if (warp_u == W_MMA) {
     // ===== MMA issuer: NS * KB instructions per block of 32 observations (N = 32 (NS - j)); whole warp in the
     // loop, one elected lane issues =====
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, K-major, N >> 3, M >> 4
@@ -622,8 +658,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     }
   } else {
     // ===== epilogue: thread = chain (TMEM lane); the EW / 4 warps of a lane quarter split the 32 columns =====
-    const int q = warp & 3, h = warp >> 2;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int q = warp_u & 3, h = warp_u >> 2;
+    const uint32_t lane_base = ((uint32_t)(q * 32) << 16) + __reduce_min_sync(FM_FULL, tmem);
     if (FAMILY == FMCMC_FAMILY_LOGISTIC) mbar_wait(tab_bar, 0u);  // the softplus table has landed
     double acc = 0.0, acc2 = 0.0;
     uint32_t blk = 0;
@@ -631,10 +667,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     for (long long tile = first; tile < ntiles; tile += step, it++) {
       const double* ymeta = mp.y + tile * G::TO;  // L1-resident broadcast loads (Gaussian / non-binary logistic only)
       const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
+      // two blocks per trip when a stage holds an even number: the accumulator set (hence the barrier and the TMEM
+      // address) is then known at compile time and the phase bit is shared by the pair
+      constexpr int UNR = (G::NBLK % 2 == 0) ? 2 : 1;
 #pragma unroll 1
-      for (int b = 0; b < G::NBLK; b++, blk++) {
-        const uint32_t buf = blk & 1u;
-        mbar_wait(&acc_full[buf], (blk >> 1) & 1u);
+      for (int bpair = 0; bpair < G::NBLK; bpair += UNR) {
+      const uint32_t par = (blk >> 1) & 1u;
+#pragma unroll
+      for (int bb = 0; bb < UNR; bb++, blk++) {
+        const int b = bpair + bb;
+        const uint32_t buf = UNR == 2 ? (uint32_t)bb : (blk & 1u);
+        mbar_wait(&acc_full[buf], par);
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < CW / CH; cc++) {
@@ -649,8 +692,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           } else
 #endif
           {
-#pragma unroll
-            for (int d = 0; d < NS; d++) tc_ld<CH>(tmem + buf * G::ACC_COLS + d * G::BLK + col0 + lane_base, a[d]);
+            static_assert(G::BLK == 32, "tc_ld_diagonals: 32 columns between diagonals");
+            tc_ld_diagonals<NS, CH>(buf * G::ACC_COLS + col0 + lane_base, a);
           }
           tc_wait_ld<NS, CH>(a);
           if (cc == CW / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
@@ -703,6 +746,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             }
           }
         }
+      }
       }
     }
     // binary logistic: acc holds sum |t|; sum(|eta| / 2 + g) = (csc / 2) sum |t| + sum g
