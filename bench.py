@@ -494,7 +494,7 @@ def main():
         achieved_tf = flops / (hot_ms * 1e-3) / 1e12
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
-        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (14 if wl.family == "logistic" else 3)
+        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (12 if wl.family == "logistic" else 3)
         pipe_util = evals * fp64_instr / 32.0 / (hot_ms * 1e-3) / pipe_slots
         kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 4: "tiled_loglik_i8_kernel", 1: "mh_resident_kernel"}[path]
         line = {
@@ -560,6 +560,16 @@ def main():
                 "fp64_slots_per_eval": fp64_instr, "fp64_floor_ms": 1e3 * t_fp64, "floor_ms": 1e3 * (t_tensor + t_fp64),
                 "frac": (t_tensor + t_fp64) / (hot_ms * 1e-3),
                 "note": "floor = int8 MACs / measured int8 peak + FP64 epilogue slots / FP64 pipe rate (time-additive on B200)"}
+            if wl.family == "logistic":
+                # every instruction of the epilogue runs on a 16-lane datapath (FP64, IMAD / IMAD.WIDE, SHF, I2F, LDS): the
+                # scheduler issues one warp instruction per 2 clk whatever the pipe (ncu: issue-active 47 % of cycles with
+                # not-selected warps waiting), so the instruction count, not the FP64 count alone, is what bounds the kernel
+                instr = 21                                                      # 12 FP64 + 6 IMAD(.WIDE) + SHF + I2F + LDS.128
+                t_issue = evals * instr / 32.0 * 2.0 / (148 * 4 * sm_clock * 1e6)
+                line["roofline_two_engine"].update({
+                    "instr_per_eval": instr, "issue_floor_ms": 1e3 * (t_tensor + t_issue),
+                    "issue_frac": (t_tensor + t_issue) / (hot_ms * 1e-3),
+                    "issue_note": "tensor time + (warp instructions per eval x 2 clk per instruction per scheduler)"})
         if not args.no_cpu_baseline and world == 1 and host_data is not None:
             X, y = host_data
             threads = os.cpu_count() or 1
