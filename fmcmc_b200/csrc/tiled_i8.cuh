@@ -34,9 +34,12 @@
 // (DFMA drops to 3 % of its rate while UTCIMMAs run), so the kernel's time is tensor time PLUS FP64 time; the
 // double buffer hides latencies only.
 //
-// FP64-pipe slots per evaluation: 17 (binary logistic: 1 scale + 16 table-driven softplus on a 128-per-unit table; the linear term
-// theta . X'(y - 1/2) is a per-chain dot product with a vector computed once per model) against 51 on path 3;
-// Gaussian: 3 against 2 p_x + 2.
+// FP64-pipe slots per evaluation: 12 (binary logistic with the 256-per-unit (tau, T) table of log(2 cosh(eta / 2)): 3 range
+// reduction with the scale folded in + 9 Taylor core and accumulation; 16 with the 128-per-unit softplus table used when the
+// Theta slices need the shared memory; the linear term theta . X'(y - 1/2) is a per-chain dot product with a vector computed
+// once per model) against 51 on path 3; Gaussian: 3 against 2 p_x + 2.
+// Role branches test a warp index that went through redux.sync, so ptxas knows they are warp-uniform and keeps TMEM / barrier
+// addresses in uniform registers (profiles/r01_i8_findings.md, section 7).
 #pragma once
 #include "tiled.cuh"
 
@@ -62,8 +65,9 @@ struct I8Geom {
   static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
 };
 
-// softplus table of the logistic epilogue (softplus.h): level 2 = 256 entries per unit (160 KB, cubic polynomials, 11 FP64
-// instructions) when it leaves room for two pipeline stages, else level 1 = 128 per unit (80 KB, degree 4, 13)
+// table of the logistic epilogue (softplus.h): level 2 = 256 entries per unit (160 KB, (tau, T) of log(2 cosh(a / 2)), one degree-4
+// Taylor core: 9 FP64 instructions) when it leaves room for two pipeline stages, else level 1 = 128 per unit (80 KB, (S, G) of
+// log1p(exp(-a)), two degree-4 polynomials: 13)
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_smem_fixed(int table_bytes) {
   return 256 + I8Geom<NS, KB>::A_SMEM_BYTES + table_bytes + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;

@@ -167,8 +167,9 @@ def test_i8_falls_back_on_unsliceable_design_matrix(oracle):
 
 
 def test_i8_large_linear_predictors(oracle):
-    """|eta| far beyond the softplus table (40): moderate magnitudes take the unclamped epilogue (index clamp only), chains
-    with |theta| >= 2^20 switch their warp to the clamped one; both must reproduce the oracle (terms ~ -|eta| or ~ 0)."""
+    """|eta| far beyond the table of the logistic epilogue (40): no chain passes the |eta| <= 39.9 bound, so every warp takes
+    the argument-clamped variant (sum |t| apart + g = h(a_c) - a_c / 2), whatever the magnitude; it must reproduce the oracle
+    (terms ~ -|eta| or ~ 0)."""
     from fmcmc_b200 import ll_logistic
     rng = np.random.default_rng(21)
     n, p, C = 900, 10, 150
@@ -180,6 +181,31 @@ def test_i8_large_linear_predictors(oracle):
     init[7] *= 1e5                                      # |theta| ~ 3e6 > 2^20: clamped variant for that warp
     init[140] *= 1e9
     g, o, _ = run_both(oracle, fam, spec, init, 25, C, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL)
+
+
+def test_i8_mixed_bounded_and_unbounded_warps(oracle):
+    """The un-clamped log(2 cosh) epilogue is chosen per warp from the chains' bound on |eta| (min of sum_j |theta_j| max_i |x_ij|
+    and |theta|_2 max_i |x_i|_2 <= 39.9): here warps 0 and 2 of the first chain block pass it, warp 1 holds one chain with
+    |eta| ~ 300 and warp 3 chains whose bound sits just above 39.9 although their actual |eta| stays small - all four must
+    reproduce the oracle, and the last partial tile (n is not a multiple of 128) goes through the clamped variant anyway."""
+    from fmcmc_b200 import ll_logistic
+    rng = np.random.default_rng(33)
+    n, p, C = 1100, 12, 140
+    X = rng.standard_normal((n, p)) / np.sqrt(p); X[:, 0] = 1.0
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ rng.standard_normal(p)))).astype(np.float64)
+    fam = ll_logistic(X, y, prior_sd=2.0)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.02)
+    init = rng.normal(0, 0.5, (C, p))
+    init[40] = rng.normal(0, 120.0, p)                  # warp 1: one chain far outside the table
+    rmax = np.sqrt((X * X).sum(axis=1).max())
+    cmax = np.abs(X).max(axis=0)
+    for c in range(96, 128):                            # warp 3: both bounds a little above 39.9
+        v = rng.normal(0, 1.0, p)
+        v *= 1.02 * 39.9 / min(np.abs(v) @ cmax, np.linalg.norm(v) * rmax)
+        init[c] = v
+    g, o, _ = run_both(oracle, fam, spec, init, 30, C, rng=rng, path=4)
     assert g[0]["report"].path == 4
     assert_parity(g[0], o[0], RTOL)
 
