@@ -654,8 +654,11 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   return cudaSuccess;
 }
 
+#ifndef I8_EPI_WARPS
 #define I8_EPI_WARPS 16   // 4 epilogue warps per TMEM lane quarter, 8 observations each per block (B200: 2.37 ms per cfg3
-#define I8_EPI_CHUNK 8    // launch; 8 warps x 2 chunks of 8: 2.78 ms; 16 x 2 chunks of 4: 2.75 ms - profiles/r01_i8_*.txt)
+#define I8_EPI_CHUNK 8    // launch; 8 warps x 2 chunks of 8: 2.78 ms; 16 x 2 chunks of 4: 2.75 ms - profiles/r01_i8_*.txt;
+                          // on the final 1.79 ms kernel: 8 warps 2.01 ms, 8 warps with the chunk loop unrolled 1.92 ms)
+#endif
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_i8(fmcmc_model* m, int NS, int KB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
 #define I8_CASE(N, K)                                                                                             \

@@ -683,7 +683,11 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
         const uint32_t buf = UNR == 2 ? (uint32_t)bb : (blk & 1u);
         mbar_wait(&acc_full[buf], par);
         tc_fence_after();
+#ifdef I8_CC_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int cc = 0; cc < CW / CH; cc++) {
           const int col0 = h * CW + cc * CH;
           uint32_t a[NS][CH];
