@@ -560,6 +560,17 @@ def main():
                 "fp64_slots_per_eval": fp64_instr, "fp64_floor_ms": 1e3 * t_fp64, "floor_ms": 1e3 * (t_tensor + t_fp64),
                 "frac": (t_tensor + t_fp64) / (hot_ms * 1e-3),
                 "note": "floor = int8 MACs / measured int8 peak + FP64 epilogue slots / FP64 pipe rate (time-additive on B200)"}
+            if wl.bound != "hbm":
+                # The headline `roofline` of a path-4 launch: the algorithmic FP64 flops against the rate at which they would
+                # complete with BOTH engines at their measured peaks (int8 tensor pipe for the exact slice products, FP64 pipe
+                # for the epilogue), time-additive as measured on B200.  The FP64-peak-only view (which exceeds 1 because the
+                # dot product has left that pipe) stays in `roofline_fp64_pipe`.
+                line["roofline_fp64_pipe"] = fp64_roof
+                peak2 = flops / (t_tensor + t_fp64) / 1e12
+                line["roofline"] = dict(fp64_roof, peak=peak2, frac=achieved_tf / peak2,
+                                        peak_source="two-engine floor: int8 MACs / measured tcgen05 int8 peak (7710 MAC/clk/SM, "
+                                                    "profiles/microbench/i8mma_vs_fp64.cu) + FP64 epilogue slots / FP64 pipe rate "
+                                                    "(measured live), time-additive; algorithmic FP64 flops / that time")
             if wl.family == "logistic":
                 # every instruction of the epilogue runs on a 16-lane datapath (FP64, IMAD / IMAD.WIDE, SHF, I2F, LDS): the
                 # scheduler issues one warp instruction per 2 clk whatever the pipe (ncu: issue-active 47 % of cycles with
