@@ -31,7 +31,7 @@ DATA_SEED = 20260317
 KERNEL_WARMUP = 500
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of this command (profiles/): a profiler figure, so it is a constant here, never measured in the timed run
-TRAFFIC_PER_LAUNCH = {("cfg3", 4): 197.1e6, ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}
+TRAFFIC_PER_LAUNCH = {("cfg3", 4): 197.1e6, ("cfg5", 4): 11.48e9, ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}
 
 
 def make_data(n=N_OBS, p=P_X, seed=DATA_SEED, block=0):
