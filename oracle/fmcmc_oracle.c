@@ -269,24 +269,32 @@ static int chol_lower(int k, const double* A, double* L) {
   return 0;
 }
 
-/* cyclic Jacobi eigen-decomposition of a symmetric matrix; eigenvalues sorted
- * decreasingly, V columns the eigenvectors (col-major).  A is destroyed. */
+/* eigen(Sigma, symmetric = TRUE) as MASS::mvrnorm consumes it (R/kernel_adapt.R:173-178).
+ * Third-party: MASS (no pin, DESCRIPTION) -> base R eigen() -> LAPACK dsyevr.  What is restated:
+ *   - eigenvalues DEcreasing, obtained as R does by REVERSING LAPACK's ascending order, so that ties
+ *     come out in descending index order (eps*I, the whole warm-up, gives the exchange matrix, i.e.
+ *     the draw is sqrt(eps) * (z_k, ..., z_1): pinned by the logpost trace the reference publishes in
+ *     man/figures/get_-1.png, tests/test_oracle_readme_golden.py);
+ *   - the SIGN of each eigenvector is an artefact of LAPACK's MRRR internals (dstemr: the component at
+ *     the twist index, in the tridiagonal basis, is positive) and, for the exactly repeated eigenvalue
+ *     of the first adapted Sigma (eps*I + rank one), so is the basis itself.  It is not reproducible
+ *     without the R installation's own LAPACK binary (README.md:268-269 is not reproduced by OpenBLAS'
+ *     dsyevr either).  Convention here: the largest |component| of every
+ *     eigenvector is positive (lowest index on ties).
+ * Algorithm: cyclic-by-row Jacobi, rotations skipped element-wise when |a_pq| <= 1e-17 sqrt|a_pp a_qq|,
+ * sweeps until one applies no rotation; only + - * / sqrt in a fixed order, so that the CUDA head
+ * (propose.cuh eigen_factor_warp) reproduces it bit for bit.  A is destroyed. */
 static void jacobi_eigen(int k, double* A, double* ev, double* V) {
   for (int i = 0; i < k * k; i++) V[i] = 0.0;
   for (int i = 0; i < k; i++) V[i + i * k] = 1.0;
-  for (int sweep = 0; sweep < 100; sweep++) {
-    double off = 0.0, diag = 0.0;
-    for (int q = 0; q < k; q++)
-      for (int p = 0; p < k; p++) {
-        if (p != q) off += A[p + q * k] * A[p + q * k];
-        else diag += A[p + q * k] * A[p + q * k];
-      }
-    if (off <= 1e-300 || off <= 1e-34 * diag) break;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    int rotated = 0;
     for (int p = 0; p < k - 1; p++)
       for (int q = p + 1; q < k; q++) {
         double apq = A[p + q * k];
-        if (apq == 0.0) continue;
         double app = A[p + p * k], aqq = A[q + q * k];
+        if (apq == 0.0 || fabs(apq) <= 1e-17 * sqrt(fabs(app * aqq))) continue;
+        rotated = 1;
         double theta = (aqq - app) / (2.0 * apq);
         double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
@@ -306,19 +314,37 @@ static void jacobi_eigen(int k, double* A, double* ev, double* V) {
           V[r + q * k] = s * vrp + c * vrq;
         }
       }
+    if (!rotated) break;
   }
   for (int i = 0; i < k; i++) ev[i] = A[i + i * k];
-  for (int i = 0; i < k - 1; i++) { /* selection sort, decreasing */
+  /* selection sort, decreasing; among equal eigenvalues the HIGHER original index first */
+  int idx[k];
+  for (int i = 0; i < k; i++) idx[i] = i;
+  for (int i = 0; i < k - 1; i++) {
     int m = i;
     for (int j = i + 1; j < k; j++)
-      if (ev[j] > ev[m]) m = j;
+      if (ev[j] > ev[m] || (ev[j] == ev[m] && idx[j] > idx[m])) m = j;
     if (m != i) {
       double tv = ev[i]; ev[i] = ev[m]; ev[m] = tv;
+      int ti = idx[i]; idx[i] = idx[m]; idx[m] = ti;
       for (int r = 0; r < k; r++) {
         double tt = V[r + i * k]; V[r + i * k] = V[r + m * k]; V[r + m * k] = tt;
       }
     }
   }
+  for (int j = 0; j < k; j++) { /* sign convention */
+    int m = 0;
+    for (int r = 1; r < k; r++)
+      if (fabs(V[r + j * k]) > fabs(V[m + j * k])) m = r;
+    if (V[m + j * k] < 0.0)
+      for (int r = 0; r < k; r++) V[r + j * k] = -V[r + j * k];
+  }
+}
+/* test hook: eigen-decomposition of a col-major symmetric matrix as the EIGEN draw uses it */
+void fmcmc_oracle_eigen(int k, const double* Sigma, double* ev, double* V) {
+  double A[k * k];
+  memcpy(A, Sigma, sizeof(A));
+  jacobi_eigen(k, A, ev, V);
 }
 
 /* ======================================================================== */

@@ -66,6 +66,10 @@ def lib():
         L.r_runif.argtypes = [C.c_int64, C.c_double, C.c_double, dp]
         L.r_norm_rand_vec.argtypes = [C.c_int64, dp]
         L.r_log_runif.argtypes = [C.c_int64, dp]
+        L.r_rt.argtypes = [C.c_int64, C.c_double, dp]
+        L.r_rgamma_vec.argtypes = [C.c_int64, C.c_double, C.c_double, dp]
+        L.r_exp_rand_vec.argtypes = [C.c_int64, dp]
+        L.r_exp_rand_q.argtypes = [dp]
         L.r_sd.restype = C.c_double
         L.r_sd.argtypes = [dp, C.c_int64]
         _lib = L
@@ -102,6 +106,24 @@ class RRng:
     def log_runif(n):
         out = np.empty(n)
         lib().r_log_runif(n, A.ptr(out))
+        return out
+
+    @staticmethod
+    def rt(n, df):
+        out = np.empty(n)
+        lib().r_rt(n, float(df), A.ptr(out))
+        return out
+
+    @staticmethod
+    def rgamma(n, shape, scale=1.0):
+        out = np.empty(n)
+        lib().r_rgamma_vec(n, float(shape), float(scale), A.ptr(out))
+        return out
+
+    @staticmethod
+    def rexp(n):
+        out = np.empty(n)
+        lib().r_exp_rand_vec(n, A.ptr(out))
         return out
 
     @staticmethod

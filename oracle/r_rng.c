@@ -178,3 +178,168 @@ double r_sd(const double* x, int64_t n) {
   }
   return sqrt((double)(ss / (n - 1)));
 }
+
+/* ------------------------------------------------------------------------ */
+/* exp_rand / rgamma / rchisq / rt — what kernel_ram's default qfun consumes */
+/* (R/kernel_ram.R:68 `stats::rt(k, k)`, called at :124).  Third-party, base  */
+/* R's nmath (sexp.c, rgamma.c, rchisq.c, rt.c), restated from the published  */
+/* algorithms: Ahrens & Dieter (1972) SA for the exponential, Ahrens & Dieter */
+/* (1982) GD for shape >= 1, Ahrens & Dieter (1974) GS for shape < 1.  Pinned */
+/* by README.md:245-246 (tests/test_oracle_readme_golden.py).                 */
+/* ------------------------------------------------------------------------ */
+double r_exp_rand(void) {
+  /* q[k-1] = sum_{j=1..k} log(2)^j / j! */
+  static const double q[] = {
+      0.6931471805599453, 0.9333736875190459, 0.9888777961838675, 0.9984589039328340,
+      0.9998292811061389, 0.9999833164100727, 0.9999985691438767, 0.9999998906925558,
+      0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
+      0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0000000000000000};
+  double a = 0.;
+  double u = r_unif_rand();
+  while (u <= 0. || u >= 1.) u = r_unif_rand();
+  for (;;) {
+    u += u;
+    if (u > 1.) break;
+    a += q[0];
+  }
+  u -= 1.;
+  if (u <= q[0]) return a + u;
+  int i = 0;
+  double ustar = r_unif_rand(), umin = ustar;
+  do {
+    ustar = r_unif_rand();
+    if (umin > ustar) umin = ustar;
+    i++;
+  } while (u > q[i]);
+  return a + umin * q[0];
+}
+void r_exp_rand_q(double* out16) { /* the table, recomputed, for the unit test */
+  long double s = 0, term = 1, l2 = 0.693147180559945309417232121458L;
+  for (int k = 1; k <= 16; k++) {
+    term *= l2 / k;
+    s += term;
+    out16[k - 1] = (double)s;
+  }
+}
+
+double r_rgamma(double a, double scale) {
+  const double sqrt32 = 5.656854;
+  const double exp_m1 = 0.36787944117144233;
+  const double q1 = 0.04166669, q2 = 0.02083148, q3 = 0.00801191, q4 = 0.00144121,
+               q5 = -7.388e-5, q6 = 2.4511e-4, q7 = 2.424e-4;
+  const double a1 = 0.3333333, a2 = -0.250003, a3 = 0.2000062, a4 = -0.1662921,
+               a5 = 0.1423657, a6 = -0.1367177, a7 = 0.1233795;
+  static double aa = 0., aaa = 0.;
+  static double s, s2, d;
+  static double q0, b, si, c;
+  double e, p, q, r, t, u, v, w, x, ret_val;
+
+  if (isnan(a) || isnan(scale)) return NAN;
+  if (a <= 0.0 || scale <= 0.0) {
+    if (scale == 0. || a == 0.) return 0.;
+    return NAN;
+  }
+  if (!isfinite(a) || !isfinite(scale)) return INFINITY;
+
+  if (a < 1) { /* GS */
+    e = 1.0 + exp_m1 * a;
+    for (;;) {
+      p = e * r_unif_rand();
+      if (p >= 1.0) {
+        x = -log((e - p) / a);
+        if (r_exp_rand() >= (1.0 - a) * log(x)) break;
+      } else {
+        x = exp(log(p) / a);
+        if (r_exp_rand() >= x) break;
+      }
+    }
+    return scale * x;
+  }
+
+  /* GD, step 1 */
+  if (a != aa) {
+    aa = a;
+    s2 = a - 0.5;
+    s = sqrt(s2);
+    d = sqrt32 - s * 12;
+  }
+  /* step 2: immediate acceptance */
+  t = r_norm_rand();
+  x = s + 0.5 * t;
+  ret_val = x * x;
+  if (t >= 0) return scale * ret_val;
+  /* step 3: squeeze acceptance */
+  u = r_unif_rand();
+  if (d * u <= t * t * t) return scale * ret_val;
+  /* step 4 */
+  if (a != aaa) {
+    aaa = a;
+    r = 1 / a;
+    q0 = ((((((q7 * r + q6) * r + q5) * r + q4) * r + q3) * r + q2) * r + q1) * r;
+    if (a <= 3.686) {
+      b = 0.463 + s + 0.178 * s2;
+      si = 1.235;
+      c = 0.195 / s - 0.079 + 0.16 * s;
+    } else if (a <= 13.022) {
+      b = 1.654 + 0.0076 * s2;
+      si = 1.68 / s + 0.275;
+      c = 0.062 / s + 0.024;
+    } else {
+      b = 1.77;
+      si = 0.75;
+      c = 0.1515 / s;
+    }
+  }
+  /* step 5-7 */
+  if (x > 0.0) {
+    v = t / (s + s);
+    if (fabs(v) <= 0.25)
+      q = q0 + 0.5 * t * t * ((((((a7 * v + a6) * v + a5) * v + a4) * v + a3) * v + a2) * v + a1) * v;
+    else
+      q = q0 - s * t + 0.25 * t * t + (s2 + s2) * log(1.0 + v);
+    if (log(1.0 - u) <= q) return scale * ret_val;
+  }
+  for (;;) {
+    /* step 8: double-exponential sample */
+    e = r_exp_rand();
+    u = r_unif_rand();
+    u = u + u - 1.0;
+    if (u < 0.0) t = b - si * e;
+    else t = b + si * e;
+    /* step 9 */
+    if (t >= -0.71874483771719) {
+      v = t / (s + s);
+      if (fabs(v) <= 0.25)
+        q = q0 + 0.5 * t * t * ((((((a7 * v + a6) * v + a5) * v + a4) * v + a3) * v + a2) * v + a1) * v;
+      else
+        q = q0 - s * t + 0.25 * t * t + (s2 + s2) * log(1.0 + v);
+      if (q > 0.0) {
+        w = expm1(q);
+        if (c * fabs(u) <= w * exp(e - 0.5 * t * t)) break;
+      }
+    }
+  }
+  x = s + 0.5 * t;
+  return scale * x * x;
+}
+
+double r_rchisq(double df) {
+  if (!isfinite(df) || df < 0.0) return NAN;
+  return r_rgamma(df / 2.0, 2.0);
+}
+
+double r_rt1(double df) {
+  if (isnan(df) || df <= 0.0) return NAN;
+  if (!isfinite(df)) return r_norm_rand();
+  double num = r_norm_rand();
+  return num / sqrt(r_rchisq(df) / df);
+}
+void r_rt(int64_t n, double df, double* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = r_rt1(df);
+}
+void r_rgamma_vec(int64_t n, double a, double scale, double* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = r_rgamma(a, scale);
+}
+void r_exp_rand_vec(int64_t n, double* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = r_exp_rand();
+}

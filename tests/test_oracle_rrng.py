@@ -46,3 +46,37 @@ def test_unif_open_interval_and_norm_moments(oracle):
     assert u.min() > 0 and u.max() < 1
     z = oracle.RRng.rnorm(20000, 10.0, 1.5)
     assert abs(z.mean() - 10) < 0.05 and abs(z.std() - 1.5) < 0.05
+
+
+def test_r_exp_rand_table_and_moments(oracle):
+    """exp_rand's q[k] = sum_{j<=k} ln(2)^j / j! (Ahrens & Dieter 1972).  R's sexp.c carries q[3] as
+    0.9984589039328340 where the series gives 0.99849593...; the restatement keeps R's literal (the
+    stream R users see), every other entry agrees with the series to 1e-15."""
+    import ctypes as C
+    from fmcmc_b200 import _abi as A
+    q = np.empty(16)
+    oracle.lib().r_exp_rand_q(A.ptr(q))
+    lit = [0.6931471805599453, 0.9333736875190459, 0.9888777961838675, 0.9984589039328340,
+           0.9998292811061389, 0.9999833164100727, 0.9999985691438767, 0.9999998906925558,
+           0.9999999924734159, 0.9999999995283275, 0.9999999999728814, 0.9999999999985598,
+           0.9999999999999289, 0.9999999999999968, 0.9999999999999999, 1.0]
+    for i in range(16):
+        if i != 3:
+            assert abs(q[i] - lit[i]) < 1e-15, i
+    R = oracle.RRng
+    R.set_seed(1)
+    e = R.rexp(200000)
+    assert abs(e.mean() - 1) < 0.01 and abs(e.var() - 1) < 0.03 and e.min() > 0
+
+
+def test_r_rgamma_rt_distributions(oracle):
+    """rgamma (GD for a >= 1, GS for a < 1) and rt against scipy's cdfs (Kolmogorov-Smirnov)."""
+    from scipy import stats
+    R = oracle.RRng
+    R.set_seed(42)
+    for a in (0.3, 1.0, 1.5, 3.686, 5.0, 16.0, 64.0):            # both branches, all three (b, si, c) regimes
+        g = R.rgamma(40000, a, 2.0)
+        assert stats.kstest(g, stats.gamma(a, scale=2.0).cdf).pvalue > 1e-3, a
+    for df in (1, 3, 7, 32, 128):
+        t = R.rt(40000, df)
+        assert stats.kstest(t, stats.t(df).cdf).pvalue > 1e-3, df
