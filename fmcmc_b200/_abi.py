@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes
 OK, EINVAL, ENAN, ECUDA, ENOMEM, ENOTPD, EUNSUP, ENANRATIO = range(8)

@@ -79,7 +79,11 @@ def lib():
     L.fmcmc_gelman_finish.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp, vp, vp, C.c_int, dp, dp,
                                       C.c_char_p, C.c_size_t]
     L.fmcmc_gelman.restype = C.c_int
-    L.fmcmc_gelman.argtypes = [vp, u8p, dp, dp, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
+    L.fmcmc_gelman.argtypes = [vp, u8p, C.c_int64, C.c_int64, dp, dp, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
+    L.fmcmc_gelman_window_begin.restype = C.c_int64
+    L.fmcmc_gelman_window_begin.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+    L.fmcmc_host_sym_eigmax.restype = C.c_int
+    L.fmcmc_host_sym_eigmax.argtypes = [C.c_int32, dp, dp]
     L.fmcmc_cov_recursive.restype = C.c_int
     L.fmcmc_cov_recursive.argtypes = [C.c_int, C.c_int32, C.c_int64, dp, dp, dp, C.c_double, C.c_double,
                                       C.c_double, dp, dp, dp, C.c_char_p, C.c_size_t]
@@ -103,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "fmcmc_version", "fmcmc_device_count", "fmcmc_model_nparams", "fmcmc_kernel_state_len",
     "fmcmc_rows_kept", "fmcmc_model_create", "fmcmc_model_create_device", "fmcmc_model_free",
     "fmcmc_set_path", "fmcmc_run", "fmcmc_logpost", "fmcmc_store_reset", "fmcmc_store_rows",
-    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_shard_alloc", "fmcmc_shard_attach", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
+    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_gelman_window_begin", "fmcmc_host_sym_eigmax", "fmcmc_shard_alloc", "fmcmc_shard_attach", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
 ]
 
 

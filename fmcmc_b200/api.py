@@ -80,6 +80,10 @@ def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_i
     total_chains = sharding.total if sharding else nchains
     if total_chains > 1 and not kernel.is_list:                 # R/mcmc.R:526-527 rep_kernel
         kernel._replicate(nchains)
+    elif kernel.is_list and len(kernel) != nchains:
+        raise ValueError(f"The passed kernel is a list of {len(kernel)} kernels, but this run has {nchains} chains"
+                         + (" on this rank" if sharding else "") + ". Pass a fresh kernel or one replicated for "
+                         "the same number of chains.")
     elif total_chains == 1 and kernel.is_list:
         raise ValueError("The passed kernel is for MCMC with more than one chain. Right now, -kernel- is of "
                          f"length {len(kernel)}")

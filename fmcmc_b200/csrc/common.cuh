@@ -12,7 +12,7 @@
 
 // Device copy of fmcmc_kernel_spec: every pointer is a DEVICE pointer.
 struct KParams {
-  int type, k, kf, scheme, order_len, nadapt_len;
+  int type, k, kf, scheme, order_len, nadapt_len, mvn_method;
   const int* order;        // explicit scheme (1-based)
   const int* seq;          // random scheme, fed: [C][seq_len] (1-based)
   long long seq_len;

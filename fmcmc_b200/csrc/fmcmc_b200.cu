@@ -404,7 +404,7 @@ static int validate_run(const fmcmc_model* m, const fmcmc_run_spec* run, const f
   }
   if (ks->type == FMCMC_KERNEL_ADAPT) {
     if (ks->bw > 0 && ks->bw > ks->warmup) { set_err(err, errlen, "The `warmup` parameter must be greater than `bw`."); return FMCMC_EINVAL; }
-    if (ks->mvn_method != FMCMC_MVN_CHOLESKY) { set_err(err, errlen, "the device draws mvrnorm through the Cholesky factor (FMCMC_MVN_CHOLESKY) only"); return FMCMC_EUNSUP; }
+    if (ks->mvn_method != FMCMC_MVN_CHOLESKY && ks->mvn_method != FMCMC_MVN_EIGEN) { set_err(err, errlen, "unknown mvn_method %d", ks->mvn_method); return FMCMC_EINVAL; }
     if (ks->freq < 1) { set_err(err, errlen, "-freq- must be >= 1."); return FMCMC_EINVAL; }
   }
   if (ks->type == FMCMC_KERNEL_RAM && ks->freq < 1) { set_err(err, errlen, "-freq- must be >= 1."); return FMCMC_EINVAL; }
@@ -728,7 +728,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   Blob blob;
   KParams kp{};
   kp.type = ks->type; kp.k = k; kp.kf = kf; kp.scheme = ks->scheme; kp.order_len = ks->order_len;
-  kp.nadapt_len = ks->nadapt_len; kp.seq_len = ks->seq_len;
+  kp.nadapt_len = ks->nadapt_len; kp.seq_len = ks->seq_len; kp.mvn_method = ks->mvn_method;
   kp.warmup = ks->warmup; kp.freq = ks->freq < 1 ? 1 : ks->freq; kp.bw = ks->bw;
   kp.until = ks->until; kp.eps = ks->eps; kp.Sd = ks->Sd; kp.arate = ks->arate; kp.dlen = dlen;
   std::vector<double> dflt0(k, 0.0), dflt1(k, 1.0), dfltlo(k, -1.79769313486231570815e308), dflthi(k, 1.79769313486231570815e308);
@@ -774,7 +774,8 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
 
   // ---- run buffers ---------------------------------------------------------------------
   const bool is_ram = ks->type == FMCMC_KERNEL_RAM;
-  const long long worklen = is_ram ? 4LL * kf * kf : (ks->type == FMCMC_KERNEL_ADAPT ? (long long)kf * kf : 0);
+  const long long worklen = is_ram ? 4LL * kf * kf
+                                  : (ks->type == FMCMC_KERNEL_ADAPT ? (ks->mvn_method == FMCMC_MVN_EIGEN ? 3LL : 1LL) * kf * kf : 0);  // L | eigen: A, V
   CU_CHECK(ensure(m->ans, (size_t)T * C * k * 8));
   CU_CHECK(ensure(m->draws, (size_t)T * C * k * 8));
   CU_CHECK(ensure(m->logpost, (size_t)T * C * 8));
@@ -1231,7 +1232,8 @@ extern "C" int fmcmc_gelman_partials(fmcmc_model* m, int64_t row_begin, int64_t 
   if (kf < 1) { set_err(err, errlen, "no free parameters"); return FMCMC_EINVAL; }
   CU_CHECK(ensure(m->g_mask, kf * sizeof(int)));
   CU_CHECK(cudaMemcpyAsync(m->g_mask.p, fidx.data(), kf * sizeof(int), cudaMemcpyHostToDevice, m->stream));
-  const int nblocks = std::min(C, 4 * m->sm_count);
+  const bool tiled = kf <= 144;  // moments + tiled SYRK (gelman.cuh); beyond that the per-pair kernel
+  const int nblocks = tiled ? std::min(C, m->sm_count) : std::min(C, 4 * m->sm_count);
   CU_CHECK(ensure(m->g_wpart, (size_t)nblocks * kf * kf * 8));
   double *dx = xbar, *ds = s2, *dw = wsum;
   if (!dev_out) {
@@ -1240,9 +1242,21 @@ extern "C" int fmcmc_gelman_partials(fmcmc_model* m, int64_t row_begin, int64_t 
     CU_CHECK(ensure(m->g_wsum, (size_t)kf * kf * 8));
     dx = m->g_xbar.as<double>(); ds = m->g_s2.as<double>(); dw = m->g_wsum.as<double>();
   }
-  const size_t smem = (size_t)kf * 8;
-  gelman_chain_stats_kernel<<<nblocks, 256, smem, m->stream>>>(m->store.as<double>(), C, k, row_begin, row_end,
-                                                               m->g_mask.as<int>(), kf, dx, ds, m->g_wpart.as<double>());
+  if (tiled) {
+    const double* st = m->store.as<double>();
+    const int* fi = m->g_mask.as<int>();
+    double* wp = m->g_wpart.as<double>();
+    gelman_chain_moments_kernel<<<std::min(C, 8 * m->sm_count), 256, 2 * 256 * 8, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, ds);
+    if (kf <= 16) gelman_syrk_kernel<1><<<nblocks, 256, 0, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, wp);
+    else if (kf <= 32) gelman_syrk_kernel<2><<<nblocks, 256, 0, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, wp);
+    else if (kf <= 64) gelman_syrk_kernel<4><<<nblocks, 256, 0, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, wp);
+    else if (kf <= 128) gelman_syrk_kernel<8><<<nblocks, 256, 0, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, wp);
+    else gelman_syrk_kernel<9><<<nblocks, 256, 0, m->stream>>>(st, C, k, row_begin, row_end, fi, kf, dx, wp);
+  } else {
+    const size_t smem = (size_t)kf * 8;
+    gelman_chain_stats_kernel<<<nblocks, 256, smem, m->stream>>>(m->store.as<double>(), C, k, row_begin, row_end,
+                                                                 m->g_mask.as<int>(), kf, dx, ds, m->g_wpart.as<double>());
+  }
   gelman_wsum_kernel<<<(kf * kf + 255) / 256, 256, 0, m->stream>>>(m->g_wpart.as<double>(), nblocks, kf * kf, dw);
   CU_CHECK(cudaGetLastError());
   if (!dev_out) {
@@ -1256,6 +1270,7 @@ extern "C" int fmcmc_gelman_partials(fmcmc_model* m, int64_t row_begin, int64_t 
 
 // Host finish of coda::gelman.diag's multivariate part: largest eigenvalue of
 // L^-1 B L^-T with W = L L' (== backsolve(CW, t(backsolve(CW, B, transpose=TRUE)), transpose=TRUE)).
+static int host_sym_eigmax(int p, std::vector<double>& Mx, double* emax);
 static int host_gelman_emax(int p, const std::vector<double>& W, const std::vector<double>& B, double* emax) {
   std::vector<double> L((size_t)p * p, 0.0), Y((size_t)p * p), Mx((size_t)p * p);
   for (int j = 0; j < p; j++) {
@@ -1287,38 +1302,76 @@ static int host_gelman_emax(int p, const std::vector<double>& W, const std::vect
       const double v = 0.5 * (Mx[a + (size_t)b * p] + Mx[b + (size_t)a * p]);
       Mx[a + (size_t)b * p] = Mx[b + (size_t)a * p] = v;
     }
-  // cyclic Jacobi, eigenvalues only
-  for (int sweep = 0; sweep < 100; sweep++) {
-    double off = 0.0, diag = 0.0;
-    for (int q = 0; q < p; q++)
-      for (int r = 0; r < p; r++) {
-        const double v = Mx[r + (size_t)q * p] * Mx[r + (size_t)q * p];
-        if (r != q) off += v; else diag += v;
-      }
-    if (off <= 1e-300 || off <= 1e-34 * diag) break;
-    for (int a = 0; a < p - 1; a++)
-      for (int b = a + 1; b < p; b++) {
-        const double apq = Mx[a + (size_t)b * p];
-        if (apq == 0.0) continue;
-        const double theta = (Mx[b + (size_t)b * p] - Mx[a + (size_t)a * p]) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int r = 0; r < p; r++) {
-          const double x = Mx[r + (size_t)a * p], y = Mx[r + (size_t)b * p];
-          Mx[r + (size_t)a * p] = c * x - s * y;
-          Mx[r + (size_t)b * p] = s * x + c * y;
-        }
-        for (int r = 0; r < p; r++) {
-          const double x = Mx[a + (size_t)r * p], y = Mx[b + (size_t)r * p];
-          Mx[a + (size_t)r * p] = c * x - s * y;
-          Mx[b + (size_t)r * p] = s * x + c * y;
-        }
-      }
+  return host_sym_eigmax(p, Mx, emax);
+}
+
+// largest eigenvalue of the symmetric p x p Mx (col-major, destroyed): Householder tridiagonalisation (O(4/3 p^3)) + Sturm-count bisection.
+static int host_sym_eigmax(int p, std::vector<double>& Mx, double* emax) {
+  // (The cyclic Jacobi this replaces took ~40 ms at p = 128; this is ~1 ms.)
+  std::vector<double> d(p), e(p > 1 ? p - 1 : 1, 0.0), v(p), w(p);
+  for (int c = 0; c + 2 < p; c++) {
+    const int nn = p - c - 1;                       // x = Mx[c+1 .., c]
+    double nrm = 0.0;
+    for (int r = 0; r < nn; r++) nrm += Mx[(c + 1 + r) + (size_t)c * p] * Mx[(c + 1 + r) + (size_t)c * p];
+    nrm = sqrt(nrm);
+    d[c] = Mx[c + (size_t)c * p];
+    const double x0 = Mx[(c + 1) + (size_t)c * p];
+    const double alpha = x0 > 0.0 ? -nrm : nrm;
+    e[c] = alpha;
+    double vn = 0.0;
+    for (int r = 0; r < nn; r++) { v[r] = Mx[(c + 1 + r) + (size_t)c * p]; }
+    v[0] -= alpha;
+    for (int r = 0; r < nn; r++) vn += v[r] * v[r];
+    if (!(vn > 0.0)) continue;                      // column already in tridiagonal form
+    vn = sqrt(vn);
+    for (int r = 0; r < nn; r++) v[r] /= vn;
+    double K = 0.0;                                  // A22 <- H A22 H, H = I - 2 v v'
+    for (int r = 0; r < nn; r++) {
+      double acc = 0.0;
+      for (int q = 0; q < nn; q++) acc += Mx[(c + 1 + r) + (size_t)(c + 1 + q) * p] * v[q];
+      w[r] = 2.0 * acc;
+      K += v[r] * w[r];
+    }
+    for (int r = 0; r < nn; r++) w[r] -= K * v[r];
+    for (int q = 0; q < nn; q++)
+      for (int r = 0; r < nn; r++) Mx[(c + 1 + r) + (size_t)(c + 1 + q) * p] -= v[r] * w[q] + w[r] * v[q];
   }
-  double e = Mx[0];
-  for (int a = 1; a < p; a++) e = std::max(e, Mx[a + (size_t)a * p]);
-  *emax = e;
+  if (p >= 2) {
+    d[p - 2] = Mx[(p - 2) + (size_t)(p - 2) * p];
+    e[p - 2] = Mx[(p - 1) + (size_t)(p - 2) * p];
+  }
+  d[p - 1] = Mx[(p - 1) + (size_t)(p - 1) * p];
+  double lo = d[0], hi = d[0];                       // Gershgorin
+  for (int a = 0; a < p; a++) {
+    const double rad = (a > 0 ? fabs(e[a - 1]) : 0.0) + (a + 1 < p ? fabs(e[a]) : 0.0);
+    lo = std::min(lo, d[a] - rad);
+    hi = std::max(hi, d[a] + rad);
+  }
+  const double tiny = 2.2250738585072014e-308;
+  auto below = [&](double x) {                       // number of eigenvalues < x
+    int cnt = 0;
+    double q = d[0] - x;
+    if (q < 0.0) cnt++;
+    for (int a = 1; a < p; a++) {
+      if (fabs(q) < tiny) q = q < 0.0 ? -tiny : tiny;
+      q = d[a] - x - e[a - 1] * e[a - 1] / q;
+      if (q < 0.0) cnt++;
+    }
+    return cnt;
+  };
+  for (int it = 0; it < 200 && hi - lo > 4.0 * 2.220446049250313e-16 * std::max(fabs(lo), fabs(hi)); it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    if (below(mid) >= p) hi = mid; else lo = mid;   // all p eigenvalues below mid -> the largest is below mid
+  }
+  *emax = 0.5 * (lo + hi);
   return 0;
+}
+
+extern "C" int fmcmc_host_sym_eigmax(int32_t p, const double* A, double* emax) {
+  if (p < 1 || !A || !emax) return FMCMC_EINVAL;
+  std::vector<double> Mx(A, A + (size_t)p * p);
+  return host_sym_eigmax(p, Mx, emax);
 }
 
 extern "C" int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, int32_t kf,
@@ -1386,13 +1439,36 @@ extern "C" int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchain
   return status;
 }
 
-extern "C" int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double* mpsrf,
-                            int64_t* niter_used, char* err, size_t errlen) {
+// 0-based first store row kept by coda::gelman.diag's autoburnin on an mcmc.list with mcpar = (start, start + (rows-1) thin, thin):
+//   if (autoburnin && start(x) < end(x)/2) x <- window(x, start = end(x)/2 + 1)
+// window.mcmc() snaps a start that is not on the iteration grid UP to the next kept iteration (ts.eps = 1e-5), then
+// keeps rows from trunc((start' - start)/thin + 1.5) (1-based).  Third-party coda, restated from its published source;
+// the Python glue's window_first_row (fmcmc_b200/coda.py) is the same arithmetic and tests/test_host_logic.py pins both.
+extern "C" int64_t fmcmc_gelman_window_begin(int64_t start_iter, int64_t thin, int64_t rows) {
+  if (rows < 1 || thin < 1) return 0;
+  const double start = (double)start_iter, th = (double)thin;
+  const double end = start + th * (double)(rows - 1);
+  if (!(start < end / 2.0)) return 0;
+  double ns = end / 2.0 + 1.0;
+  if (ns < start) ns = start;
+  const double q = (ns - start) / th;
+  const double near = start + th * floor(q + 0.5);                  // closest grid point
+  if (fabs(near - ns) > fabs(ns) * 1e-5) ns = start + th * (floor(q) + 1.0);  // not on the grid: next kept iteration
+  long long first = (long long)((ns - start) / th + 1.5);            // 1-based
+  if (first < 1) first = 1;
+  if (first > rows) first = rows;
+  return first - 1;
+}
+
+extern "C" int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, int64_t start_iter, int64_t thin, double* psrf,
+                            double* mpsrf, int64_t* niter_used, char* err, size_t errlen) {
   if (!m) { set_err(err, errlen, "null model"); return FMCMC_EINVAL; }
   const long long rows = m->store_rows;
-  // coda: if (autoburnin && start(x) < end(x)/2) x <- window(x, start = end(x)/2 + 1); on the
-  // store's own 1..rows grid this keeps rows (floor(rows/2)+1 .. rows) (0-based: rows/2 ..).
-  const long long begin = rows / 2;
+  const long long begin = fmcmc_gelman_window_begin(start_iter, thin, rows);
+  if (rows - begin < 2) {
+    set_err(err, errlen, "the Gelman-Rubin window holds %lld row(s); at least 2 are needed", rows - begin);
+    return FMCMC_EINVAL;
+  }
   int kf = 0;
   for (int j = 0; j < m->store_k; j++) kf += (!free_mask || free_mask[j]) ? 1 : 0;
   if (m->store_C < 2) {

@@ -47,6 +47,134 @@ __global__ void gelman_chain_stats_kernel(const double* __restrict__ store, int 
   }
 }
 
+// ---- the scalable pair (kf <= 144): O(C N kf) moments + a tiled batched SYRK -----------------------------------------
+// gelman_chain_stats_kernel above walks the window once per (a, b) pair of every chain: kf^2 strided passes.  At
+// BASELINE configs[4] (8 192 chains x 128 parameters per GPU, 500-row window) that is ~1.3e11 strided loads.  Here:
+//   gelman_chain_moments_kernel  one CTA per chain, two coalesced passes: refined mean (R's mean(): sum / N, then
+//                                the mean of the residuals added back) and variance = (q - r^2 / N) / (N - 1),
+//                                q / r the sums of squared / plain residuals about the first-pass mean;
+//   gelman_syrk_kernel<NB>       sum_j sum_t (x_jt - xbar_j)(x_jt - xbar_j)' as ONE centred SYRK over all (chain, row)
+//                                pairs: a CTA keeps a 16 NB x 16 NB accumulator in registers (NB x NB per thread,
+//                                strided so the shared-memory reads are broadcasts / conflict-free), streams 16-row
+//                                tiles of its chains through shared memory (next tile prefetched into registers
+//                                while the current one is multiplied) and writes one kf x kf partial; partials are
+//                                summed in block order (gelman_wsum_kernel) -> deterministic.
+// Algorithmic work at configs[4]: 3 passes over the 4.2 GB window (2 ms of HBM) + 6.7e10 FP64 FMAs x 2 (full square,
+// no symmetry exploited) = 7.3 ms at the FP64 peak.
+#define GS_RT 16
+__global__ void __launch_bounds__(256)
+gelman_chain_moments_kernel(const double* __restrict__ store, int C, int k, long long row_begin, long long row_end,
+                            const int* __restrict__ fidx, int kf, double* __restrict__ xbar, double* __restrict__ s2) {
+  extern __shared__ double gm_sh[];  // 2 x [G][KP] partial sums (G * KP = 256)
+  int KP = 1;
+  while (KP < kf && KP < 256) KP <<= 1;
+  const int G = 256 / KP, g = threadIdx.x / KP, a0 = threadIdx.x % KP;
+  double* part = gm_sh;
+  double* part2 = gm_sh + (size_t)G * KP;
+  const long long N = row_end - row_begin;
+  const size_t rowlen = (size_t)C * k;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const double* base = store + (size_t)row_begin * rowlen + (size_t)c * k;
+    for (int ab = 0; ab < kf; ab += KP) {  // kf <= 256: one trip; uniform so that the barriers are not divergent
+      const int a = ab + a0;
+      const bool on = a < kf;
+      const int ja = on ? fidx[a] : 0;
+      double s = 0.0;
+      if (on)
+        for (long long t = g; t < N; t += G) s += base[t * rowlen + ja];
+      __syncthreads();
+      part[g * KP + a0] = s;
+      __syncthreads();
+      double tot = 0.0;
+      for (int q = 0; q < G; q++) tot += part[q * KP + a0];
+      const double mean0 = tot / (double)N;
+      double r = 0.0, qq = 0.0;
+      if (on)
+        for (long long t = g; t < N; t += G) {
+          const double d = base[t * rowlen + ja] - mean0;
+          r += d;
+          qq = fma(d, d, qq);
+        }
+      __syncthreads();
+      part[g * KP + a0] = r;
+      part2[g * KP + a0] = qq;
+      __syncthreads();
+      if (g == 0 && on) {
+        double rt = 0.0, qt = 0.0;
+        for (int q = 0; q < G; q++) { rt += part[q * KP + a0]; qt += part2[q * KP + a0]; }
+        xbar[(size_t)c * kf + a] = mean0 + rt / (double)N;
+        s2[(size_t)c * kf + a] = (qt - rt * rt / (double)N) / (double)(N - 1);
+      }
+    }
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+gelman_syrk_kernel(const double* __restrict__ store, int C, int k, long long row_begin, long long row_end,
+                   const int* __restrict__ fidx, int kf, const double* __restrict__ xbar,
+                   double* __restrict__ wpart) {
+  constexpr int KFP = 16 * NB;
+  constexpr int PER = GS_RT * KFP / 256;  // tile elements per thread (= NB)
+  __shared__ double tile[GS_RT][KFP];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long N = row_end - row_begin;
+  const size_t rowlen = (size_t)C * k;
+  double acc[NB][NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) acc[i][j] = 0.0;
+  // this thread's slots of a tile: element e = threadIdx.x + 256 q -> (row e / KFP, column e % KFP)
+  int col[PER], jcol[PER];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    col[q] = (threadIdx.x + 256 * q) % KFP;
+    jcol[q] = col[q] < kf ? fidx[col[q]] : -1;
+  }
+  const long long ntile = (N + GS_RT - 1) / GS_RT;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const double* base = store + (size_t)row_begin * rowlen + (size_t)c * k;
+    double mean[PER], nxt[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) mean[q] = jcol[q] >= 0 ? xbar[(size_t)c * kf + col[q]] : 0.0;
+    auto fetch = [&](long long tl) {
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const long long t = tl * GS_RT + (threadIdx.x + 256 * q) / KFP;
+        nxt[q] = (jcol[q] >= 0 && t < N) ? base[t * rowlen + jcol[q]] - mean[q] : 0.0;
+      }
+    };
+    fetch(0);
+    for (long long tl = 0; tl < ntile; tl++) {
+      __syncthreads();  // previous tile consumed
+#pragma unroll
+      for (int q = 0; q < PER; q++) tile[(threadIdx.x + 256 * q) / KFP][col[q]] = nxt[q];
+      __syncthreads();
+      if (tl + 1 < ntile) fetch(tl + 1);  // in flight while this tile is multiplied
+#pragma unroll 4
+      for (int tt = 0; tt < GS_RT; tt++) {
+        double av[NB], bv[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) { av[i] = tile[tt][ty + 16 * i]; bv[i] = tile[tt][tx + 16 * i]; }
+#pragma unroll
+        for (int i = 0; i < NB; i++)
+#pragma unroll
+          for (int j = 0; j < NB; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+  double* wp = wpart + (size_t)blockIdx.x * kf * kf;
+  const double inv = 1.0 / (double)(N - 1);
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int a = ty + 16 * i, b = tx + 16 * j;
+      if (a < kf && b < kf) wp[a + (size_t)b * kf] = acc[i][j] * inv;
+    }
+}
+
 // out[e] = sum_b part[b][e] in block order (deterministic)
 __global__ void gelman_wsum_kernel(const double* __restrict__ part, int nblocks, int len, double* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -130,6 +130,79 @@ __device__ int chol_lower_warp(int k, const double* A, double* L, int lane) {
   return 0;
 }
 
+// ---- MASS::mvrnorm's factor: F = V diag(sqrt(max(ev, 0))), eigen(Sigma, symmetric = TRUE) with R's ordering and the
+// sign convention of oracle/fmcmc_oracle.c jacobi_eigen() (R/kernel_adapt.R:173-178; FMCMC_MVN_EIGEN).  Cyclic-by-row
+// Jacobi on the warp: every lane derives the same rotation from the same three elements with the oracle's unfused
+// operations, the three length-k updates of a rotation are lane-strided (their elements are independent), so A, V and
+// therefore every draw are the oracle's bit for bit.  A, V: kf^2 doubles of scratch each (shared or global), evs:
+// 2 kf doubles.  Returns 0 or FMCMC_ENOTPD (mvrnorm's tol = 1e-6), warp-uniform.
+__device__ int eigen_factor_warp(int k, const double* Sigma, double* A, double* V, double* F, double* evs, int lane) {
+  for (int e = lane; e < k * k; e += FM_WARP) {
+    A[e] = Sigma[e];
+    V[e] = ((e % k) == (e / k)) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  for (int sweep = 0; sweep < 64; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < k - 1; p++)
+      for (int q = p + 1; q < k; q++) {
+        const double apq = A[p + q * k], app = A[p + p * k], aqq = A[q + q * k];
+        if (apq == 0.0 || fabs(apq) <= xmul(1e-17, sqrt(fabs(xmul(app, aqq))))) continue;  // warp-uniform
+        rotated = true;
+        const double theta = xdiv(xsub(aqq, app), xmul(2.0, apq));
+        const double t = xdiv(theta >= 0 ? 1.0 : -1.0, xadd(fabs(theta), sqrt(xadd(xmul(theta, theta), 1.0))));
+        const double c = xdiv(1.0, sqrt(xadd(xmul(t, t), 1.0))), s = xmul(t, c);
+        __syncwarp();
+        for (int r = lane; r < k; r += FM_WARP) {  // columns p, q
+          const double arp = A[r + p * k], arq = A[r + q * k];
+          A[r + p * k] = xsub(xmul(c, arp), xmul(s, arq));
+          A[r + q * k] = xadd(xmul(s, arp), xmul(c, arq));
+        }
+        __syncwarp();
+        for (int r = lane; r < k; r += FM_WARP) {  // rows p, q; eigenvector columns p, q
+          const double apr = A[p + r * k], aqr = A[q + r * k];
+          A[p + r * k] = xsub(xmul(c, apr), xmul(s, aqr));
+          A[q + r * k] = xadd(xmul(s, apr), xmul(c, aqr));
+          const double vrp = V[r + p * k], vrq = V[r + q * k];
+          V[r + p * k] = xsub(xmul(c, vrp), xmul(s, vrq));
+          V[r + q * k] = xadd(xmul(s, vrp), xmul(c, vrq));
+        }
+        __syncwarp();
+      }
+    if (!rotated) break;
+  }
+  int* idx = reinterpret_cast<int*>(evs + k);
+  if (lane == 0) {  // decreasing eigenvalues; among equal ones the higher original index first (R reverses LAPACK's order)
+    for (int i = 0; i < k; i++) { evs[i] = A[i + i * k]; idx[i] = i; }
+    for (int i = 0; i < k - 1; i++) {
+      int m = i;
+      for (int j = i + 1; j < k; j++)
+        if (evs[j] > evs[m] || (evs[j] == evs[m] && idx[j] > idx[m])) m = j;
+      if (m != i) {
+        const double tv = evs[i]; evs[i] = evs[m]; evs[m] = tv;
+        const int ti = idx[i]; idx[i] = idx[m]; idx[m] = ti;
+      }
+    }
+  }
+  __syncwarp();
+  const double ev0 = evs[0];
+  bool bad = false;
+  for (int j = lane; j < k; j += FM_WARP) {  // one eigenvector per lane: sign convention, scaling
+    const double ev = evs[j];
+    bad |= ev < xmul(-1e-6, fabs(ev0));
+    const double* v = V + (size_t)idx[j] * k;
+    int m = 0;
+    for (int r = 1; r < k; r++)
+      if (fabs(v[r]) > fabs(v[m])) m = r;
+    const bool neg = v[m] < 0.0;
+    const double sd = sqrt(ev > 0.0 ? ev : 0.0);
+    for (int r = 0; r < k; r++) F[r + j * k] = xmul(neg ? -v[r] : v[r], sd);
+  }
+  bad = __any_sync(FM_FULL, bad);
+  __syncwarp();
+  return bad ? FMCMC_ENOTPD : 0;
+}
+
 // RAM phase B (after the likelihood of the un-reflected proposal is known):
 // Sigma <- t(chol(Sigma (I + eta (a_n - arate) UU'/|U|^2) Sigma'))   R/kernel_ram.R:132-150
 __device__ int ram_adapt_warp(const KParams& kp, const RunBuffers& rb, const ChainCtx& cx, double f1u, int lane) {
@@ -339,8 +412,13 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       }
       abs_iter += 1;  // :170
       const double* Lr = L;  // factor the matvec below reads
+      const bool eigen = kp.mvn_method == FMCMC_MVN_EIGEN;
       if (dirty) {
-        if (cx.mat) {  // factorise in shared memory, keep a copy in HBM for the rows that do not re-adapt
+        if (eigen) {  // MASS::mvrnorm's own factor (verification mode): A, V in shared memory or behind L in rb.work
+          double* As = cx.mat ? cx.mat : L + (size_t)kf * kf;
+          double* Vs = As + (size_t)kf * kf;
+          if (eigen_factor_warp(kf, Sigma, As, Vs, L, cx.scr, lane)) return FMCMC_ENOTPD;
+        } else if (cx.mat) {  // factorise in shared memory, keep a copy in HBM for the rows that do not re-adapt
           double* As = cx.mat;
           double* Ls = cx.mat + (size_t)kf * kf;
           for (int e = lane; e < kf * kf; e += FM_WARP) As[e] = Sigma[e];
@@ -352,6 +430,7 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
           return FMCMC_ENOTPD;  // mvrnorm: "'Sigma' is not positive definite"
         }
         if (lane == 0) *cflag |= 2;
+        __syncwarp();
       }
       double* z = cx.scr + 3 * kf;
       for (int a = lane; a < kf; a += FM_WARP) z[a] = draw_z(sp, rb, cx, a);
@@ -359,7 +438,8 @@ __device__ int propose_warp(const KParams& kp, const StreamParams& sp, const Run
       __syncwarp();
       for (int a = lane; a < kf; a += FM_WARP) {  // :173-180
         double s = 0.0;
-        for (int b = 0; b <= a; b++) s = xadd(s, xmul(Lr[a + b * kf], z[b]));
+        const int nb = eigen ? kf : a + 1;  // full factor / lower triangle
+        for (int b = 0; b < nb; b++) s = xadd(s, xmul(Lr[a + b * kf], z[b]));
         const int w = kp.free_idx[a];
         th1[w] = reflect1(xadd(th0[w], xadd(kp.mu[w], s)), kp.lb[w], kp.ub[w]);
       }

@@ -121,6 +121,18 @@ class DeviceModel:
         _lib.check(rc, err)
         return None
 
+    def gelman(self, free_mask, start_iter=1, thin=1):
+        """fmcmc_gelman: coda's autoburnin window + statistics + finish in one call (single GPU).
+        Returns (psrf, mpsrf, niter_used)."""
+        mask = np.ascontiguousarray(free_mask, dtype=np.uint8)
+        psrf = np.empty(int(mask.sum()))
+        mpsrf, used = C.c_double(), C.c_int64()
+        err = _lib.errbuf()
+        rc = _lib.lib().fmcmc_gelman(self._h, A.ptr(mask, C.POINTER(C.c_uint8)), int(start_iter), int(thin),
+                                     A.ptr(psrf), C.byref(mpsrf), C.byref(used), err, len(err))
+        _lib.check(rc, err)
+        return psrf, mpsrf.value, used.value
+
     def gelman_finish(self, niter, nchains_total, kf, xbar, s2, wsum, dev_in=False):
         psrf = np.empty(kf)
         mpsrf = C.c_double()

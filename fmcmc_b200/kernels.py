@@ -131,11 +131,20 @@ class FmcmcKernel:
             return self._istate, self._dstate
         ist = np.zeros((nchains, A.ISTATE_LEN), dtype=np.int64)
         dst = np.zeros((nchains, max(dlen, 1)), dtype=np.float64)
-        user_sigma = getattr(self, "Sigma", None)
-        if user_sigma is not None and self.type in (A.KERNEL_ADAPT, A.KERNEL_RAM) and not self.is_list:
-            sig = np.asfortranarray(user_sigma, dtype=np.float64)
-            dst[:, :kf * kf] = sig.reshape(-1, order="F")[None, :]
-            ist[:, 1] |= A.STATE_INIT
+        if self.type in (A.KERNEL_ADAPT, A.KERNEL_RAM):
+            # a user-supplied Sigma seeds EVERY chain: rep_kernel copies the whole environment, Sigma included
+            # (R/kernel.R:407-434), and each chain's copy may have been edited since (kernel[[i]]$Sigma <- ...)
+            owners = self._chains if self._chains is not None else [self] * nchains
+            for c in range(nchains):
+                user_sigma = getattr(owners[c], "Sigma", None)
+                if user_sigma is None:
+                    continue
+                sig = np.asarray(user_sigma, dtype=np.float64)
+                if sig.shape != (kf, kf):
+                    raise ValueError(f"-Sigma- must be a {kf} x {kf} matrix (one row per non-fixed parameter), "
+                                     f"got {sig.shape}.")
+                dst[c, :kf * kf] = sig.reshape(-1, order="F")
+                ist[c, 1] |= A.STATE_INIT
         self._istate, self._dstate = ist, dst
         return ist, dst
 
@@ -189,12 +198,17 @@ def kernel_unif_reflective(min_=-1.0, max_=1.0, lb=None, ub=None, fixed=False, s
 
 
 def kernel_adapt(mu=0.0, bw=0, lb=-A.DBL_MAX, ub=A.DBL_MAX, freq=1, warmup=500, Sigma=None, Sd=None,
-                 eps=1e-4, fixed=False, until=math.inf):
-    """R/kernel_adapt.R:54-208 (Haario et al. 2001)."""
+                 eps=1e-4, fixed=False, until=math.inf, *, mvn="cholesky"):
+    """R/kernel_adapt.R:54-208 (Haario et al. 2001).  `mvn` (not in the reference) picks the factor the normal draw
+    goes through: "cholesky" (default) or "eigen", MASS::mvrnorm's own V sqrt(ev) z with R's eigenvalue order - same
+    N(mu, Sigma) either way."""
     if bw > 0 and bw > warmup:
         raise ValueError("The `warmup` parameter must be greater than `bw`.")
+    if mvn not in ("cholesky", "eigen"):
+        raise ValueError("-mvn- must be 'cholesky' or 'eigen'.")
     return FmcmcKernel(A.KERNEL_ADAPT, mu=mu, bw=bw, lb=lb, ub=ub, freq=freq, warmup=warmup, Sigma=Sigma, Sd=Sd,
-                       eps=eps, fixed=fixed, until=until, Mean_t_prev=None)
+                       eps=eps, fixed=fixed, until=until, Mean_t_prev=None,
+                       mvn_method=A.MVN_EIGEN if mvn == "eigen" else A.MVN_CHOLESKY)
 
 
 kernel_am = kernel_adapt

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FMCMC_ABI_VERSION 1
+#define FMCMC_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------- */
 enum {
@@ -107,9 +107,11 @@ enum {
 
 /* how kernel_adapt turns Sigma into a draw */
 enum {
-  FMCMC_MVN_CHOLESKY = 0, /* mu + L z           (device production path)                 */
-  FMCMC_MVN_EIGEN    = 1  /* mu + V sqrt(max(ev,0)) z, MASS::mvrnorm's published form;
-                             oracle only (eigenvector signs are LAPACK-specific)          */
+  FMCMC_MVN_CHOLESKY = 0, /* mu + L z  (production default: same N(mu, Sigma), O(k^3 / 3) per re-adapted row)   */
+  FMCMC_MVN_EIGEN    = 1  /* mu + V sqrt(max(ev,0)) z, MASS::mvrnorm's own form (R/kernel_adapt.R:173-178) with
+                             R's eigenvalue ordering; the eigenvector SIGNS are a LAPACK-build artefact, the
+                             convention is "largest |component| positive" (DESIGN.md section 5).  Device and
+                             oracle agree bit for bit; costs a Jacobi sweep set per re-adapted row. */
 };
 
 typedef struct fmcmc_kernel_spec {
@@ -304,10 +306,18 @@ int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, in
                         const double* xbar, const double* s2, const double* wsum, int dev_in,
                         double* psrf, double* mpsrf, char* err, size_t errlen);
 
-/* Single-GPU convenience: autoburnin window (second half) + partials + finish
- * on everything in the store; `start_iter`/`end_iter`/`thin` describe mcpar. */
-int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, double* psrf, double* mpsrf,
-                 int64_t* niter_used, char* err, size_t errlen);
+/* Single-GPU convenience = what `conv_checker(ans)` costs the R glue in ONE call (R/mcmc.R:968 ->
+ * R/convergence.R:207 coda::gelman.diag): coda's autoburnin window + partials + finish on everything in the
+ * store.  `start_iter` / `thin` are the store's mcpar (first kept iteration, thinning); the window is
+ * fmcmc_gelman_window_begin(start_iter, thin, rows) .. rows, i.e. coda only drops the first half when
+ * start < end/2 and snaps to the next kept iteration.  Fewer than 2 rows in the window -> FMCMC_EINVAL. */
+int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, int64_t start_iter, int64_t thin, double* psrf,
+                 double* mpsrf, int64_t* niter_used, char* err, size_t errlen);
+int64_t fmcmc_gelman_window_begin(int64_t start_iter, int64_t thin, int64_t rows);
+
+/* Host-only helper of the Gelman finish, exported for the CPU test-suite: largest eigenvalue of a symmetric
+ * p x p matrix (col-major; Householder tridiagonalisation + Sturm bisection). */
+int fmcmc_host_sym_eigmax(int32_t p, const double* A, double* emax);
 
 /* ---- observation sharding across GPUs (few chains, huge n) -------------------------
  * Every rank creates its model on a ROW SLICE of X / y and runs the SAME chains with the same streams.  The

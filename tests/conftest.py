@@ -29,3 +29,17 @@ def readme_data(oracle):
     X = R.rnorm(n)
     y = 3.0 + 2.0 * X + R.rnorm(n, 0.0, 4.0)
     return dict(n=n, X=X, y=y, sd_y=R.sd(y))
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Worst norm-wise and element-wise errors the parity helper saw (tests/gpu_util.py)."""
+    try:
+        from gpu_util import PARITY_LOG
+    except Exception:
+        return
+    if PARITY_LOG:
+        worst_n = max(PARITY_LOG, key=lambda r: r[2])
+        worst_e = max(PARITY_LOG, key=lambda r: r[3])
+        terminalreporter.write_line(
+            f"parity: {len(PARITY_LOG)} comparisons; worst norm-wise {worst_n[2]:.2e} ({worst_n[0]} {worst_n[1]}); "
+            f"worst element-wise {worst_e[3]:.2e} ({worst_e[0]} {worst_e[1]})")

@@ -83,16 +83,36 @@ def col_rel_err(a, b):
     return float(d.max() / max(bb.max(), 1e-300))
 
 
-def assert_parity(g, o, rtol=1e-12, what=""):
-    """Fed-stream contract: every accept/reject decision identical, samples within rtol (relative to
-    the parameter's scale, see col_rel_err)."""
+def elem_rel_err(a, b):
+    """Element-wise relative error |a - b| / max(|b|, 1e-3 * column scale): the literal reading of "every sample
+    within 1e-12 relative", with a floor so that samples passing near zero do not divide rounding noise by ~0."""
+    fin = np.isfinite(b)
+    d = np.where(fin, np.abs(np.where(fin, a, 0.0) - np.where(fin, b, 0.0)), 0.0)
+    bb = np.where(fin, np.abs(b), 0.0)
+    scale = bb.max(axis=(0, 1), keepdims=True) if a.ndim == 3 else bb.max()
+    return float(np.max(d / np.maximum(np.maximum(bb, 1e-3 * scale), 1e-300)))
+
+
+PARITY_LOG = []      # (what, name, norm-wise, element-wise) of every assert_parity call (printed by conftest at exit)
+
+
+def assert_parity(g, o, rtol=1e-12, what="", elem_rtol=None):
+    """Fed-stream contract: every accept/reject decision identical, samples within rtol norm-wise (relative to
+    the parameter's scale, see col_rel_err) AND within elem_rtol element-wise (default 1000 rtol = what the norm-wise
+    bound implies for an element at elem_rel_err's floor of 1e-3 of its column's scale; the run summary prints the
+    worst figure actually seen, which for most kernels is the norm-wise one: the large elements carry the error)."""
     acc_g = np.any(g["ans"][:, 1:, :] != g["ans"][:, :-1, :], axis=2)
     acc_o = np.any(o["ans"][:, 1:, :] != o["ans"][:, :-1, :], axis=2)
     assert np.array_equal(acc_g, acc_o), f"{what}: accept/reject decisions differ at {np.argwhere(acc_g != acc_o)[:5]}"
+    if elem_rtol is None:
+        elem_rtol = 1000 * rtol
     for name in ("ans", "draws", "logpost"):
         a, b = g[name], o[name]
         fin = np.isfinite(b)
         assert np.array_equal(np.isfinite(a), fin), f"{what}: {name} finiteness differs"
         assert np.array_equal(a[~fin], b[~fin], equal_nan=True), f"{what}: {name} non-finite values differ"
         err = col_rel_err(a, b)
+        eerr = elem_rel_err(a, b)
+        PARITY_LOG.append((what, name, err, eerr))
         assert err <= rtol, f"{what}: {name} max rel err {err:.3e} > {rtol}"
+        assert eerr <= elem_rtol, f"{what}: {name} max element-wise rel err {eerr:.3e} > {elem_rtol}"

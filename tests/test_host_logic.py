@@ -178,3 +178,56 @@ def test_bench_ess_estimator_on_ar1():
     x[:, :, 1] = e[:, :, 1]
     ess = bench.ess_pooled(x) / (C * T)
     assert abs(ess[0] - (1 - phi) / (1 + phi)) < 0.02 and abs(ess[1] - 1.0) < 0.1
+
+
+def test_c_gelman_window_matches_the_python_glue_and_coda():
+    """fmcmc_gelman's autoburnin window: coda only windows when start(x) < end(x)/2, to iteration
+    end/2 + 1 snapped UP to the next kept iteration; cases from the advisor's report + a sweep against the Python
+    restatement the MCMC() glue uses."""
+    import fmcmc_b200
+    L = fmcmc_b200.lib()
+    wb = L.fmcmc_gelman_window_begin
+    assert wb(1, 1, 200) == 100 and wb(1, 1, 400) == 200
+    assert wb(1, 1, 201) == 101                  # end/2 + 1 = 101.5 -> iteration 102
+    assert wb(1, 1, 5) == 3                      # rows = 5: coda keeps iterations 4, 5 (2 rows), not 3
+    assert wb(501, 1, 1000) == 250               # burnin = 500, 1000 kept rows: start 501 < 750 -> from iteration 751: 750 rows
+    assert wb(1501, 1, 1000) == 0                # start >= end/2: no window at all
+    assert wb(10, 10, 200) == 100 and wb(110, 10, 30) == 10
+    assert wb(1, 1, 2) == 0                      # start = 1 is not < end/2 = 1: both rows stay (N = 2)
+    for start in (1, 2, 7, 50, 101, 1000):
+        for thin in (1, 2, 3, 10):
+            for rows in (2, 3, 5, 10, 11, 64, 101, 1000):
+                end = start + (rows - 1) * thin
+                want = window_first_row(start, end, thin, rows, end / 2 + 1) if start < end / 2 else 0
+                assert wb(start, thin, rows) == want, (start, thin, rows)
+
+
+def test_host_sym_eigmax_against_numpy():
+    """The Gelman finish's scalar tail: Householder tridiagonalisation + Sturm bisection == numpy's eigvalsh."""
+    import ctypes as C
+    import fmcmc_b200
+    L = fmcmc_b200.lib()
+    rng = np.random.default_rng(0)
+    for p in (1, 2, 3, 5, 32, 128, 129):
+        for kind in ("spd", "indef", "diag", "rank1", "blocks"):
+            G = rng.standard_normal((p, p))
+            if kind == "spd":
+                M = G @ G.T / p
+            elif kind == "indef":
+                M = G + G.T
+            elif kind == "diag":
+                M = np.diag(rng.standard_normal(p))
+            elif kind == "rank1":
+                v = rng.standard_normal(p)
+                M = np.outer(v, v) + 1e-4 * np.eye(p)
+            else:
+                M = np.zeros((p, p))
+                h = p // 2
+                M[:h, :h] = (G @ G.T)[:h, :h]
+                M[h:, h:] = 3 * np.eye(p - h)
+            A_ = np.asfortranarray(M)
+            out = C.c_double()
+            assert L.fmcmc_host_sym_eigmax(p, A_.ctypes.data_as(C.POINTER(C.c_double)), C.byref(out)) == 0
+            want = np.linalg.eigvalsh(M)[-1]
+            scale = max(np.abs(np.linalg.eigvalsh(M)).max(), 1e-300)
+            assert abs(out.value - want) <= 1e-13 * scale, (p, kind, out.value, want)
