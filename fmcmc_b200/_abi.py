@@ -77,7 +77,7 @@ class RunSpec(C.Structure):
     _fields_ = [
         ("nsteps", C.c_int64), ("burnin", C.c_int64), ("thin", C.c_int64),
         ("nchains", C.c_int32), ("flags", C.c_uint32), ("chain_offset", C.c_int64),
-        ("initial", _dp),
+        ("initial", _dp), ("nchains_total", C.c_int64),
     ]
 
 
@@ -248,11 +248,12 @@ def marshal_stream(mode=STREAM_PHILOX, seed=0, run_index=0, logu=None, z=None, k
     return Marshalled(ss, keep)
 
 
-def marshal_run(nsteps, nchains, initial=None, burnin=0, thin=1, flags=0, chain_offset=0) -> Marshalled:
+def marshal_run(nsteps, nchains, initial=None, burnin=0, thin=1, flags=0, chain_offset=0, nchains_total=0) -> Marshalled:
     rs = RunSpec()
     keep = []
     rs.nsteps, rs.burnin, rs.thin = nsteps, burnin, thin
     rs.nchains, rs.flags, rs.chain_offset = nchains, flags, chain_offset
+    rs.nchains_total = nchains_total
     if initial is not None:
         initial = _as_f64(initial)
         keep.append(initial)

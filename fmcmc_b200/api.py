@@ -102,7 +102,7 @@ def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_i
     out = model.run(spec, nsteps, nchains, initial=initial, burnin=burnin, thin=thin, stream=stream,
                     istate=istate, dstate=dstate if dstate.size and A.state_len(spec["type"], k, kernel._kf) else None,
                     flags=A.RUN_APPEND if append else 0, chain_offset=sharding.offset if sharding else 0,
-                    want_draws=want_draws)
+                    want_draws=want_draws, nchains_total=sharding.total if sharding else 0)
     kernel.absorb_state(k)
     rep = out["report"]
     first, last = rep.first_iter, rep.last_iter
@@ -185,11 +185,14 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
                    kernel=kernel, conv_checker=conv_checker)
     info.MCMC_OUTPUT.kernel = kernel
     info.MCMC_OUTPUT.obs_sharding = obs_sharding
-    model = DeviceModel(obs_sharding.local_family(fun) if obs_sharding else fun, device=device)
     if obs_sharding:
+        model = DeviceModel(obs_sharding.local_family(fun), device=device)
         obs_sharding.attach(model, fun.n, 2 * nchains)          # kernel_ram evaluates 2 columns per chain
-    if path:
-        model.set_path(path)
+    else:
+        # X / y go to HBM (and are packed for the tensor-core path) ONCE per family object and device, like the data an
+        # R closure captures: later MCMC() calls on the same family reuse the resident copy (fun.release() frees it)
+        model = fun.device_model(device)
+    model.set_path(path or 0)
     feds = fed if isinstance(fed, (list, tuple)) else ([fed] if fed is not None else None)
     try:
         if conv_checker is None:
@@ -203,7 +206,8 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
             ans = _with_conv_checker(model, init_local, nsteps, nlocal, nchains, burnin, thin, kernel, seed, feds,
                                      names, sharding, conv_checker)
     finally:
-        model.close()
+        if obs_sharding:
+            model.close()
     info.MCMC_finalize()
     return ans
 
@@ -236,8 +240,11 @@ def _with_conv_checker(model, initial, nsteps, nlocal, nchains, burnin, thin, ke
     dr_acc = [[] for _ in range(nlocal)]
     for i, nst in enumerate(bulks, start=1):
         if i > 1:
+            # :909-911 restarts from ans[niter(ans),], the last KEPT row.  When thin divides the previous bulk that is the
+            # last row computed, which is still resident on the device (no copy); otherwise it is an earlier row
+            prev_rows = bulks[i - 2] - burnin
+            initial = None if prev_rows % thin == 0 else np.stack([c.data[-1] for c in chains])
             burnin = 0
-            initial = None                                       # continue from the device state (:909-911)
         chains, out = _run_bulk(model, initial, nst, nlocal, burnin, thin, kernel, seed, i - 1,
                                 feds[i - 1] if feds else None, names, sharding, append=device_checker)
         tmp = chains[0] if nchains == 1 else McmcList(chains)

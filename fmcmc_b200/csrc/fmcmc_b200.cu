@@ -79,9 +79,11 @@ struct fmcmc_model {
   cudaStream_t copy_stream = nullptr;        // output rows leave the device while later rows are still being computed
   std::vector<cudaEvent_t> chunk_ev;         // "kept rows of chunk q are final" (recorded on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t marks[8] = {};                 // fmcmc_event_mark
   int sm_count = 148;
   int smem_optin = 0;
   int forced_path = 0;
+  int trimmed_to = 0;     // fmcmc_model_trim: the only stepping path whose copy of X is still resident (0 = all)
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
   int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
   int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
@@ -281,6 +283,7 @@ extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   for (auto& e : m->chunk_ev) cudaEventDestroy(e);
+  for (auto& e : m->marks) if (e) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
@@ -362,8 +365,42 @@ extern "C" int fmcmc_shard_attach(fmcmc_model* m, int rank, int world, const fmc
   return FMCMC_OK;
 }
 
+// Device-clock stopwatch on the library's launch stream (bench.py: a timed region that spans several ABI calls -
+// stepping, the R-hat statistics, the host finish - is bracketed by two marks; torch.cuda.Event would only see torch's stream).
+extern "C" int fmcmc_event_mark(fmcmc_model* m, int slot) {
+  if (!m || slot < 0 || slot > 7) return FMCMC_EINVAL;
+  if (cudaSetDevice(m->device) != cudaSuccess) return FMCMC_ECUDA;
+  if (!m->marks[slot] && cudaEventCreate(&m->marks[slot]) != cudaSuccess) return FMCMC_ECUDA;
+  return cudaEventRecord(m->marks[slot], m->stream) == cudaSuccess ? FMCMC_OK : FMCMC_ECUDA;
+}
+extern "C" int fmcmc_event_elapsed_ms(fmcmc_model* m, int from, int to, double* ms) {
+  if (!m || !ms || from < 0 || from > 7 || to < 0 || to > 7 || !m->marks[from] || !m->marks[to]) return FMCMC_EINVAL;
+  if (cudaSetDevice(m->device) != cudaSuccess || cudaEventSynchronize(m->marks[to]) != cudaSuccess) return FMCMC_ECUDA;
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, m->marks[from], m->marks[to]) != cudaSuccess) return FMCMC_ECUDA;
+  *ms = t;
+  return FMCMC_OK;
+}
+
 extern "C" int fmcmc_set_path(fmcmc_model* m, int path) {
   if (!m || path < 0 || path > 4) return FMCMC_EINVAL;
+  m->forced_path = path;
+  return FMCMC_OK;
+}
+
+extern "C" int fmcmc_model_trim(fmcmc_model* m, int path, char* err, size_t errlen) {
+  if (!m || (path != 3 && path != 4)) { set_err(err, errlen, "fmcmc_model_trim: path must be 3 or 4"); return FMCMC_EINVAL; }
+  if ((path == 4 && m->xq_NS <= 0) || (path == 3 && m->xt_PB == 0)) {
+    set_err(err, errlen, "fmcmc_model_trim: path %d has not run on this model yet (its copy of X is built by the first run)", path);
+    return FMCMC_EINVAL;
+  }
+  if (m->shard_world > 1 && path != 3) { set_err(err, errlen, "observation-sharded models run path 3"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  if (path == 4) { release(m->Xt); m->xt_PB = 0; m->mp.Xt = nullptr; }
+  if (path == 3) { release(m->Xq); m->xq_NS = 0; m->xq_KB = 0; m->mp.Xq = nullptr; }
+  if (!m->borrowed) { release(m->X); m->mp.X = nullptr; }   // y stays: the Gaussian epilogue of path 4 and every head read it
+  m->trimmed_to = path;
   m->forced_path = path;
   return FMCMC_OK;
 }
@@ -456,13 +493,20 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, double* __res
 }
 // kept rows [r0, r1) only, into the same [C][keep][k] layout (streamed outputs)
 __global__ void gather_rows_range_kernel(const double* __restrict__ src, double* __restrict__ dst, int C, int k,
-                                         long long keep, long long r0, long long r1, long long burnin, long long thin) {
+                                         long long keep, long long r0, long long r1, long long burnin, long long thin,
+                                         int colmajor) {
   const long long nr = r1 - r0, total = (long long)C * nr * k;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % k);
-    const long long r = r0 + (e / k) % nr, c = e / ((long long)k * nr);
-    const long long srow = burnin + (r + 1) * thin - 1;
-    dst[((size_t)c * keep + r) * k + j] = src[((size_t)srow * C + c) * k + j];
+    if (colmajor) {  // R matrices: [chain][param][row]
+      const long long r = r0 + e % nr, j = (e / nr) % k, c = e / (nr * k);
+      const long long srow = burnin + (r + 1) * thin - 1;
+      dst[((size_t)c * k + j) * keep + r] = src[((size_t)srow * C + c) * k + j];
+    } else {
+      const int j = (int)(e % k);
+      const long long r = r0 + (e / k) % nr, c = e / ((long long)k * nr);
+      const long long srow = burnin + (r + 1) * thin - 1;
+      dst[((size_t)c * keep + r) * k + j] = src[((size_t)srow * C + c) * k + j];
+    }
   }
 }
 __global__ void append_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, long long rowlen,
@@ -843,10 +887,15 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     // narrow X: the DFMA kernel's 8 / 16-column tiers do no padded work.  Otherwise, many likelihood columns (chains):
     // the split-integer tcgen05 kernel (path 4), whose FP64 pipe only runs the family epilogue; few columns: the
     // DMMA kernel's observation-split mapping, which is HBM-bound (tiled_mma.cuh)
-    const int ncols_auto = is_ram ? 2 * C : C;
+    const long long ctot = run->nchains_total > C ? run->nchains_total : C;  // the whole job's chains: sharding must not change the path
+    const long long ncols_auto = is_ram ? 2 * ctot : ctot;
     path = (tiled_ok && data_bytes > 96 * 1024)
                ? (mp.p_x <= 16 ? 2 : ((ncols_auto > 128 && m->tiled_default != 2) ? m->tiled_many : (mp.p_x > 32 ? 3 : m->tiled_default)))
                : 1;
+  }
+  if (m->trimmed_to && path != m->trimmed_to) {
+    set_err(err, errlen, "the model was trimmed to stepping path %d (fmcmc_model_trim); this run needs path %d", m->trimmed_to, path);
+    return FMCMC_EUNSUP;
   }
   if ((path == 2 && !(lm_or_logit && mp.p_x <= 32)) || ((path == 3 || path == 4) && !tiled_ok)) {
     set_err(err, errlen, "the observation-tiled paths support gaussian_lm / logistic with p_x <= 32 (path 2) or <= 128 (paths 3, 4); got family %d, p_x %d", mp.family, mp.p_x);
@@ -856,6 +905,10 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   // kernel_ram (its adaptation consumes f itself) and short data (less averaging, and the tensor work is negligible
   // there anyway) run on 7 slices: ~1e-14 in eta, ~1e-15 relative in f.
   const int i8_NS = m->i8_slices ? m->i8_slices : ((is_ram || mp.n_total < 65536) ? 7 : 6), i8_KB = i8_kblocks(mp.p_x);
+  if (m->trimmed_to == 4 && (m->xq_NS != i8_NS || m->xq_KB != i8_KB)) {
+    set_err(err, errlen, "the model was trimmed to path 4 with %d int8 slices; this run needs %d (kernel_ram / short data use 7) and X is gone", m->xq_NS, i8_NS);
+    return FMCMC_EUNSUP;
+  }
   if (path == 4) {  // int8 slice tiles of X (once per model); X with non-finite entries cannot be sliced
     cudaError_t pe = ensure_packed_i8(m, i8_NS, i8_KB);
     if (pe == cudaErrorNotSupported) {
@@ -994,8 +1047,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     // Streamed outputs: the stepping launches are all queued first; while the GPU works through them the host copies
     // the kept rows of finished chunks (gather on a second stream + strided D2H) - only the last chunk's copy is exposed.
     {
-      const bool want_out = !(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0 && !(run->flags & FMCMC_RUN_COLMAJOR) &&
-                            (ans_out || draws_out || logpost_out);
+      const bool want_out = !(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0 && (ans_out || draws_out || logpost_out);
       const size_t row_bytes = (size_t)C * k * 8 * ((ans_out ? 1 : 0) + ((draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) ? 1 : 0)) +
                                (logpost_out ? (size_t)C * 8 : 0);
       if (want_out && row_bytes * (size_t)keep >= ((size_t)8 << 20)) {
@@ -1061,19 +1113,24 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     for (long long q = 0; q < stream_nchunks; q++) {
       const long long r0 = q * stream_chunk, r1 = std::min<long long>(keep, r0 + stream_chunk);
       CU_CHECK(cudaStreamWaitEvent(m->copy_stream, m->chunk_ev[q], 0));
-      const size_t pitch = (size_t)keep * k * 8, width = (size_t)(r1 - r0) * k * 8, off = (size_t)r0 * k;
+      // row-major [c][r][k]: chain c's rows r0..r1 are one run of (r1 - r0) k doubles, C runs a pitch of keep k apart;
+      // column-major [c][j][r]: (r1 - r0) doubles per (chain, parameter), C k runs a pitch of keep apart
+      const int cm = (run->flags & FMCMC_RUN_COLMAJOR) ? 1 : 0;
+      const size_t pitch = cm ? (size_t)keep * 8 : (size_t)keep * k * 8;
+      const size_t width = cm ? (size_t)(r1 - r0) * 8 : (size_t)(r1 - r0) * k * 8;
+      const size_t off = cm ? (size_t)r0 : (size_t)r0 * k, height = cm ? (size_t)C * k : (size_t)C;
       if (ans_out) {
-        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin);
-        CU_CHECK(cudaMemcpy2DAsync(ans_out + off, pitch, m->out_ans.as<double>() + off, pitch, width, C, cudaMemcpyDeviceToHost, m->copy_stream));
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin, cm);
+        CU_CHECK(cudaMemcpy2DAsync(ans_out + off, pitch, m->out_ans.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
       }
       if (want_draws) {
-        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin);
-        CU_CHECK(cudaMemcpy2DAsync(draws_out + off, pitch, m->out_draws.as<double>() + off, pitch, width, C, cudaMemcpyDeviceToHost, m->copy_stream));
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin, cm);
+        CU_CHECK(cudaMemcpy2DAsync(draws_out + off, pitch, m->out_draws.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
       }
       if (logpost_out) {
-        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, r0, r1, run->burnin, run->thin);
+        gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, r0, r1, run->burnin, run->thin, 0);
         CU_CHECK(cudaMemcpy2DAsync(logpost_out + r0, (size_t)keep * 8, m->out_lp.as<double>() + r0, (size_t)keep * 8, (size_t)(r1 - r0) * 8, C,
                                    cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
@@ -1191,6 +1248,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
 extern "C" int fmcmc_logpost(fmcmc_model* m, int32_t nchains, const double* theta, double* out, char* err,
                              size_t errlen) {
   if (!m || !theta || !out || nchains < 1) { set_err(err, errlen, "bad argument"); return FMCMC_EINVAL; }
+  if (m->trimmed_to) { set_err(err, errlen, "fmcmc_logpost reads the FP64 copy of X, which fmcmc_model_trim released"); return FMCMC_EUNSUP; }
   CU_CHECK(cudaSetDevice(m->device));
   const int k = m->mp.k;
   CU_CHECK(ensure(m->initial, (size_t)nchains * k * 8));

@@ -44,6 +44,21 @@ class DeviceModel:
         if rc:
             raise _lib.FmcmcError(rc, "bad path")
 
+    def mark(self, slot: int):
+        if _lib.lib().fmcmc_event_mark(self._h, slot):
+            raise _lib.FmcmcError(A.ECUDA, "fmcmc_event_mark failed")
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        v = C.c_double()
+        if _lib.lib().fmcmc_event_elapsed_ms(self._h, a, b, C.byref(v)):
+            raise _lib.FmcmcError(A.ECUDA, "fmcmc_event_elapsed_ms failed")
+        return v.value
+
+    def trim(self, path: int):
+        """fmcmc_model_trim: free the device copies of X that stepping path `path` does not read."""
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_model_trim(self._h, path, err, len(err)), err)
+
     def logpost(self, theta):
         theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
         out = np.empty(theta.shape[0])
@@ -52,7 +67,7 @@ class DeviceModel:
         return out
 
     def run(self, kernel_spec: dict, nsteps, nchains, initial=None, burnin=0, thin=1, stream=None,
-            istate=None, dstate=None, flags=0, chain_offset=0, want_draws=True, outputs=True):
+            istate=None, dstate=None, flags=0, chain_offset=0, want_draws=True, outputs=True, nchains_total=0):
         """One MCMC_without_conv_checker call (R/mcmc.R:485-838) for `nchains` chains."""
         L = _lib.lib()
         k = self.k
@@ -63,7 +78,7 @@ class DeviceModel:
         if initial is not None:
             initial = np.ascontiguousarray(np.broadcast_to(np.asarray(initial, dtype=np.float64), (nchains, k)))
         rs = A.marshal_run(nsteps, nchains, initial, burnin, thin, flags | (0 if outputs else A.RUN_NO_OUTPUT)
-                           | (0 if want_draws else A.RUN_NO_DRAWS), chain_offset)
+                           | (0 if want_draws else A.RUN_NO_DRAWS), chain_offset, nchains_total)
         if stream is None:
             stream = A.marshal_stream()
         keep = A.rows_kept(nsteps, burnin, thin)

@@ -23,9 +23,20 @@ class ChainSharding:
         self.device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if self.on_cuda \
             else torch.device("cpu")
 
-    def gelman(self, model, row_begin, row_end, free_mask, nlocal, kf, niter):
-        """partials on every GPU -> all_gather(xbar, s2) + all_reduce(wsum) -> replicated finish."""
+    def gelman(self, model, row_begin, row_end, free_mask, nlocal, kf, niter, timings=None):
+        """partials on every GPU -> all_gather(xbar, s2) + all_reduce(wsum) -> replicated finish.
+        timings: a dict that receives the wall-clock milliseconds of every stage (each closed by a device
+        synchronise, so the figures are only meaningful as a breakdown; leave None on the production path)."""
+        import time
         torch, dist = self.torch, self.dist
+        t = [time.perf_counter()]
+
+        def lap():
+            if timings is not None:
+                if self.on_cuda:
+                    torch.cuda.synchronize(self.device)
+                t.append(time.perf_counter())
+
         if self.on_cuda:
             xbar = torch.empty((nlocal, kf), dtype=torch.float64, device=self.device)
             s2 = torch.empty_like(xbar)
@@ -35,13 +46,23 @@ class ChainSharding:
         else:   # gloo (CPU tests): statistics computed by the caller-supplied model on host arrays
             xb, s, w = model.gelman_partials(row_begin, row_end, free_mask, nlocal)
             xbar, s2, ws = torch.from_numpy(xb), torch.from_numpy(s), torch.from_numpy(w.reshape(-1, order="F").copy())
+        lap()
         gx, gs = self.all_gather_rows(xbar), self.all_gather_rows(s2)
+        lap()
         dist.all_reduce(ws, op=dist.ReduceOp.SUM)
+        lap()
         if self.on_cuda:
             torch.cuda.synchronize(self.device)
-            return model.gelman_finish(niter, self.total, kf, gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), dev_in=True)
-        return model.gelman_finish(niter, self.total, kf, gx.numpy(), gs.numpy(),
-                                   ws.numpy().reshape(kf, kf, order="F"))
+            out = model.gelman_finish(niter, self.total, kf, gx.data_ptr(), gs.data_ptr(), ws.data_ptr(), dev_in=True)
+        else:
+            out = model.gelman_finish(niter, self.total, kf, gx.numpy(), gs.numpy(),
+                                      ws.numpy().reshape(kf, kf, order="F"))
+        lap()
+        if timings is not None:
+            d = [1e3 * (b - a) for a, b in zip(t[:-1], t[1:])]
+            timings.update(stats_ms=d[0], all_gather_ms=d[1], all_reduce_ms=d[2], finish_ms=d[3],
+                           all_gather_bytes_per_rank=2 * nlocal * kf * 8, all_reduce_bytes=kf * kf * 8)
+        return out
 
     def all_gather_rows(self, t):
         """all_gather of [n_r][kf] blocks with (possibly) different n_r, in rank order."""

@@ -25,6 +25,27 @@ class DeviceFamily:
             return self.p_x
         return self.n_groups + 1 + (2 if self.flags & A.MODEL_SCALES else 0)
 
+    # ---- the device-resident copy (X / y uploaded and packed once per family object and device) ----
+    def device_model(self, device: int = 0):
+        from .device import DeviceModel
+        cache = self.__dict__.setdefault("_models", {})
+        m = cache.get(device)
+        if m is None or not m._h:
+            m = cache[device] = DeviceModel(self, device=device)
+        return m
+
+    def release(self):
+        """Free the HBM copy(ies) of this family's data (also happens when the object is collected)."""
+        for m in self.__dict__.get("_models", {}).values():
+            m.close()
+        self.__dict__["_models"] = {}
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
     def marshal(self) -> A.Marshalled:
         return A.marshal_model(self.family, self.n, self.p_x, self.n_groups, self.X, self.y, self.group,
                                self.flags, self.hyper)

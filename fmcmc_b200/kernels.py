@@ -148,6 +148,17 @@ class FmcmcKernel:
         self._istate, self._dstate = ist, dst
         return ist, dst
 
+    def load_state(self, istate, dstate, nchains, k):
+        """Restore a saved per-chain state (what a previous MCMC() call left in this object - abs_iter, Sigma,
+        Mean_t_prev, mu / scale / obs_arate): the next MCMC() continues the adaptation from it."""
+        self.to_spec(k)
+        if nchains > 1 and not self.is_list:
+            self._replicate(nchains)
+        self._istate = np.ascontiguousarray(istate, dtype=np.int64).reshape(nchains, A.ISTATE_LEN).copy()
+        dlen = A.state_len(self.type, k, self._kf)
+        self._dstate = np.ascontiguousarray(dstate, dtype=np.float64).reshape(nchains, max(dlen, 1)).copy()
+        self.absorb_state(k)
+
     def absorb_state(self, k):
         """Write the device state back into user-visible attributes (R/mcmc.R:629-631)."""
         ist, dst = self._istate, self._dstate

@@ -215,6 +215,9 @@ typedef struct fmcmc_run_spec {
   int64_t chain_offset;  /* global id of local chain 0 (Philox keying)       */
   const double* initial; /* [nchains][k] row-major; NULL => continue from the
                             last state kept on the device (next bulk)        */
+  int64_t nchains_total; /* chains of the whole job over all GPUs (0 => nchains).  The stepping path is chosen
+                            from THIS count, so a chain's log-posterior bits do not depend on how many
+                            GPUs the job was sharded over                                              */
 } fmcmc_run_spec;
 
 typedef struct fmcmc_run_report {
@@ -248,6 +251,14 @@ int fmcmc_model_create(const fmcmc_model_desc* desc, int device,
 int fmcmc_model_create_device(const fmcmc_model_desc* desc_with_device_ptrs, int device,
                               fmcmc_model** out, char* err, size_t errlen);
 void fmcmc_model_free(fmcmc_model* m);
+/* Device-clock stopwatch on the library's launch stream: slots 0..7.  A timed region that spans several calls
+ * (stepping + R-hat statistics + host finish) is bracketed by two marks (bench.py). */
+int fmcmc_event_mark(fmcmc_model* m, int slot);
+int fmcmc_event_elapsed_ms(fmcmc_model* m, int from_slot, int to_slot, double* ms);
+/* Frees the device copies of X the given stepping path does not read (path 4 reads only its int8 slice tiles,
+ * path 3 its tile-major FP64 copy): at BASELINE configs[4] that returns 20.7 of 28.4 GB per GPU.  Afterwards
+ * the model runs that path only (anything else -> FMCMC_EUNSUP); borrowed device pointers are never freed. */
+int fmcmc_model_trim(fmcmc_model* m, int path, char* err, size_t errlen);
 
 /*
  * Run `nsteps` rows for `nchains` chains.  Outputs (host, caller-allocated, may

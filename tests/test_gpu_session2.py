@@ -1,0 +1,175 @@
+"""Round 2, second session: the host-facing pieces around the hot path.
+
+* streamed outputs in R's column-major layout (the layout INTEGRATION.md's .Call shim requests)
+* the HBM copy of X / y cached on the family object (MCMC() uploads and packs once, like the data an R closure
+  captures) and fmcmc_model_trim
+* the stepping path chosen from the whole job's chain count (sharding must not change a chain's bits)
+* bulks that restart from the last KEPT row when thin does not divide the bulk (R/mcmc.R:909-911, quirk D2)
+* kernel-state save / restore across MCMC() calls (FmcmcKernel.load_state)
+"""
+import numpy as np
+import pytest
+
+import fmcmc_b200 as fm
+from fmcmc_b200 import _abi as A
+from fmcmc_b200.device import DeviceModel
+
+pytestmark = pytest.mark.gpu
+
+
+def _logistic(rng, n, p):
+    X = rng.standard_normal((n, p)) / np.sqrt(p)
+    X[:, 0] = 1.0
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ rng.standard_normal(p)))).astype(float)
+    return fm.ll_logistic(X, y)
+
+
+@pytest.mark.parametrize("burnin,thin", [(0, 1), (37, 3)])
+@pytest.mark.parametrize("path", [2, 3, 4])
+def test_colmajor_streamed_outputs(path, burnin, thin):
+    """FMCMC_RUN_COLMAJOR ([chain][param][row], an R matrix per chain) takes the streamed-output route as well: same values
+    as the row-major call, which tests/test_gpu_parity.py::test_streamed_outputs_match_oracle pins on the oracle."""
+    rng = np.random.default_rng(5)
+    n, p, C, T = 2500, 8 if path == 2 else 20, 600, 400
+    fam = _logistic(rng, n, p)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.05)
+    init = rng.normal(0, 0.1, (C, p))
+    m = DeviceModel(fam)
+    m.set_path(path)
+    try:
+        r = m.run(spec, T, C, initial=init, burnin=burnin, thin=thin, stream=A.marshal_stream(A.STREAM_PHILOX, seed=3))
+        c = m.run(spec, T, C, initial=init, burnin=burnin, thin=thin, stream=A.marshal_stream(A.STREAM_PHILOX, seed=3),
+                  flags=A.RUN_COLMAJOR)
+    finally:
+        m.close()
+    keep = (T - burnin) // thin
+    assert r["report"].path == path and r["ans"].nbytes * 2 >= 8 << 20
+    for name in ("ans", "draws"):
+        cm = c[name].reshape(C, p, keep).transpose(0, 2, 1)        # the buffer holds [chain][param][row]
+        assert np.array_equal(cm, r[name]), name
+    assert np.array_equal(c["logpost"], r["logpost"])
+
+
+def test_family_keeps_its_device_copy_between_calls():
+    """MCMC() on the same family object reuses the resident X / y (and the int8 slices of path 4): one upload, same results."""
+    rng = np.random.default_rng(9)
+    fam = _logistic(rng, 70000, 24)
+    init = rng.normal(0, 0.1, (160, 24))
+    a = fm.MCMC(init, fam, 30, nchains=160, seed=5, kernel=fm.kernel_normal(scale=0.02))
+    m1 = fam.device_model(0)
+    b = fm.MCMC(init, fam, 30, nchains=160, seed=5, kernel=fm.kernel_normal(scale=0.02))
+    assert fam.device_model(0) is m1 and m1._h
+    assert np.array_equal(a.as_array(), b.as_array())
+    assert fm.MCMC_OUTPUT.report.path == 4
+    # a forced path on one call does not stick to the next one
+    c = fm.MCMC(init, fam, 30, nchains=160, seed=5, kernel=fm.kernel_normal(scale=0.02), path=3)
+    assert fm.MCMC_OUTPUT.report.path == 3
+    d = fm.MCMC(init, fam, 30, nchains=160, seed=5, kernel=fm.kernel_normal(scale=0.02))
+    assert fm.MCMC_OUTPUT.report.path == 4 and np.array_equal(d.as_array(), a.as_array())
+    assert np.allclose(c.as_array(), a.as_array(), rtol=0, atol=1e-9)
+    fam.release()
+    assert not m1._h
+    e = fm.MCMC(init, fam, 30, nchains=160, seed=5, kernel=fm.kernel_normal(scale=0.02))   # re-uploads on demand
+    assert np.array_equal(e.as_array(), a.as_array())
+    fam.release()
+
+
+def test_model_trim_keeps_the_path_and_frees_the_rest():
+    rng = np.random.default_rng(10)
+    fam = _logistic(rng, 70000, 24)
+    C, T = 160, 12
+    init = rng.normal(0, 0.1, (C, 24))
+    spec = dict(type=A.KERNEL_NORMAL, k=24, mu=0.0, scale=0.02)
+    m = DeviceModel(fam)
+    try:
+        with pytest.raises(fm.FmcmcError, match="has not run"):
+            m.trim(4)
+        full = m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
+        assert full["report"].path == 4
+        m.trim(4)
+        again = m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
+        assert again["report"].path == 4 and np.array_equal(again["ans"], full["ans"])
+        m.set_path(3)
+        with pytest.raises(fm.FmcmcError, match="trimmed"):
+            m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
+        with pytest.raises(fm.FmcmcError, match="released"):
+            m.logpost(init[:2])
+        ram = dict(type=A.KERNEL_RAM, k=24)          # kernel_ram needs 7 slices: X is gone, so this must be refused, not mis-run
+        m.set_path(4)
+        with pytest.raises(fm.FmcmcError, match="7"):
+            m.run(ram, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
+    finally:
+        m.close()
+
+
+def test_path_follows_the_whole_jobs_chain_count():
+    """64 chains of a 256-chain job (what one of 4 GPUs holds) run the path 256 chains run - and give the bits the un-sharded
+    run gives for those chains (per-call path selection made results depend on the number of GPUs)."""
+    rng = np.random.default_rng(12)
+    fam = _logistic(rng, 70000, 24)
+    C, T = 256, 10
+    init = rng.normal(0, 0.1, (C, 24))
+    spec = dict(type=A.KERNEL_NORMAL, k=24, mu=0.0, scale=0.02)
+    m = DeviceModel(fam)
+    try:
+        whole = m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=8))
+        alone = m.run(spec, T, 64, initial=init[128:192], stream=A.marshal_stream(A.STREAM_PHILOX, seed=8), chain_offset=128)
+        shard = m.run(spec, T, 64, initial=init[128:192], stream=A.marshal_stream(A.STREAM_PHILOX, seed=8), chain_offset=128,
+                      nchains_total=C)
+    finally:
+        m.close()
+    assert whole["report"].path == 4 and alone["report"].path == 3 and shard["report"].path == 4
+    assert np.array_equal(shard["ans"], whole["ans"][128:192]) and np.array_equal(shard["logpost"], whole["logpost"][128:192])
+
+
+@pytest.mark.parametrize("thin,burnin", [(3, 0), (7, 50), (4, 0)])
+def test_bulks_restart_from_the_last_kept_row(oracle, readme_data, thin, burnin):
+    """R/mcmc.R:909-911: bulk b + 1 starts from ans[niter(ans), ], the last KEPT row - an earlier row than the last one
+    computed when thin does not divide the bulk.  Fed streams, two chains, three bulks of 200 against the oracle driven
+    the way the reference's loop drives it."""
+    from helpers import r_fed_stream, readme_model
+    R = oracle.RRng
+    R.set_seed(99)
+    freq, nsteps, C = 200, 600 + burnin, 2
+    bulks = [freq + burnin, freq, freq]
+    feds, raw = [], []
+    for b in bulks:
+        logu, z = r_fed_stream(R, C, b, 3)
+        raw.append((logu, z))
+        feds.append(fm.FedStream(logu, z))
+    never = fm.convergence_gelman(freq, threshold=1.0)            # R-hat < 1 never holds: all bulks run
+    kern = fm.kernel_normal_reflective(scale=0.05, lb=[-5.0, 0.0, 0.0], ub=5.0)
+    init = np.array([[0.0, 0.0, readme_data["sd_y"]], [1.0, 1.0, 3.0]])
+    g = fm.MCMC(init, fm.ll_gaussian_lm(readme_data["X"], readme_data["y"], intercept=True, guard=False), nsteps,
+                nchains=C, thin=thin, burnin=burnin, kernel=kern, conv_checker=never, fed=feds)
+    spec = fm.kernel_normal_reflective(scale=0.05, lb=[-5.0, 0.0, 0.0], ub=5.0).to_spec(3)
+    cur, rows = init, []
+    for i, b in enumerate(bulks):
+        o = oracle.run(readme_model(readme_data, guard=False), spec, cur, b, nchains=C, burnin=burnin if i == 0 else 0,
+                       thin=thin, stream=A.marshal_stream(A.STREAM_FED, logu=raw[i][0], z=raw[i][1]), threads=2)
+        rows.append(o["ans"])
+        cur = o["ans"][:, -1, :]
+    want = np.concatenate(rows, axis=1)
+    got = g.as_array()
+    assert got.shape == want.shape
+    assert np.array_equal(np.any(got[:, 1:] != got[:, :-1], axis=2), np.any(want[:, 1:] != want[:, :-1], axis=2))
+    assert np.max(np.abs(got - want) / np.abs(want).max(axis=(0, 1))) < 1e-12
+
+
+def test_kernel_state_save_and_restore(readme_data):
+    """A kernel's per-chain state survives outside the object: load_state() into a fresh kernel continues the adaptation
+    exactly where the saved one stopped (the reference keeps it in the kernel environment, R/mcmc.R:629-631)."""
+    ll = fm.ll_gaussian_lm(readme_data["X"], readme_data["y"], intercept=True, guard=True)
+    C = 8
+    init = np.tile([3.0, 2.0, 4.0], (C, 1))
+    lb = [np.nan, np.nan, 0.0]
+    k1 = fm.kernel_adapt(warmup=50, lb=lb)
+    a = fm.MCMC(init, ll, 300, nchains=C, seed=3, kernel=k1)
+    ist, dst = k1._istate.copy(), k1._dstate.copy()
+    b = fm.MCMC(a, ll, 200, nchains=C, seed=4, kernel=k1)
+    k2 = fm.kernel_adapt(warmup=50, lb=lb)
+    k2.load_state(ist, dst, C, 3)
+    assert k2.is_list and k2[0].abs_iter == 299
+    c = fm.MCMC(a, ll, 200, nchains=C, seed=4, kernel=k2)
+    assert np.array_equal(b.as_array(), c.as_array())
+    ll.release()
