@@ -9,11 +9,19 @@ every chain on the GPU = 1024 chain-steps = 1.024e9 chain-step x observation eva
   python bench.py [--gpus N] [--steps K] [--warmup W]        our CUDA path
   python bench.py --impl reference ...                        the reference's CPU path (oracle port, all host threads)
 
-Under torchrun (N > 1) chains are sharded over ranks (weak scaling: 1024 chains per GPU, X replicated),
-no data-path collective; one Gelman-Rubin check over NCCL runs after the timed region (untimed).
+Under torchrun (N > 1) chains are sharded over ranks (weak scaling: 1024 chains per GPU, X replicated), no data-path
+collective.  The timed region is the reference's bulk loop (R/mcmc.R:901-968) in small: after every `--check-every` steps
+(default 10; the reference's default freq is 1000) the kept rows go to the sample store and ONE Gelman-Rubin check runs over
+all chains of all GPUs (statistics kernels + NCCL all_gather / all_reduce + finish), so `value` and the 1 -> 8 scaling curve
+contain the collective; `stepping_only` is the same region without the checks' time.
+`e2e` is the public call: fm.MCMC(initial, family, nsteps, nchains, kernel, conv_checker = convergence_gelman(...)) with host
+buffers (the family's X / y already resident in HBM like the data of an R closure; model creation reported apart).
+For N > 1 the line also carries `strong_scaling` (the literal BASELINE configs[2]: 1 024 chains in TOTAL, 1 024 / N per GPU);
+with the default workload it carries `cfg5` too, one GPU's share of BASELINE configs[4] (FMCMC_BENCH_CFG5=0 skips it).
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -233,9 +241,19 @@ class Workload:
         else:
             raise SystemExit(f"unknown workload {key}")
 
-    def make(self, fm, A, torch, local, rank):
-        """Returns (family, device_ptrs or None, kernel, init[C][k], host X / y or None)."""
+    def make(self, fm, A, torch, local, rank, kernel_only=False):
+        """Returns (family, device_ptrs or None, kernel, init[C][k], host X / y or None); kernel_only: a fresh kernel object."""
         C, k = self.chains, self.k
+        if kernel_only:
+            if self.key in ("cfg3", "few"):
+                return fm.kernel_adapt()
+            if self.key == "cfg4":
+                return fm.kernel_ram(lb=[np.nan] * 5 + [1e-3, 1e-3])
+            if self.key == "cfg2":
+                return fm.kernel_normal_reflective(scale=0.1, lb=[-5.0, 0.0, 0.0], ub=5.0)
+            if self.key == "cfg1":
+                return fm.kernel_normal(scale=0.1)
+            return self._kernel5()
         rng = np.random.default_rng(1000 + rank)
         if self.key in ("cfg3", "few"):
             if getattr(self, "obs_shard", None):                 # this rank's rows only (same beta* on every rank)
@@ -284,9 +302,238 @@ class Workload:
         self._keep = (Xd, yd)
         centre = np.r_[beta.cpu().numpy(), 2.0]
         lb = np.full(k, np.nan); lb[-1] = 0.0
-        kern = fm.kernel_nmirror(mu=centre, scale=2.0 / np.sqrt(n) * 0.3, lb=lb)
+        self._kernel5 = lambda: fm.kernel_nmirror(mu=centre, scale=2.0 / np.sqrt(n) * 0.3, lb=lb)
+        kern = self._kernel5()
         init = centre + rng.normal(0, 2.0 / np.sqrt(n), (C, k))
         return fam, (Xd.data_ptr(), yd.data_ptr(), None), kern, init, None
+
+
+def _never():
+    """convergence_gelman whose threshold cannot be met: every bulk runs, every check is computed."""
+    import fmcmc_b200 as fm
+    return fm.convergence_gelman(freq=1, threshold=0.0)
+
+
+def measure(wl, args, env, brief=False, chains_total=None):
+    """W warm-up + K timed steps of workload `wl` on this rank's GPU.  Returns the dict of measurements (rank-local; the caller
+    reduces over ranks).  brief: device-timed leg only (no e2e / ESS / CPU baseline)."""
+    torch, dist, fm, A = env["torch"], env["dist"], env["fm"], env["A"]
+    from fmcmc_b200.device import DeviceModel
+    world, rank, local = env["world"], env["rank"], env["local"]
+    barrier = env["barrier"]
+    obs_shard = getattr(wl, "obs_shard", None)
+    C, k = wl.chains, wl.k
+    K, W = wl.steps, args.warmup
+    ce = max(1, min(args.check_every, K)) if args.check_every > 0 else 0
+    t0 = time.perf_counter()
+    fam, dev_ptrs, kern, init0, host_data = wl.make(fm, A, torch, local, rank)
+    t_data = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    model = DeviceModel(fam, device=local, device_ptrs=dev_ptrs)      # X, y -> HBM once
+    fam.__dict__.setdefault("_models", {})[local] = model             # MCMC() finds the resident copy on the family object
+    torch.cuda.synchronize()
+    t_model = time.perf_counter() - t0
+    chain_offset = rank * C
+    ntot = chains_total or (C if obs_shard else C * world)
+    if obs_shard:
+        from fmcmc_b200.dist import ObservationSharding
+        ObservationSharding().attach(model, wl.n, 2 * C)
+        chain_offset = 0
+    spec = kern.to_spec(k)
+    dlen = A.state_len(spec["type"], k, k)
+    istate = np.zeros((C, A.ISTATE_LEN), dtype=np.int64)
+    dstate = np.zeros((C, max(dlen, 1)))
+    init = torch.empty((C, k), dtype=torch.float64).pin_memory().numpy()
+    init[:] = init0
+    seed = 20260317
+    run_idx = [0]
+
+    def stream():
+        run_idx[0] += 1
+        return A.marshal_stream(A.STREAM_PHILOX, seed=seed, run_index=run_idx[0])
+
+    def run(rows, **kw):
+        kw.setdefault("chain_offset", chain_offset)
+        kw.setdefault("nchains_total", ntot)
+        return model.run(spec, rows, C, stream=stream(), **kw)
+
+    # ---- setup (untimed): the kernel's own warm-up so the timed rows do the full adaptive step
+    # (kernel_adapt: covariance recurrence + Cholesky + mvn proposal every row) ---------------------------------
+    if args.skip_kernel_warmup or wl.key == "cfg5":
+        # cfg5: 500 warm-up rows cost minutes of GPU time; the post-warm-up mirror step does the same work per
+        # row as a warm-up one (the adaptation is O(k) per chain), so abs_iter is primed past the warm-up instead
+        istate[:, 0] = wl.kwarm + 1
+        if wl.key == "cfg5":
+            istate[:, 1] = A.STATE_INIT | (2 << A.STATE_OBS_SHIFT)
+            dstate[:, :k] = np.asarray(spec["mu"]); dstate[:, k:2 * k] = np.asarray(spec["scale"]); dstate[:, 2 * k:] = 0.4
+        run(3, initial=init, istate=istate, dstate=dstate, outputs=False)
+    else:
+        run(wl.kwarm + 3, initial=init, istate=istate, dstate=dstate, outputs=False)
+    assert wl.kwarm == 0 or istate[0, 0] > wl.kwarm
+    path = None
+    free = np.ones(k, dtype=np.uint8)
+    sh = None
+    if world > 1 and not obs_shard and ce:
+        from fmcmc_b200.dist import ChainSharding
+        sh = ChainSharding(ntot)
+        assert sh.local == C and sh.offset == chain_offset, (sh.local, C, sh.offset, chain_offset)
+
+    def region(nsteps, timings=None):
+        """The bulk loop in small: bulks of `ce` steps appended to the store, one R-hat check over ALL chains after each
+        (R/mcmc.R:901-968).  Returns (device ms over everything, [run reports], mpsrf of the last check, checks, check ms)."""
+        nb = (nsteps + ce - 1) // ce if ce else 1
+        if ce:
+            model.store_reset(C, nsteps + nb)
+        reps, mps, nchk, chk_ms = [], None, 0, 0.0
+        model.mark(0)
+        done = 0
+        while done < nsteps:
+            s = min(ce, nsteps - done) if ce else nsteps
+            o = run(s + 1, initial=None, outputs=False, flags=A.RUN_DEVICE_STATE | (A.RUN_APPEND if ce else 0))
+            reps.append(o["report"])
+            done += s
+            if ce:
+                rows = model.store_rows()
+                first = rows // 2
+                model.mark(2)
+                try:
+                    if sh is not None:
+                        _, mps = sh.gelman(model, first, rows, free, C, k, rows - first, timings=timings)
+                    else:
+                        xb, s2, ws = model.gelman_partials(first, rows, free, C)
+                        _, mps = model.gelman_finish(rows - first, C, k, xb, s2, ws)
+                except fm.FmcmcError as e:          # chol(W) may fail on a very short window: the reference warns and goes on
+                    mps = f"unavailable: {e}"
+                model.mark(3)
+                chk_ms += model.elapsed_ms(2, 3)
+                nchk += 1
+        model.mark(1)
+        return model.elapsed_ms(0, 1), reps, mps, nchk, chk_ms
+
+    # ---- W untimed warm-up steps, then K timed steps: inputs resident in HBM ---------------------------------
+    region(W)
+    barrier()
+    sampler = ClockSampler(local) if (rank == 0 and not brief) else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    tm = {}
+    dev_ms, reps, mpsrf, nchk, chk_ms = region(K, timings=tm)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = float(sum(r.device_ms for r in reps))
+    hot_l = int(sum(r.hot_launches for r in reps))
+    hot_ms = float(sum(r.hot_ms for r in reps)) / hot_l if hot_l else step_ms / K      # path 1: one fused launch per bulk
+    launches = int(sum(r.n_launches for r in reps)) + nchk * 6                          # + the 3 statistics + 3 finish kernels of a check
+    accept = int(sum(r.n_accept for r in reps)) / (C * K)
+    path = int(reps[0].path)
+    repeats = []
+    for _ in range(0 if brief else 2):                 # run-to-run spread of the same region (reported, not used for `value`)
+        barrier()
+        repeats.append(region(K)[0] / K)
+    res = dict(dev_ms=dev_ms, step_ms=step_ms, hot_ms=hot_ms, launches=launches, accept=accept, path=path, t_wall=t_wall,
+               mpsrf=mpsrf, checks=nchk, check_ms=chk_ms / max(nchk, 1), check_timings=tm, repeats=repeats,
+               t_data=t_data, t_model=t_model, C=C, k=k, K=K, ce=ce, ntot=ntot, fam=fam, host_data=host_data,
+               model=model, sampler=sampler)
+    if brief:
+        return res
+
+    # ---- e2e: the PUBLIC call, fm.MCMC(), with HOST buffers: H2D of initial + kernel state, D2H of ans / draws / logpost /
+    # state per bulk and the R-hat check after every bulk inside the timed region; X / y stay resident on the family
+    # object like the data an R closure captures (model creation: t_model above) ----------------------------------------
+    init_all = np.tile(init0, (1 if obs_shard else world, 1))[:ntot] if world > 1 else init0
+    if world > 1 and not obs_shard:                     # every rank's own initial rows, in rank order
+        parts = [None] * world
+        dist.all_gather_object(parts, np.asarray(init0))
+        init_all = np.concatenate(parts, axis=0)
+
+    def public_call(nsteps_rows, freq_rows):
+        kq = wl.make(fm, A, torch, local, rank, kernel_only=True)
+        kq.load_state(istate, dstate, C, k)             # the adaptation continues from the warm-up state
+        chk = fm.convergence_gelman(freq=freq_rows, threshold=0.0) if ce else None
+        t0 = time.perf_counter()
+        with open(os.devnull, "w") as devnull, contextlib.redirect_stderr(devnull):
+            a = fm.MCMC(init_all, fam, nsteps_rows, nchains=ntot, kernel=kq, conv_checker=chk, seed=seed + 1, device=local,
+                        shard="observations" if obs_shard else "chains")
+        torch.cuda.synchronize()
+        return a, time.perf_counter() - t0
+
+    # K steps = bulks of ce steps = ce + 1 rows each (the first row of a bulk repeats the last state, quirk D2)
+    nb = (K + ce - 1) // ce if ce else 1
+    rows_call, freq_rows = (K + nb, ce + 1) if ce else (K + 1, 0)
+    e2e_runs, h2d, d2h, ans = [], 0, 0, None
+    if obs_shard:
+        # observation sharding: MCMC(shard="observations") slices the family itself; here every rank already holds its rows, so
+        # the host-buffer call is fmcmc_run through the Python mirror (initial + kernel state in, ans / draws / logpost / state out)
+        run(W + 1, initial=init, istate=istate.copy(), dstate=dstate.copy(), outputs=True, want_draws=True)
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            m2 = run(K + 1, initial=init, istate=istate.copy(), dstate=dstate.copy(), outputs=True, want_draws=True)
+            torch.cuda.synchronize()
+            e2e_runs.append(time.perf_counter() - t0)
+        h2d, d2h = int(m2["report"].h2d_bytes), int(m2["report"].d2h_bytes)
+        res.update(e2e_sec=float(np.median(e2e_runs)), e2e_runs=e2e_runs, h2d=h2d, d2h=d2h, e2e_rows=K + 1, e2e_freq=0, e2e_bulks=1)
+        res["clocks"] = sampler.stop() if sampler else None
+        res["ess"] = ess_pooled(m2["ans"][:, 1:, :]) if rank == 0 else None
+        return res
+    public_call(rows_call, freq_rows)                   # untimed: first-use allocations (output staging, sample store, R-hat scratch)
+    for _ in range(1 if wl.key == "cfg5" else 3):       # median of 3 host-side timings; cfg5: 1 (seconds each)
+        barrier()
+        ans, sec = public_call(rows_call, freq_rows)
+        e2e_runs.append(sec)
+        h2d = int(sum(r.h2d_bytes for r in fm.MCMC_OUTPUT.reports))
+        d2h = int(sum(r.d2h_bytes for r in fm.MCMC_OUTPUT.reports))
+    res.update(e2e_sec=float(np.median(e2e_runs)), e2e_runs=e2e_runs, h2d=h2d, d2h=d2h,
+               e2e_rows=rows_call, e2e_freq=freq_rows, e2e_bulks=len(fm.MCMC_OUTPUT.reports))
+    res["clocks"] = sampler.stop() if sampler else None
+    res["ess"] = ess_pooled(ans.as_array()[:, 1:, :] if hasattr(ans, "as_array") else ans.data[None, 1:, :]) if rank == 0 else None
+    return res
+
+
+def rhat_at_scale(env, C=8192, k=128, rows=1000):
+    """convergence_gelman at BASELINE configs[4]'s size: C chains x k parameters per GPU, a 500-row window (the second half of
+    1 000 accumulated rows, coda's autoburnin).  The rows come from a cheap on-chip model of the same C and k (Gaussian LM,
+    80 observations) - the statistics kernels only see the sample store, whatever produced it.  Returns the timings of one check."""
+    torch, dist, fm, A = env["torch"], env["dist"], env["fm"], env["A"]
+    from fmcmc_b200.device import DeviceModel
+    world, rank, local = env["world"], env["rank"], env["local"]
+    rng = np.random.default_rng(77 + rank)
+    n, p = 80, k - 1
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) * 0.1 + rng.normal(0, 1.0, n)
+    fam = fm.ll_gaussian_lm(X, y, intercept=False, guard=True)
+    lb = np.full(k, np.nan); lb[-1] = 0.0
+    spec = fm.kernel_normal_reflective(scale=0.01, lb=lb).to_spec(k)
+    init = np.c_[rng.normal(0, 0.1, (C, p)), np.full(C, 1.0) + np.abs(rng.normal(0, 0.05, C))]
+    m = DeviceModel(fam, device=local)
+    try:
+        m.store_reset(C, rows)
+        m.run(spec, rows, C, initial=init, flags=A.RUN_APPEND, outputs=False, chain_offset=rank * C, nchains_total=C * world,
+              stream=A.marshal_stream(A.STREAM_PHILOX, seed=5))
+        free = np.ones(k, dtype=np.uint8)
+        first = rows // 2
+        out = {}
+        for rep in range(2):                            # the second call: buffers allocated, kernels loaded
+            tm = {}
+            env["barrier"]()
+            m.mark(4)
+            if world > 1:
+                from fmcmc_b200.dist import ChainSharding
+                _, mps = ChainSharding(C * world).gelman(m, first, rows, free, C, k, rows - first, timings=tm)
+            else:
+                t0 = time.perf_counter()
+                xb, s2, ws = m.gelman_partials(first, rows, free, C)
+                t1 = time.perf_counter()
+                _, mps = m.gelman_finish(rows - first, C, k, xb, s2, ws)
+                tm = {"stats_ms": 1e3 * (t1 - t0), "finish_ms": 1e3 * (time.perf_counter() - t1)}
+            m.mark(5)
+            out = {"ms": m.elapsed_ms(4, 5), "breakdown": tm, "mpsrf": mps, "chains_total": C * world, "k": k,
+                   "window_rows": rows - first,
+                   "note": "one convergence_gelman check: per-chain moments + centred SYRK on the device, all_gather(means, variances) + "
+                           "all_reduce(W) over NCCL when N > 1, cross-chain moments on the device, chol(W) + top eigenvalue on the host"}
+        return out
+    finally:
+        m.close()
 
 
 def main():
@@ -302,6 +549,8 @@ def main():
     ap.add_argument("--shard", default="chains", choices=["chains", "observations"],
                     help="multi-GPU mode: chains (default, weak scaling) or observations (workload few: rows of X split over "
                          "ranks, every rank runs all chains, partial sums exchanged over NVLink inside the kernels; strong scaling)")
+    ap.add_argument("--check-every", type=int, default=10,
+                    help="steps between Gelman-Rubin checks inside the timed region (0 = none; the reference's default freq is 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-kernel-warmup", action="store_true",
                     help="prime abs_iter instead of running the kernel's 500 warm-up rows (profiling runs)")
@@ -323,7 +572,6 @@ def main():
 
     import fmcmc_b200 as fm
     from fmcmc_b200 import _abi as A
-    from fmcmc_b200.device import DeviceModel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -339,131 +587,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    env = dict(torch=torch, dist=dist, fm=fm, A=A, world=world, rank=rank, local=local, barrier=barrier)
+
+    def reduce_max(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
     wl = Workload(args.workload, args)
+    wl.steps = args.steps
     obs_shard = args.shard == "observations" and world > 1
     if obs_shard:
         if args.workload != "few":
             raise SystemExit("--shard observations is for --workload few")
         wl.obs_shard = world
-    C, k = wl.chains, wl.k
-    K, W = args.steps, args.warmup
-    fam, dev_ptrs, kern, init0, host_data = wl.make(fm, A, torch, local, rank)
-    model = DeviceModel(fam, device=local, device_ptrs=dev_ptrs)      # X, y -> HBM once
-    chain_offset = rank * C
-    if obs_shard:
-        from fmcmc_b200.dist import ObservationSharding
-        ObservationSharding().attach(model, wl.n, 2 * C)
-        chain_offset = 0
-    spec = kern.to_spec(k)
-    dlen = A.state_len(spec["type"], k, k)
-    istate = np.zeros((C, A.ISTATE_LEN), dtype=np.int64)
-    dstate = np.zeros((C, max(dlen, 1)))
-    init = torch.empty((C, k), dtype=torch.float64).pin_memory().numpy()
-    init[:] = init0
-    seed = 20260317
-
-    def stream(run_index):
-        return A.marshal_stream(A.STREAM_PHILOX, seed=seed, run_index=run_index)
-
-    # ---- setup (untimed): the kernel's own warm-up so the timed rows do the full adaptive step
-    # (kernel_adapt: covariance recurrence + Cholesky + mvn proposal every row) ---------------------------------
-    run_idx = 0
-    if args.skip_kernel_warmup or wl.key == "cfg5":
-        # cfg5: 500 warm-up rows cost minutes of GPU time; the post-warm-up mirror step does the same work per
-        # row as a warm-up one (the adaptation is O(k) per chain), so abs_iter is primed past the warm-up instead
-        istate[:, 0] = wl.kwarm + 1
-        if wl.key == "cfg5":
-            istate[:, 1] = A.STATE_INIT | (2 << A.STATE_OBS_SHIFT)
-            dstate[:, :k] = np.asarray(spec["mu"]); dstate[:, k:2 * k] = np.asarray(spec["scale"]); dstate[:, 2 * k:] = 0.4
-        model.run(spec, 3, C, initial=init, stream=stream(run_idx), istate=istate, dstate=dstate,
-                  chain_offset=chain_offset, outputs=False)
-    else:
-        model.run(spec, wl.kwarm + 3, C, initial=init, stream=stream(run_idx), istate=istate, dstate=dstate,
-                  chain_offset=chain_offset, outputs=False)
-    run_idx += 1
-    assert wl.kwarm == 0 or istate[0, 0] > wl.kwarm
-
-    # ---- W untimed warm-up steps, then K timed steps: inputs resident in HBM ---------------------------------
-    model.run(spec, W + 1, C, initial=None, stream=stream(run_idx), chain_offset=chain_offset, outputs=False,
-              flags=A.RUN_DEVICE_STATE)
-    run_idx += 1
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    t_wall0 = time.perf_counter()
-    out = model.run(spec, K + 1, C, initial=None, stream=stream(run_idx), chain_offset=chain_offset, outputs=False,
-                    flags=A.RUN_DEVICE_STATE)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    run_idx += 1
-    rep = out["report"]
-    dev_ms = float(rep.device_ms)                   # CUDA events on the library's launch stream
-    hot_ms = float(rep.hot_ms) / int(rep.hot_launches) if int(rep.hot_launches) else dev_ms / K   # path 1: one fused launch
-    launches = int(rep.n_launches)
-    accept = int(rep.n_accept) / (C * K)
-    path = int(rep.path)
-
-    # ---- e2e: the public call with HOST buffers (H2D of initial + kernel state, D2H of ans / draws /
-    # logpost / state inside the timed region); data X stays cached on the device like the closure's data ----
-    # W untimed warm-up rows through the same host-buffer call (first-use allocation of the output staging)
-    model.run(spec, W + 1, C, initial=init, stream=stream(run_idx), istate=istate.copy(), dstate=dstate.copy(),
-              chain_offset=chain_offset, outputs=True, want_draws=True)
-    run_idx += 1
-    e2e_runs = []
-    for _ in range(1 if wl.key == "cfg5" else 3):      # median of 3 host-side timings (page faults / host jitter); cfg5: 1 (seconds each)
-        ist_in, dst_in = istate.copy(), dstate.copy()
-        barrier()
-        e2e_t0 = time.perf_counter()
-        m2 = model.run(spec, K + 1, C, initial=init, stream=stream(run_idx), istate=ist_in, dstate=dst_in,
-                       chain_offset=chain_offset, outputs=True, want_draws=True)
-        torch.cuda.synchronize()
-        e2e_runs.append(time.perf_counter() - e2e_t0)
-    e2e_sec = float(np.median(e2e_runs))
-    run_idx += 1
-    last = m2["ans"][:, -1, :]
-    h2d, d2h = int(m2["report"].h2d_bytes), int(m2["report"].d2h_bytes)
-
-    clocks = sampler.stop() if sampler else None
-    ess = ess_pooled(m2["ans"][:, 1:, :]) if rank == 0 else None
-
-    # ---- one Gelman-Rubin check across all chains / GPUs (untimed; NCCL all_gather + all_reduce) ------------
-    gel_ms, mpsrf = None, None
-    try:
-        model.store_reset(C, K + 1)
-        model.run(spec, K + 1, C, initial=last, stream=stream(run_idx), istate=m2["istate"], dstate=m2["dstate"],
-                  chain_offset=chain_offset, outputs=False, flags=A.RUN_APPEND)
-        free = np.ones(k, dtype=np.uint8)
-        torch.cuda.synchronize()
-        g0 = time.perf_counter()
-        if world > 1 and not obs_shard:
-            from fmcmc_b200.dist import ChainSharding
-            sh = ChainSharding(C * world)
-            _, mpsrf = sh.gelman(model, (K + 1) // 2, K + 1, free, C, k, K + 1 - (K + 1) // 2)
-        else:
-            xb, s2, ws = model.gelman_partials((K + 1) // 2, K + 1, free, C)
-            _, mpsrf = model.gelman_finish(K + 1 - (K + 1) // 2, C, k, xb, s2, ws)
-        gel_ms = 1e3 * (time.perf_counter() - g0)
-    except Exception as e:  # the R-hat of a short window may be degenerate; never fail the bench on it
-        mpsrf = f"unavailable: {e}"
+    if wl.key in ("cfg1", "cfg2", "cfg4") and args.check_every == 10:
+        args.check_every = {"cfg1": 0, "cfg2": 200, "cfg4": 100}[wl.key]    # 1 chain has no R-hat; README's own freq for cfg2
+    r = measure(wl, args, env)
+    C, k, K, W, path = r["C"], r["k"], r["K"], args.warmup, r["path"]
+    fam, host_data, model = r["fam"], r["host_data"], r["model"]
+    dev_ms, step_ms, hot_ms, e2e_sec, t_wall = reduce_max(r["dev_ms"], r["step_ms"], r["hot_ms"], r["e2e_sec"], r["t_wall"])
+    clocks, ess = r["clocks"], r["ess"]
 
     # ---- cfg2: the whole public call with the convergence checker (bulks of 200 rows, R-hat on the device after each) ----
     autostop = None
-    if wl.key == "cfg2" and rank == 0:
-        msgs = []
+    if wl.key == "cfg2" and rank == 0 and world == 1:
         chk = fm.convergence_gelman(200)
         a0 = time.perf_counter()
-        res = fm.MCMC(init0, fam, 5000, nchains=C, kernel=wl.make(fm, A, torch, local, rank)[2], conv_checker=chk, seed=11)
+        with open(os.devnull, "w") as devnull, contextlib.redirect_stderr(devnull):
+            res = fm.MCMC(wl.make(fm, A, torch, local, rank)[3], fam, 5000, nchains=C, kernel=wl.make(fm, A, torch, local, rank, kernel_only=True),
+                          conv_checker=chk, seed=11)
         a_sec = time.perf_counter() - a0
         rows = res.niter()
         autostop = {"rows_per_chain_until_converged": rows, "wall_ms": 1e3 * a_sec,
                     "chain_steps_per_s": C * rows / a_sec, "threshold": 1.1, "freq": 200,
                     "call": "MCMC(initial, ll_gaussian_lm, 5000, nchains=4, kernel_normal_reflective, conv_checker=convergence_gelman(200))"}
 
-    # ---- max over ranks ------------------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, hot_ms, e2e_sec, t_wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, hot_ms, e2e_sec, t_wall = [float(v) for v in t.cpu()]
+    # ---- strong scaling: the literal BASELINE configs[2] - 1 024 chains in TOTAL, 1 024 / N per GPU (N > 1 only) --------
+    strong = None
+    if world > 1 and wl.key == "cfg3" and not obs_shard and not args.chains and CHAINS_PER_GPU % world == 0:
+        model.close()
+        fam.release()
+        ws = Workload("cfg3", args)
+        ws.chains, ws.steps = CHAINS_PER_GPU // world, K
+        rs = measure(ws, args, env, brief=True, chains_total=CHAINS_PER_GPU)
+        s_dev, s_step, s_hot = reduce_max(rs["dev_ms"], rs["step_ms"], rs["hot_ms"])
+        rs["model"].close()
+        strong = {"chains_total": CHAINS_PER_GPU, "chains_per_gpu": ws.chains, "value": CHAINS_PER_GPU * K / (s_dev * 1e-3),
+                  "unit": "chain-steps/s", "ms_per_step": s_dev / K, "stepping_only_ms_per_step": s_step / K,
+                  "hot_kernel_ms": s_hot, "path": rs["path"], "rhat_checks_in_region": rs["checks"],
+                  "hbm_floor_ms": 1e3 * (N_OBS * 6 * 32) / (load_peaks()[0] * 1e9),
+                  "note": "same n, p, kernel; the whole job is 1 024 chains, so each GPU runs 1 024 / N of them on the SAME stepping "
+                          "path as one GPU would (fmcmc_run_spec.nchains_total); X is replicated, every GPU still streams all of it "
+                          "per step, which is what bounds this mode (hbm_floor_ms = the int8 slices of X / measured HBM bandwidth)"}
+
+    # ---- one GPU's share of BASELINE configs[4] next to the headline (weak over ranks; FMCMC_BENCH_CFG5=0 skips it) ---------
+    cfg5 = None
+    if wl.key == "cfg3" and os.environ.get("FMCMC_BENCH_CFG5", "1") != "0" and not obs_shard and not args.chains:
+        try:
+            model.close()
+            fam.release()
+            a5 = argparse.Namespace(**vars(args))
+            a5.chains, a5.n = None, None
+            w5 = Workload("cfg5", a5)
+            w5.steps = 5
+            r5 = measure(w5, a5, env, brief=True)
+            d5, st5, h5 = reduce_max(r5["dev_ms"], r5["step_ms"], r5["hot_ms"])
+            r5["model"].close()
+            ev5 = float(w5.n) * w5.chains
+            macs5 = ev5 * 21 * 32 * 4
+            sm_clock5 = (clocks or {}).get("sm_mhz") or 1965.0
+            t_t5 = macs5 / (148 * 7710.0 * sm_clock5 * 1e6)
+            t_f5 = ev5 * 3 / 32.0 / (148 * 2 * sm_clock5 * 1e6)
+            cfg5 = {"workload": w5.label, "value": w5.chains * world * w5.steps / (d5 * 1e-3), "unit": "chain-steps/s",
+                    "steps": w5.steps, "warmup": W, "ms_per_step": d5 / w5.steps, "stepping_only_ms_per_step": st5 / w5.steps,
+                    "evals_per_s": w5.chains * world * w5.steps / (d5 * 1e-3) * w5.n, "path": r5["path"],
+                    "rhat_checks_in_region": r5["checks"], "rhat_check_ms": r5["check_ms"], "rhat_check_timings": r5["check_timings"],
+                    "mpsrf": r5["mpsrf"], "chains_per_gpu": w5.chains, "chains_total": w5.chains * world,
+                    "model_create_s": r5["t_model"], "data_s": r5["t_data"],
+                    "rhat_500_row_window": rhat_at_scale(env),
+                    "roofline": {"bound": "tensor", "kernel": "tiled_loglik_i8_kernel", "launch_ms": h5,
+                                 "floor_ms": 1e3 * (t_t5 + t_f5), "frac": (t_t5 + t_f5) / (h5 * 1e-3),
+                                 "note": "two-engine floor: 21 slice pairs x 128 int8 MACs per eval / measured int8 peak + 3 FP64 slots "
+                                         "per eval / FP64 pipe rate (time-additive on B200)"}}
+        except Exception as e:                          # never lose the headline line over the secondary workload
+            cfg5 = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
@@ -506,24 +715,38 @@ def main():
                        "sharding": "observations (rows of X split over ranks; partial sums exchanged over NVLink peer memory "
                                    "inside the kernels)" if obs_shard else "chains",
                        "kernel": wl.kernel_name, "stream": "Philox4x32-10", "path": path,
+                       "rhat_check_every_steps": r["ce"],
                        "l2": (f"X ({8e-6 * n * p_x:.0f} MB) is larger than L2 (126 MB) and streamed every step: no flush needed"
                               if path != 1 else "data staged once into shared memory by TMA: on-chip by construction")},
             "evals_per_s": value * wl.n,
-            "accept_rate": accept,
+            "accept_rate": r["accept"],
+            "timed_region": {"what": f"{K} MH steps in bulks of {r['ce']} appended to the sample store + one Gelman-Rubin check over all "
+                                     f"{C * cw} chains after every bulk" if r["ce"] else f"{K} MH steps (no R-hat: one chain)",
+                             "device_ms": dev_ms, "stepping_only_ms": step_ms, "rhat_checks": r["checks"],
+                             "rhat_check_ms": r["check_ms"], "rhat_check_breakdown": r["check_timings"] or None,
+                             "mpsrf_last_check": r["mpsrf"],
+                             "repeat_ms_per_step": r["repeats"]},
+            "stepping_only": {"value": total_chain_steps / (step_ms * 1e-3), "ms_per_step": step_ms / K,
+                              "note": "the same timed region counting only the stepping kernels' CUDA-event time (what round 1 reported as `value`)"},
             "ess_per_s": float(ess.min()) * cw / e2e_sec if ess is not None else None,
             "ess": {"min_over_params": float(ess.min()), "median_over_params": float(np.median(ess)),
-                    "rows_per_chain": K, "chains": C,
+                    "rows_per_chain": r["e2e_rows"] - 1, "chains": C,
                     "method": "per-chain Geyer initial-positive-sequence, summed over rank 0's chains (x n_gpus in ess_per_s); "
                               "time = the e2e call"} if ess is not None else None,
             "e2e": {"value": C * cw * K / e2e_sec, "unit": "chain-steps/s",
-                    "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-                    "call": "fmcmc_run via the Python mirror with host numpy buffers (initial pinned): H2D initial + "
-                            "kernel state + spec, D2H ans + draws + logpost + kernel state, per bulk of K rows; median of the timed calls",
-                    "timed_calls_s": e2e_runs},
-            "gpu_launches": launches,
+                    "h2d_bytes_per_step": r["h2d"] / K, "d2h_bytes_per_step": r["d2h"] / K,
+                    "call": (f"fm.MCMC(initial, family, nsteps={r['e2e_rows']}, nchains={C * cw}, kernel=<state past warm-up>, "
+                             f"conv_checker=convergence_gelman(freq={r['e2e_freq']}, never met))" if r["ce"] else
+                             f"fm.MCMC(initial, family, nsteps={r['e2e_rows']}, nchains={C * cw}, kernel)") +
+                            f": {r['e2e_bulks']} bulk(s) = {K} MH steps with host numpy buffers - H2D initial + kernel state, D2H ans + "
+                            "draws + logpost + kernel state per bulk, R-hat check after every bulk; X / y resident on the family "
+                            "object (model_create_s apart); median of the timed calls",
+                    "timed_calls_s": r["e2e_runs"], "model_create_s": r["t_model"]},
+            "gpu_launches": r["launches"],
             "wall_ms_per_step": 1e3 * t_wall / K,
             "roofline": None, "roofline_other": None,
-            "gelman": {"mpsrf": mpsrf, "ms": gel_ms, "chains": C * cw},
+            "strong_scaling": strong,
+            "cfg5": cfg5,
             "autostop": autostop,
             "clocks": clocks,
         }
@@ -560,6 +783,16 @@ def main():
                 "fp64_slots_per_eval": fp64_instr, "fp64_floor_ms": 1e3 * t_fp64, "floor_ms": 1e3 * (t_tensor + t_fp64),
                 "frac": (t_tensor + t_fp64) / (hot_ms * 1e-3),
                 "note": "floor = int8 MACs / measured int8 peak + FP64 epilogue slots / FP64 pipe rate (time-additive on B200)"}
+            # the same launch against a roof that does NOT depend on how this kernel splits its operands: the algorithm's own
+            # p_x multiply-adds per eval on the int8 tensor pipe at its measured peak + the algorithm's epilogue flops (6 logistic /
+            # 4 Gaussian, transcendentals not counted) at the measured FP64 peak.  Adding slices or instructions cannot raise it.
+            t_alg = evals * p_x / int8_peak + evals * (wl.flops_per_eval - 2 * p_x) / (peak_tf * 1e12)
+            line["roofline_algorithmic"] = {
+                "floor_ms": 1e3 * t_alg, "frac": t_alg / (hot_ms * 1e-3),
+                "fp64_flops_over_fp64_peak": achieved_tf / peak_tf,
+                "note": "implementation-independent: p_x MACs per eval / measured int8 peak + (flops_per_eval - 2 p_x) epilogue flops per "
+                        "eval / measured FP64 peak (transcendentals not counted); fp64_flops_over_fp64_peak = all algorithmic flops as if "
+                        "on the FP64 pipe (exceeds 1: the contraction has left that pipe)"}
             if wl.bound != "hbm":
                 # The headline `roofline` of a path-4 launch: the algorithmic FP64 flops against the rate at which they would
                 # complete with BOTH engines at their measured peaks (int8 tensor pipe for the exact slice products, FP64 pipe
@@ -597,8 +830,8 @@ def main():
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    model.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes
 OK, EINVAL, ENAN, ECUDA, ENOMEM, ENOTPD, EUNSUP, ENANRATIO = range(8)
@@ -30,7 +30,7 @@ STATE_HAS_MEAN, STATE_INIT, STATE_OBS_SHIFT = 1, 2, 2
 
 STREAM_PHILOX, STREAM_FED = 0, 1
 
-RUN_NO_DRAWS, RUN_COLMAJOR, RUN_APPEND, RUN_NO_OUTPUT, RUN_DEVICE_STATE = 1, 2, 4, 8, 16
+RUN_NO_DRAWS, RUN_COLMAJOR, RUN_APPEND, RUN_NO_OUTPUT, RUN_DEVICE_STATE, RUN_KEEP_STATE = 1, 2, 4, 8, 16, 32
 
 DBL_MAX = float(np.finfo(np.float64).max)
 
@@ -77,7 +77,7 @@ class RunSpec(C.Structure):
     _fields_ = [
         ("nsteps", C.c_int64), ("burnin", C.c_int64), ("thin", C.c_int64),
         ("nchains", C.c_int32), ("flags", C.c_uint32), ("chain_offset", C.c_int64),
-        ("initial", _dp), ("nchains_total", C.c_int64),
+        ("initial", _dp), ("nchains_total", C.c_int64), ("out_rows_total", C.c_int64), ("out_row_offset", C.c_int64),
     ]
 
 
@@ -248,12 +248,14 @@ def marshal_stream(mode=STREAM_PHILOX, seed=0, run_index=0, logu=None, z=None, k
     return Marshalled(ss, keep)
 
 
-def marshal_run(nsteps, nchains, initial=None, burnin=0, thin=1, flags=0, chain_offset=0, nchains_total=0) -> Marshalled:
+def marshal_run(nsteps, nchains, initial=None, burnin=0, thin=1, flags=0, chain_offset=0, nchains_total=0,
+                out_rows_total=0, out_row_offset=0) -> Marshalled:
     rs = RunSpec()
     keep = []
     rs.nsteps, rs.burnin, rs.thin = nsteps, burnin, thin
     rs.nchains, rs.flags, rs.chain_offset = nchains, flags, chain_offset
     rs.nchains_total = nchains_total
+    rs.out_rows_total, rs.out_row_offset = out_rows_total, out_row_offset
     if initial is not None:
         initial = _as_f64(initial)
         keep.append(initial)

@@ -6,13 +6,14 @@ libfmcmcb200.so.  `fun` must be a DeviceFamily: closures are a TypeError, never 
 from __future__ import annotations
 
 import sys
+import threading
 import warnings
 
 import numpy as np
 
 from . import _abi as A
 from . import mcmc_info as info
-from .coda import Mcmc, McmcList, append_chains
+from .coda import Mcmc, McmcList, append_chains, append_mcpar
 from .convergence import (GelmanChecker, convergence_data_flush, convergence_msg_get, convergence_msg_set)
 from .device import DeviceModel
 from .dist import current_sharding
@@ -67,8 +68,10 @@ class FedStream:
 
 
 def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_index, fed, names,
-              sharding, append, want_draws=True):
-    """MCMC_without_conv_checker, R/mcmc.R:485-838 (chains fan out on the device, not in a loop)."""
+              sharding, append, want_draws=True, resident_state=False, into=None, keep_state=False):
+    """MCMC_without_conv_checker, R/mcmc.R:485-838 (chains fan out on the device, not in a loop).
+    resident_state: the kernel state of the previous bulk is still on the device and stays there (no upload, no download,
+    no write-back into the kernel objects: the caller fetches it once after its last bulk)."""
     if nchains < 1:
         raise ValueError("`nchains` must be an integer greater than 1.")
     if burnin >= nsteps:
@@ -99,16 +102,27 @@ def _run_bulk(model, initial, nsteps, nchains, burnin, thin, kernel, seed, run_i
     obs = getattr(info.MCMC_OUTPUT, "obs_sharding", None)
     if obs is not None:
         obs.dist.barrier()                                       # fmcmc_run is collective when observation-sharded
+    flags = (A.RUN_APPEND if append else 0) | (A.RUN_DEVICE_STATE if resident_state else 0) | \
+        (A.RUN_KEEP_STATE if keep_state else 0)
     out = model.run(spec, nsteps, nchains, initial=initial, burnin=burnin, thin=thin, stream=stream,
                     istate=istate, dstate=dstate if dstate.size and A.state_len(spec["type"], k, kernel._kf) else None,
-                    flags=A.RUN_APPEND if append else 0, chain_offset=sharding.offset if sharding else 0,
-                    want_draws=want_draws, nchains_total=sharding.total if sharding else 0)
-    kernel.absorb_state(k)
+                    flags=flags, chain_offset=sharding.offset if sharding else 0,
+                    want_draws=want_draws, nchains_total=sharding.total if sharding else 0, into=into)
+    if not resident_state and not keep_state:
+        kernel.absorb_state(k)
     rep = out["report"]
-    first, last = rep.first_iter, rep.last_iter
-    chains = [Mcmc(out["ans"][c], start=first, end=last, thin=thin, varnames=names) for c in range(nchains)]
     info.MCMC_OUTPUT.report = rep
-    return chains, out
+    info.MCMC_OUTPUT.reports.append(rep)
+    # every chain is a view of the one [chain][row][param] array the device filled
+    return McmcList.from_array(out["ans"], rep.first_iter, rep.last_iter, thin, names), out
+
+
+def _fetch_state(model, kernel, nchains):
+    """The resident kernel state -> the kernel objects (R/mcmc.R:629-631), once per MCMC() call."""
+    k = model.k
+    istate, dstate = kernel.state_arrays(nchains, k)
+    model.fetch_state(istate, dstate if dstate.size and A.state_len(kernel.type, k, kernel._kf) else None)
+    kernel.absorb_state(k)
 
 
 def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel=None, multicore=False,
@@ -198,10 +212,9 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
         if conv_checker is None:
             chains, out = _run_bulk(model, init_local, nsteps, nlocal, burnin, thin, kernel, seed, 0,
                                     feds[0] if feds else None, names, sharding, append=False)
-            for c in range(nlocal):
-                info.MCMC_OUTPUT.logpost[c] = out["logpost"][c]
-                info.MCMC_OUTPUT.draws[c] = out["draws"][c]
-            ans = chains[0] if nchains == 1 else McmcList(chains)
+            info.MCMC_OUTPUT.logpost = list(out["logpost"])      # per-chain views of the arrays the device filled
+            info.MCMC_OUTPUT.draws = list(out["draws"])
+            ans = chains[0] if nchains == 1 else chains
         else:
             ans = _with_conv_checker(model, init_local, nsteps, nlocal, nchains, burnin, thin, kernel, seed, feds,
                                      names, sharding, conv_checker)
@@ -235,45 +248,100 @@ def _with_conv_checker(model, initial, nsteps, nlocal, nchains, burnin, thin, ke
         model.store_reset(nlocal, total_keep)
     fixed = np.broadcast_to(np.asarray(getattr(kernel, "fixed", False), dtype=bool), (model.k,))
     free_mask = (~fixed).astype(np.uint8)
-    ans, converged, i = None, False, 0
-    lp_acc = [[] for _ in range(nlocal)]
-    dr_acc = [[] for _ in range(nlocal)]
+    converged, i = False, 0
+    # ONE set of host arrays for the whole call, filled bulk after bulk by the device (append_chains, R/mcmc.R:947, without
+    # re-copying what is already there).  Their pages are touched by a helper thread while the first bulk computes: a fresh
+    # anonymous mapping costs ~0.35 ms per MB of page faults when the copy engine is the first to write it.
+    k = model.k
+    ans_all = np.empty((nlocal, total_keep, k))
+    draws_all = np.empty((nlocal, total_keep, k))
+    lp_all = np.empty((nlocal, total_keep))
+    toucher = None
+    if ans_all.nbytes >= (4 << 20):
+        toucher = threading.Thread(target=_populate, args=((ans_all, draws_all, lp_all),), daemon=True)
+        toucher.start()
+    mcpars, done = [], 0
+
+    def so_far():
+        """append_chains of every bulk so far as an array-backed mcmc.list (views of the rows filled so far)."""
+        start, end, th = append_mcpar(mcpars)
+        return McmcList.from_array(ans_all[:, :done], start, end, th, names)
+
     for i, nst in enumerate(bulks, start=1):
+        resident = False
         if i > 1:
             # :909-911 restarts from ans[niter(ans),], the last KEPT row.  When thin divides the previous bulk that is the
             # last row computed, which is still resident on the device (no copy); otherwise it is an earlier row
             prev_rows = bulks[i - 2] - burnin
-            initial = None if prev_rows % thin == 0 else np.stack([c.data[-1] for c in chains])
+            initial = None if prev_rows % thin == 0 else np.ascontiguousarray(ans_all[:, done - 1, :])
             burnin = 0
+            resident = True                                      # the kernel state never leaves the device between bulks
         chains, out = _run_bulk(model, initial, nst, nlocal, burnin, thin, kernel, seed, i - 1,
-                                feds[i - 1] if feds else None, names, sharding, append=device_checker)
-        tmp = chains[0] if nchains == 1 else McmcList(chains)
-        ans = append_chains(ans, tmp) if ans is not None else tmp  # :947
-        for c in range(nlocal):
-            lp_acc[c].append(out["logpost"][c])
-            dr_acc[c].append(out["draws"][c])
+                                feds[i - 1] if feds else None, names, sharding, append=device_checker,
+                                resident_state=resident, into=(ans_all, draws_all, lp_all, done),
+                                keep_state=(i == 1 and len(bulks) > 1))
+        done += out["ans"].shape[1]
+        mcpars.append(chains.mcpar)
         convergence_msg_set()
+        steps = sum(bulks[:i])
+        nsamp = done
         if device_checker:
+            # the device checker reads the sample store: it only needs the shape of what has been accumulated
             conv_checker._device_ctx = (model, nlocal, free_mask, sharding)
-            x = ans if isinstance(ans, McmcList) else McmcList([ans])
-            converged = conv_checker(x.select(np.where(free_mask)[0]) if nchains > 1 else ans)
+            converged = conv_checker(_Accumulated(append_mcpar(mcpars), nsamp, int(free_mask.sum()),
+                                                  sharding.total if sharding else nlocal))
             conv_checker._device_ctx = None
         else:                                                    # arbitrary checker: host path on the samples
             free = np.where(free_mask)[0]
-            converged = conv_checker(ans.select(free) if isinstance(ans, McmcList) else ans[:, free])
+            ans = so_far()
+            converged = conv_checker(ans.select(free) if nchains > 1 else ans[0][:, free])
         msg = convergence_msg_get()
-        steps = sum(bulks[:i])
-        nsamp = ans.niter()
         if converged:
             _message("Convergence has been reached with ", steps, " steps. ", "" if msg is None else msg + " ",
                      "(", nsamp, " final count of samples).")
             break
         _message("No convergence yet (steps count: ", steps, "). ", "" if msg is None else msg + " ",
                  "Trying with the next bulk.")
+    if toucher is not None:
+        toucher.join()
+    ans = so_far()
     if i == len(bulks) and not converged:
         _message("No convergence reached after ", sum(bulks[:i]), " steps (", ans.niter(),
                  " final count of samples).")
-    for c in range(nlocal):
-        info.MCMC_OUTPUT.logpost[c] = np.concatenate(lp_acc[c])
-        info.MCMC_OUTPUT.draws[c] = np.concatenate(dr_acc[c])
-    return ans
+    if len(bulks) > 1:
+        _fetch_state(model, kernel, nlocal)                      # write-back once (R/mcmc.R:629-631)
+    info.MCMC_OUTPUT.logpost = list(lp_all[:, :done])
+    info.MCMC_OUTPUT.draws = list(draws_all[:, :done])
+    return ans[0] if nchains == 1 else ans
+
+
+def _populate(arrays):
+    """Fault the pages of freshly allocated arrays in, writable, WITHOUT touching their contents
+    (madvise(MADV_POPULATE_WRITE), Linux >= 5.14): safe while the device is already copying into them.  Best effort."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        libc.madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        for a in arrays:
+            lo = a.ctypes.data & ~4095
+            hi = (a.ctypes.data + a.nbytes + 4095) & ~4095
+            libc.madvise(lo, hi - lo, 23)                        # MADV_POPULATE_WRITE; an error (old kernel) is ignored
+    except Exception:
+        pass
+
+
+class _Accumulated:
+    """What convergence_gelman's device path needs to know about the accumulated mcmc.list: its shape and mcpar (the
+    samples themselves are in the device's sample store)."""
+
+    def __init__(self, mcpar, niter, nvar, nchain):
+        self.mcpar, self._niter, self._nvar, self._nchain = mcpar, niter, nvar, nchain
+
+    def niter(self):
+        return self._niter
+
+    def nvar(self):
+        return self._nvar
+
+    def nchain(self):
+        return self._nchain

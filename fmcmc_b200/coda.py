@@ -16,6 +16,14 @@ class Mcmc:
         self.end = int(end) if end is not None else self.start + (n - 1) * self.thin
         self.varnames = list(varnames) if varnames is not None else [f"par{i + 1}" for i in range(self.data.shape[1])]
 
+    @classmethod
+    def _view(cls, data, start, end, thin, varnames):
+        """A chain that is a VIEW of one slab of a [chain][row][param] array (no copy, shared names): what an mcmc.list of
+        thousands of chains is made of."""
+        self = object.__new__(cls)
+        self.data, self.start, self.end, self.thin, self.varnames = data, start, end, thin, varnames
+        return self
+
     # coda accessors
     @property
     def mcpar(self):
@@ -52,6 +60,20 @@ class Mcmc:
 
 
 class McmcList(list):
+    _arr = None          # [nchains][niter][nvar] when the chains are views of one array (from_array)
+
+    @classmethod
+    def from_array(cls, arr, start=1, end=None, thin=1, varnames=None):
+        """mcmc.list over one [nchains][niter][nvar] array: every chain is a view, as_array() / select() / append_chains
+        work on the whole block at once (65 536 chains are one array, not 65 536 objects' worth of copies)."""
+        arr = np.asarray(arr, dtype=np.float64)
+        start, thin = int(start), int(thin)
+        end = int(end) if end is not None else start + (arr.shape[1] - 1) * thin
+        names = list(varnames) if varnames is not None else [f"par{i + 1}" for i in range(arr.shape[2])]
+        self = cls(Mcmc._view(arr[c], start, end, thin, names) for c in range(arr.shape[0]))
+        self._arr = arr
+        return self
+
     def nchain(self):
         return len(self)
 
@@ -71,9 +93,12 @@ class McmcList(list):
 
     def as_array(self):
         """[nchains][niter][nvar]"""
-        return np.stack([m.data for m in self])
+        return self._arr if self._arr is not None else np.stack([m.data for m in self])
 
     def select(self, cols):
+        if self._arr is not None:
+            cols = np.atleast_1d(np.arange(self.nvar())[cols])
+            return McmcList.from_array(self._arr[:, :, cols], *self.mcpar, [self.varnames[c] for c in cols])
         return McmcList([m[:, cols] for m in self])
 
     def __repr__(self):
@@ -92,6 +117,10 @@ def append_chains(*objs):
         if len(nch) != 1:
             raise ValueError("All mcmc.list objects must have the same number of chains. The passed objects have "
                              + ", ".join(str(o.nchain()) for o in objs) + " respectively.")
+        if all(o._arr is not None for o in objs) and len({o._arr.shape[2] for o in objs}) == 1 \
+                and len({o[0].thin for o in objs}) == 1:
+            start, end, thin = append_mcpar([o.mcpar for o in objs])
+            return McmcList.from_array(np.concatenate([o._arr for o in objs], axis=1), start, end, thin, objs[0].varnames)
         return McmcList([append_chains(*[o[i] for o in objs]) for i in range(objs[0].nchain())])
     thin = [o.thin for o in objs]
     if len(set(thin)) != 1:
@@ -107,6 +136,16 @@ def append_chains(*objs):
         end[i] = end[i] + thin[i] - start[i]
     data = np.concatenate([o.data for o in objs], axis=0)
     return Mcmc(data, start=start[0], end=sum(end), thin=thin[0], varnames=objs[0].varnames)
+
+
+def append_mcpar(mcpars):
+    """mcpar of rbind-ed consecutive runs (R/append_chains.R:113-142): start of the first, the ends renumbered."""
+    start = [m[0] for m in mcpars]
+    end = [m[1] for m in mcpars]
+    thin = mcpars[0][2]
+    for i in range(1, len(mcpars)):                   # R/append_chains.R:128
+        end[i] = end[i] + thin - start[i]
+    return start[0], sum(end), thin
 
 
 def __len_mcmc(self):

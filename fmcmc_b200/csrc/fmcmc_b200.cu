@@ -90,7 +90,7 @@ struct fmcmc_model {
   // run buffers (grow-only)
   DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
       errbuf, nacc, spec, fed_logu, fed_z, initial, partial, out_ans, out_draws, out_lp, tmp;
-  int state_nchains = 0, state_k = 0, state_type = 0;  // shape of cur_theta / kernel state (valid after a run)
+  int state_nchains = 0, state_k = 0, state_type = 0, state_kf = 0;  // shape of cur_theta / kernel state (valid after a run)
   std::vector<cudaEvent_t> hot_ev;
   // sample store (append_chains): [rows][C][k]
   DevBuf store;
@@ -762,6 +762,12 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   }
 
   long long h2d = 0, d2h = 0;
+  // host output arrays may be larger than this call's rows (a bulk loop fills ONE set of arrays, bulk after bulk)
+  const long long host_rows = run->out_rows_total > 0 ? run->out_rows_total : keep, host_off = run->out_rows_total > 0 ? run->out_row_offset : 0;
+  if (host_off < 0 || host_off + keep > host_rows) {
+    set_err(err, errlen, "out_row_offset %lld + %lld kept rows exceed out_rows_total %lld", host_off, (long long)keep, host_rows);
+    return FMCMC_EINVAL;
+  }
   const bool dev_state = (run->flags & FMCMC_RUN_DEVICE_STATE) != 0;
   if (dev_state && (m->state_nchains != C || m->state_k != k || m->state_type != ks->type)) {
     set_err(err, errlen, "FMCMC_RUN_DEVICE_STATE: the model holds no kernel state of this shape");
@@ -1115,24 +1121,27 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       CU_CHECK(cudaStreamWaitEvent(m->copy_stream, m->chunk_ev[q], 0));
       // row-major [c][r][k]: chain c's rows r0..r1 are one run of (r1 - r0) k doubles, C runs a pitch of keep k apart;
       // column-major [c][j][r]: (r1 - r0) doubles per (chain, parameter), C k runs a pitch of keep apart
+      // (the host arrays may hold out_rows_total >= keep rows per chain, this call's rows starting at out_row_offset: hpitch)
       const int cm = (run->flags & FMCMC_RUN_COLMAJOR) ? 1 : 0;
       const size_t pitch = cm ? (size_t)keep * 8 : (size_t)keep * k * 8;
+      const size_t hpitch = cm ? (size_t)host_rows * 8 : (size_t)host_rows * k * 8;
       const size_t width = cm ? (size_t)(r1 - r0) * 8 : (size_t)(r1 - r0) * k * 8;
       const size_t off = cm ? (size_t)r0 : (size_t)r0 * k, height = cm ? (size_t)C * k : (size_t)C;
+      const size_t hoff = cm ? (size_t)(host_off + r0) : (size_t)(host_off + r0) * k;
       if (ans_out) {
         gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin, cm);
-        CU_CHECK(cudaMemcpy2DAsync(ans_out + off, pitch, m->out_ans.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
+        CU_CHECK(cudaMemcpy2DAsync(ans_out + hoff, hpitch, m->out_ans.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
       }
       if (want_draws) {
         gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, r0, r1, run->burnin, run->thin, cm);
-        CU_CHECK(cudaMemcpy2DAsync(draws_out + off, pitch, m->out_draws.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
+        CU_CHECK(cudaMemcpy2DAsync(draws_out + hoff, hpitch, m->out_draws.as<double>() + off, pitch, width, height, cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
       }
       if (logpost_out) {
         gather_rows_range_kernel<<<gb, 256, 0, m->copy_stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, r0, r1, run->burnin, run->thin, 0);
-        CU_CHECK(cudaMemcpy2DAsync(logpost_out + r0, (size_t)keep * 8, m->out_lp.as<double>() + r0, (size_t)keep * 8, (size_t)(r1 - r0) * 8, C,
-                                   cudaMemcpyDeviceToHost, m->copy_stream));
+        CU_CHECK(cudaMemcpy2DAsync(logpost_out + host_off + r0, (size_t)host_rows * 8, m->out_lp.as<double>() + r0, (size_t)keep * 8,
+                                   (size_t)(r1 - r0) * 8, C, cudaMemcpyDeviceToHost, m->copy_stream));
         launches += 1;
       }
       CU_CHECK(cudaStreamSynchronize(m->copy_stream));
@@ -1190,6 +1199,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   m->state_nchains = C;
   m->state_k = k;
   m->state_type = ks->type;
+  m->state_kf = kf;
 
   const int gblocks = m->sm_count * 4;
   if (run->flags & FMCMC_RUN_APPEND) {
@@ -1206,39 +1216,60 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   }
   if (!(run->flags & FMCMC_RUN_NO_OUTPUT) && keep > 0 && !stream_nchunks) {
     const int colmajor = (run->flags & FMCMC_RUN_COLMAJOR) ? 1 : 0;
+    // device staging [c][keep][k] (or [c][k][keep]) -> host arrays of host_rows rows per chain, this call's at host_off
+    const size_t dpitch = colmajor ? (size_t)keep * 8 : (size_t)keep * k * 8;
+    const size_t hpitch = colmajor ? (size_t)host_rows * 8 : (size_t)host_rows * k * 8;
+    const size_t hoff = colmajor ? (size_t)host_off : (size_t)host_off * k, height = colmajor ? (size_t)C * k : (size_t)C;
     if (ans_out) {
       CU_CHECK(ensure(m->out_ans, (size_t)C * keep * k * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.ans, m->out_ans.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
-      CU_CHECK(cudaMemcpyAsync(ans_out, m->out_ans.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      CU_CHECK(cudaMemcpy2DAsync(ans_out + hoff, hpitch, m->out_ans.p, dpitch, dpitch, height, cudaMemcpyDeviceToHost, m->stream));
       d2h += (long long)C * keep * k * 8;
       launches += 1;
     }
     if (draws_out && !(run->flags & FMCMC_RUN_NO_DRAWS)) {
       CU_CHECK(ensure(m->out_draws, (size_t)C * keep * k * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.draws, m->out_draws.as<double>(), C, k, keep, run->burnin, run->thin, colmajor);
-      CU_CHECK(cudaMemcpyAsync(draws_out, m->out_draws.p, (size_t)C * keep * k * 8, cudaMemcpyDeviceToHost, m->stream));
+      CU_CHECK(cudaMemcpy2DAsync(draws_out + hoff, hpitch, m->out_draws.p, dpitch, dpitch, height, cudaMemcpyDeviceToHost, m->stream));
       d2h += (long long)C * keep * k * 8;
       launches += 1;
     }
     if (logpost_out) {
       CU_CHECK(ensure(m->out_lp, (size_t)C * keep * 8));
       gather_rows_kernel<<<gblocks, 256, 0, m->stream>>>(rb.logpost, m->out_lp.as<double>(), C, 1, keep, run->burnin, run->thin, 0);
-      CU_CHECK(cudaMemcpyAsync(logpost_out, m->out_lp.p, (size_t)C * keep * 8, cudaMemcpyDeviceToHost, m->stream));
+      CU_CHECK(cudaMemcpy2DAsync(logpost_out + host_off, (size_t)host_rows * 8, m->out_lp.p, (size_t)keep * 8, (size_t)keep * 8, C,
+                                 cudaMemcpyDeviceToHost, m->stream));
       d2h += (long long)C * keep * 8;
       launches += 1;
     }
   }
-  if (state && state->istate && !dev_state) {
+  const bool keep_state = (run->flags & FMCMC_RUN_KEEP_STATE) != 0;
+  if (state && state->istate && !dev_state && !keep_state) {
     CU_CHECK(cudaMemcpyAsync(state->istate, m->istate.p, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyDeviceToHost, m->stream));
     d2h += (long long)C * FMCMC_ISTATE_LEN * 8;
   }
-  if (state && state->dstate && dlen && !dev_state) {
+  if (state && state->dstate && dlen && !dev_state && !keep_state) {
     CU_CHECK(cudaMemcpyAsync(state->dstate, m->dstate.p, (size_t)C * dlen * 8, cudaMemcpyDeviceToHost, m->stream));
     d2h += (long long)C * dlen * 8;
   }
   CU_CHECK(cudaStreamSynchronize(m->stream));
   CU_CHECK(cudaGetLastError());
   if (report) { report->n_launches = launches; report->h2d_bytes = h2d; report->d2h_bytes = d2h; }
+  return FMCMC_OK;
+}
+
+// The kernel state the last fmcmc_run left resident on the device -> host (FMCMC_RUN_DEVICE_STATE bulks neither upload
+// nor download it; the bulk loop fetches it ONCE, after its last bulk, for the write-back of R/mcmc.R:629-631).
+extern "C" int fmcmc_kernel_state_fetch(fmcmc_model* m, fmcmc_kernel_state* state, char* err, size_t errlen) {
+  if (!m || !state || !state->istate) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  if (m->state_nchains < 1) { set_err(err, errlen, "the model holds no kernel state yet (no fmcmc_run so far)"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  const int C = m->state_nchains;
+  const long long dlen = fmcmc_kernel_state_len(m->state_type, m->state_k, m->state_kf);
+  CU_CHECK(cudaMemcpyAsync(state->istate, m->istate.p, (size_t)C * FMCMC_ISTATE_LEN * 8, cudaMemcpyDeviceToHost, m->stream));
+  if (state->dstate && dlen > 0)
+    CU_CHECK(cudaMemcpyAsync(state->dstate, m->dstate.p, (size_t)C * dlen * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
   return FMCMC_OK;
 }
 
@@ -1495,6 +1526,41 @@ extern "C" int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchain
     psrf[a] = sqrt(df_adj * ((N - 1.0) / N + (1.0 + 1.0 / M) * (1.0 / N) * (b / w)));
   }
   return status;
+}
+
+// rm_invariant's pooled moments of THIS GPU's part of the store (every stored row, local chains, free parameters):
+// out = (count, mean, M2 = sum (x - mean)^2).  Several GPUs: combine the triples with Chan's formula (dist.py).
+extern "C" int fmcmc_store_pooled(fmcmc_model* m, const uint8_t* free_mask, double* out, char* err, size_t errlen) {
+  if (!m || !out) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  const long long rows = m->store_rows;
+  const int C = m->store_C, k = m->store_k;
+  if (rows < 1 || C < 1) { set_err(err, errlen, "the sample store is empty"); return FMCMC_EINVAL; }
+  std::vector<int> fidx;
+  for (int j = 0; j < k; j++)
+    if (!free_mask || free_mask[j]) fidx.push_back(j);
+  const int kf = (int)fidx.size();
+  if (kf < 1) { set_err(err, errlen, "no free parameters"); return FMCMC_EINVAL; }
+  CU_CHECK(cudaSetDevice(m->device));
+  CU_CHECK(ensure(m->g_mask, kf * sizeof(int)));
+  CU_CHECK(cudaMemcpyAsync(m->g_mask.p, fidx.data(), kf * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  const long long total = rows * (long long)C * kf;
+  const int nb = (int)std::min<long long>((total + 255) / 256, 8LL * m->sm_count);
+  CU_CHECK(ensure(m->g_wpart, (size_t)nb * 3 * 8));
+  gelman_pooled_kernel<<<nb, 256, 0, m->stream>>>(m->store.as<double>(), C, k, rows, m->g_mask.as<int>(), kf, m->g_wpart.as<double>());
+  CU_CHECK(cudaGetLastError());
+  std::vector<double> part((size_t)nb * 3);
+  double shift = 0.0;
+  CU_CHECK(cudaMemcpyAsync(part.data(), m->g_wpart.p, part.size() * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaMemcpyAsync(&shift, m->store.as<double>() + fidx[0], 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  double n = 0.0, sd = 0.0, sdd = 0.0;
+  for (int b = 0; b < nb; b++) { n += part[(size_t)b * 3]; sd += part[(size_t)b * 3 + 1]; sdd += part[(size_t)b * 3 + 2]; }
+  if (n != (double)total) { set_err(err, errlen, "internal: pooled count %.0f != %lld", n, total); return FMCMC_ECUDA; }
+  out[0] = n;
+  out[1] = shift + sd / n;
+  out[2] = sdd - sd * sd / n;
+  if (out[2] < 0.0) out[2] = 0.0;
+  return FMCMC_OK;
 }
 
 // 0-based first store row kept by coda::gelman.diag's autoburnin on an mcmc.list with mcpar = (start, start + (rows-1) thin, thin):

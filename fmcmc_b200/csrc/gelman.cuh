@@ -238,3 +238,36 @@ __global__ void gelman_between_kernel(const double* __restrict__ xbar, long long
     bp[e] = s;
   }
 }
+
+// rm_invariant (R/convergence.R:169-186, quirk D9) tests ONE number: stats::sd() of every element of rbind(chains) - all
+// rows accumulated so far, all (free) parameters, all chains - squared, against 1e-10.  One streaming pass over the store:
+// every block sums d = x - shift and d^2 with the same shift (the store's first element) over a grid-strided range;
+// part[block] = (count, sum d, sum d^2); the host adds the blocks in order.
+__global__ void __launch_bounds__(256)
+gelman_pooled_kernel(const double* __restrict__ store, int C, int k, long long rows, const int* __restrict__ fidx, int kf,
+                     double* __restrict__ part) {
+  __shared__ double red[32];
+  const double shift = store[fidx[0]];
+  const long long per_row = (long long)C * kf, total = rows * per_row;
+  double sd = 0.0, sdd = 0.0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = e / per_row, r = e - t * per_row;
+    const int c = (int)(r / kf), a = (int)(r - (long long)c * kf);
+    const double d = store[((size_t)t * C + c) * k + fidx[a]] - shift;
+    sd += d;
+    sdd = fma(d, d, sdd);
+  }
+  const double bs = block_sum_256(sd, red), bq = block_sum_256(sdd, red);
+  if (threadIdx.x == 0) {
+    const long long first = blockIdx.x * (long long)blockDim.x;
+    long long cnt = 0;
+    if (first < total) {  // elements this block visited: threads first .. first + 255 of every grid stride
+      const long long stride = (long long)gridDim.x * blockDim.x;
+      const long long full = (total - first) / stride, rem = (total - first) - full * stride;
+      cnt = full * blockDim.x + (rem < (long long)blockDim.x ? rem : (long long)blockDim.x);
+    }
+    part[blockIdx.x * 3 + 0] = (double)cnt;
+    part[blockIdx.x * 3 + 1] = bs;
+    part[blockIdx.x * 3 + 2] = bq;
+  }
+}

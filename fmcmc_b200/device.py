@@ -67,8 +67,11 @@ class DeviceModel:
         return out
 
     def run(self, kernel_spec: dict, nsteps, nchains, initial=None, burnin=0, thin=1, stream=None,
-            istate=None, dstate=None, flags=0, chain_offset=0, want_draws=True, outputs=True, nchains_total=0):
-        """One MCMC_without_conv_checker call (R/mcmc.R:485-838) for `nchains` chains."""
+            istate=None, dstate=None, flags=0, chain_offset=0, want_draws=True, outputs=True, nchains_total=0, into=None):
+        """One MCMC_without_conv_checker call (R/mcmc.R:485-838) for `nchains` chains.
+        into = (ans, draws or None, logpost, row_offset): write this call's kept rows into rows row_offset.. of caller-owned
+        arrays [nchains][rows_total][k] / [nchains][rows_total] (the bulk loop fills one set of arrays, bulk after bulk);
+        the returned dict then holds views of those rows."""
         L = _lib.lib()
         k = self.k
         ks = A.marshal_kernel(kernel_spec)
@@ -77,17 +80,27 @@ class DeviceModel:
         st = A.marshal_state(istate, dstate)
         if initial is not None:
             initial = np.ascontiguousarray(np.broadcast_to(np.asarray(initial, dtype=np.float64), (nchains, k)))
-        rs = A.marshal_run(nsteps, nchains, initial, burnin, thin, flags | (0 if outputs else A.RUN_NO_OUTPUT)
-                           | (0 if want_draws else A.RUN_NO_DRAWS), chain_offset, nchains_total)
-        if stream is None:
-            stream = A.marshal_stream()
         keep = A.rows_kept(nsteps, burnin, thin)
+        rows_total = row_off = 0
         ans = draws = lp = None
-        if outputs:
+        if into is not None:
+            ans, draws, lp, row_off = into
+            cm = bool(flags & A.RUN_COLMAJOR)                    # [chain][param][row] instead of [chain][row][param]
+            rows_total = ans.shape[2 if cm else 1]
+            if not want_draws:
+                draws = None
+            for a in (ans, draws, lp):
+                if a is not None and not (a.flags.c_contiguous and a.dtype == np.float64 and a.shape[0] == nchains):
+                    raise ValueError("`into` arrays must be C-contiguous float64 with one block per chain")
+        elif outputs:
             ans = np.empty((nchains, keep, k))
             lp = np.empty((nchains, keep))
             if want_draws:
                 draws = np.empty((nchains, keep, k))
+        rs = A.marshal_run(nsteps, nchains, initial, burnin, thin, flags | (0 if (outputs or into is not None) else A.RUN_NO_OUTPUT)
+                           | (0 if want_draws else A.RUN_NO_DRAWS), chain_offset, nchains_total, rows_total, row_off)
+        if stream is None:
+            stream = A.marshal_stream()
         rep = A.RunReport()
         err = _lib.errbuf()
         rc = L.fmcmc_run(self._h, rs.byref(), ks.byref(), st.byref(), stream.byref(),
@@ -98,7 +111,18 @@ class DeviceModel:
             e = _lib.FmcmcError(rc, err.value.decode(errors="replace"))
             e.report = rep
             raise e
+        if into is not None:
+            sl = slice(row_off, row_off + keep)
+            ans, lp = (ans[:, :, sl] if cm else ans[:, sl]), lp[:, sl]
+            if draws is not None:
+                draws = draws[:, :, sl] if cm else draws[:, sl]
         return dict(ans=ans, draws=draws, logpost=lp, report=rep, istate=istate, dstate=dstate)
+
+    def fetch_state(self, istate, dstate=None):
+        """fmcmc_kernel_state_fetch: the resident kernel state of the last run -> the given host arrays."""
+        st = A.marshal_state(istate, dstate)
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_kernel_state_fetch(self._h, st.byref(), err, len(err)), err)
 
     # ---- observation sharding across GPUs (include/fmcmc_b200.h: fmcmc_shard_*) -----------------
     def shard_alloc(self, world: int, max_cols: int, n_total: int) -> "A.ShardHandles":
@@ -119,6 +143,14 @@ class DeviceModel:
 
     def store_rows(self) -> int:
         return _lib.lib().fmcmc_store_rows(self._h)
+
+    def store_pooled(self, free_mask):
+        """(count, mean, M2) of every element of this GPU's part of the store: rm_invariant's pooled variance (D9)."""
+        mask = np.ascontiguousarray(free_mask, dtype=np.uint8)
+        out = np.empty(3)
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_store_pooled(self._h, A.ptr(mask, C.POINTER(C.c_uint8)), A.ptr(out), err, len(err)), err)
+        return out
 
     def gelman_partials(self, row_begin, row_end, free_mask, nchains, out=None):
         """Host arrays by default; with `out=(xbar_ptr, s2_ptr, wsum_ptr)` raw device pointers."""

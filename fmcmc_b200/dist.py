@@ -64,6 +64,14 @@ class ChainSharding:
                            all_gather_bytes_per_rank=2 * nlocal * kf * 8, all_reduce_bytes=kf * kf * 8)
         return out
 
+    def pooled_variance(self, model, free_mask):
+        """rm_invariant's number over ALL chains (R/convergence.R:171-173): every rank's (count, mean, M2) of its part of
+        the store, gathered and merged in rank order with Chan's pairwise formula."""
+        mine = [float(v) for v in model.store_pooled(free_mask)]
+        box = [None] * self.world
+        self.dist.all_gather_object(box, mine)
+        return combine_pooled(box)
+
     def all_gather_rows(self, t):
         """all_gather of [n_r][kf] blocks with (possibly) different n_r, in rank order."""
         torch, dist = self.torch, self.dist
@@ -78,6 +86,20 @@ class ChainSharding:
         out = torch.empty((self.world * mx, t.shape[1]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, pad)
         return torch.cat([out[r * mx:r * mx + n] for r, n in enumerate(self.counts)], dim=0)
+
+
+def combine_pooled(triples):
+    """[(count, mean, M2), ...] -> the variance (divisor n - 1) of the union, merged left to right."""
+    n, mean, m2 = 0.0, 0.0, 0.0
+    for nb, mb, qb in triples:
+        if nb <= 0:
+            continue
+        tot = n + nb
+        delta = mb - mean
+        m2 = m2 + qb + delta * delta * n * nb / tot
+        mean = mean + delta * nb / tot
+        n = tot
+    return m2 / (n - 1.0) if n > 1 else 0.0
 
 
 def current_sharding(nchains_total: int):

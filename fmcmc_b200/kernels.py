@@ -169,16 +169,18 @@ class FmcmcKernel:
         for c, kc in enumerate(targets):
             kc.abs_iter = int(ist[c, 0])
             kc.nerrors = int(ist[c, 2])
+            # views of the state arrays, not copies: like the fields of the R environment they show the live state, and a
+            # run over 65 536 chains does not duplicate 65 536 covariance matrices to expose them
             if self.type == A.KERNEL_ADAPT:
-                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F").copy()
-                kc.Mean_t_prev = dst[c, kf * kf:kf * kf + kf].copy() if ist[c, 1] & A.STATE_HAS_MEAN else None
+                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F")
+                kc.Mean_t_prev = dst[c, kf * kf:kf * kf + kf] if ist[c, 1] & A.STATE_HAS_MEAN else None
             elif self.type == A.KERNEL_RAM:
-                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F").copy()
+                kc.Sigma = dst[c, :kf * kf].reshape(kf, kf, order="F")
             elif self.type in (A.KERNEL_NMIRROR, A.KERNEL_UMIRROR):
-                kc.mu = dst[c, :k].copy()
-                kc.scale = dst[c, k:2 * k].copy()
+                kc.mu = dst[c, :k]
+                kc.scale = dst[c, k:2 * k]
                 kind = (int(ist[c, 1]) >> A.STATE_OBS_SHIFT) & 3
-                kc.obs_arate = None if kind == 0 else (float(dst[c, 2 * k]) if kind == 1 else dst[c, 2 * k:3 * k].copy())
+                kc.obs_arate = None if kind == 0 else (float(dst[c, 2 * k]) if kind == 1 else dst[c, 2 * k:3 * k])
 
     def __repr__(self):
         if self.is_list:

@@ -17,6 +17,7 @@ class _Output:
         self.t0 = self.t1 = None
         self.kernel = None
         self.report = None
+        self.reports = []         # one fmcmc_run_report per bulk (device time, launches, bytes copied)
 
 
 MCMC_OUTPUT = _Output()

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define FMCMC_ABI_VERSION 2
+#define FMCMC_ABI_VERSION 3
 
 /* ---- status codes -------------------------------------------------------- */
 enum {
@@ -206,6 +206,9 @@ typedef struct fmcmc_stream_spec {
                                    uploaded nor downloaded; the state the previous fmcmc_run left
                                    on this model is used (bulk loop, R/mcmc.R:901-947)       */
 
+#define FMCMC_RUN_KEEP_STATE 32u /* upload `state` as usual but do not download it afterwards: the first bulk of a loop whose
+                                   later bulks run with FMCMC_RUN_DEVICE_STATE (fmcmc_kernel_state_fetch at the end)   */
+
 typedef struct fmcmc_run_spec {
   int64_t nsteps;        /* rows, including the initial state (R semantics)  */
   int64_t burnin;
@@ -218,6 +221,11 @@ typedef struct fmcmc_run_spec {
   int64_t nchains_total; /* chains of the whole job over all GPUs (0 => nchains).  The stepping path is chosen
                             from THIS count, so a chain's log-posterior bits do not depend on how many
                             GPUs the job was sharded over                                              */
+  int64_t out_rows_total; /* 0: ans / draws / logpost hold exactly rows_kept rows per chain.  > 0: they hold this many
+                            rows per chain ([nchains][out_rows_total][k], or [nchains][k][out_rows_total] with
+                            FMCMC_RUN_COLMAJOR) and this call writes rows out_row_offset .. out_row_offset + rows_kept:
+                            a bulk loop fills ONE set of arrays bulk after bulk (append_chains without the copies)  */
+  int64_t out_row_offset;
 } fmcmc_run_spec;
 
 typedef struct fmcmc_run_report {
@@ -275,6 +283,11 @@ int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_kernel_spec
 
 int64_t fmcmc_rows_kept(int64_t nsteps, int64_t burnin, int64_t thin);
 
+/* Downloads the kernel state the last fmcmc_run left on the device (shapes of that run).  A bulk loop runs its bulks
+ * after the first with FMCMC_RUN_DEVICE_STATE - no state traffic at all - and calls this once at the end for the
+ * write-back into the kernel objects (R/mcmc.R:629-631). */
+int fmcmc_kernel_state_fetch(fmcmc_model* m, fmcmc_kernel_state* state, char* err, size_t errlen);
+
 /* Force a stepping path (0 = auto, 1 = chain-resident, 2 = observation-tiled DFMA kernel,
  * 3 = observation-tiled FP64 tensor-core (DMMA) kernel, 4 = observation-tiled split-integer kernel: X.Theta
  * exact on int8 slices on the tcgen05 tensor cores, FP64 pipe for the log-density only).  Auto picks 1 for data
@@ -325,6 +338,11 @@ int fmcmc_gelman_finish(fmcmc_model* m, int64_t niter, int64_t nchains_total, in
 int fmcmc_gelman(fmcmc_model* m, const uint8_t* free_mask, int64_t start_iter, int64_t thin, double* psrf,
                  double* mpsrf, int64_t* niter_used, char* err, size_t errlen);
 int64_t fmcmc_gelman_window_begin(int64_t start_iter, int64_t thin, int64_t rows);
+
+/* rm_invariant (R/convergence.R:169-186, quirk D9): the reference tests ONE pooled number, sd(rbind(all chains))^2 over every
+ * accumulated row and every (free) parameter, against 1e-10.  out[3] = (count, mean, M2 = sum (x - mean)^2) of this GPU's part
+ * of the store; several GPUs combine the triples (Chan et al.) - fmcmc_b200/dist.py does. */
+int fmcmc_store_pooled(fmcmc_model* m, const uint8_t* free_mask, double* out, char* err, size_t errlen);
 
 /* Host-only helper of the Gelman finish, exported for the CPU test-suite: largest eigenvalue of a symmetric
  * p x p matrix (col-major; Householder tridiagonalisation + Sturm bisection). */

@@ -173,3 +173,69 @@ def test_kernel_state_save_and_restore(readme_data):
     c = fm.MCMC(a, ll, 200, nchains=C, seed=4, kernel=k2)
     assert np.array_equal(b.as_array(), c.as_array())
     ll.release()
+
+
+@pytest.mark.parametrize("colmajor", [False, True])
+@pytest.mark.parametrize("path,C,T", [(1, 40, 61), (3, 600, 300)])
+def test_bulks_write_into_one_set_of_host_arrays(path, C, T, colmajor):
+    """fmcmc_run_spec.out_rows_total / out_row_offset: three bulks fill ONE caller-owned array each for ans / draws / logpost
+    (direct and streamed copy routes, both layouts) - the same numbers three separate calls return."""
+    rng = np.random.default_rng(15)
+    n, p = (300, 6) if path == 1 else (2500, 20)
+    fam = _logistic(rng, n, p)
+    spec = dict(type=A.KERNEL_ADAPT, k=p, mu=0.0, warmup=15, freq=1, eps=1e-4)
+    init = rng.normal(0, 0.1, (C, p))
+    fl = A.RUN_COLMAJOR if colmajor else 0
+    dl = A.state_len(A.KERNEL_ADAPT, p, p)
+    m = DeviceModel(fam)
+    m.set_path(path)
+    try:
+        sep, ist, dst = [], np.zeros((C, A.ISTATE_LEN), dtype=np.int64), np.zeros((C, dl))
+        for b in range(3):
+            sep.append(m.run(spec, T, C, initial=init if b == 0 else None, istate=ist, dstate=dst, flags=fl,
+                             burnin=7 if b == 0 else 0, thin=2, stream=A.marshal_stream(A.STREAM_PHILOX, seed=4, run_index=b)))
+        keeps = [s_["logpost"].shape[1] for s_ in sep]
+        R = sum(keeps) + 5                                       # a few spare rows: never written
+        shape = (C, p, R) if colmajor else (C, R, p)
+        ans, drw, lp = np.full(shape, -7.0), np.full(shape, -7.0), np.full((C, R), -7.0)
+        ist, dst, off = np.zeros((C, A.ISTATE_LEN), dtype=np.int64), np.zeros((C, dl)), 0
+        for b in range(3):
+            o = m.run(spec, T, C, initial=init if b == 0 else None, istate=ist, dstate=dst, flags=fl, into=(ans, drw, lp, off),
+                      burnin=7 if b == 0 else 0, thin=2, stream=A.marshal_stream(A.STREAM_PHILOX, seed=4, run_index=b))
+            assert o["report"].path == path
+            want = (lambda a: a.reshape(C, p, keeps[b])) if colmajor else (lambda a: a)   # a separate call returns the raw buffer
+            assert np.array_equal(o["ans"], want(sep[b]["ans"])) and np.array_equal(o["draws"], want(sep[b]["draws"]))
+            assert np.array_equal(o["logpost"], sep[b]["logpost"])
+            off += keeps[b]
+        tail = ans[:, :, off:] if colmajor else ans[:, off:]
+        assert np.all(tail == -7.0) and np.all(lp[:, off:] == -7.0)
+        with pytest.raises(fm.FmcmcError, match="out_row_offset"):
+            m.run(spec, T, C, initial=init, flags=fl, into=(ans, drw, lp, R - 3), stream=A.marshal_stream(A.STREAM_PHILOX, seed=4))
+    finally:
+        m.close()
+
+
+def test_mcmc_with_checker_returns_views_of_one_array(readme_data):
+    """The bulk loop accumulates into one array: the mcmc.list, get_logpost() and get_draws() are views of it, the kernel
+    state is fetched once at the end, and nothing differs from running the bulks by hand."""
+    ll = fm.ll_gaussian_lm(readme_data["X"], readme_data["y"], intercept=True, guard=True)
+    C = 6
+    init = np.tile([3.0, 2.0, 4.0], (C, 1)) + np.linspace(0, 0.5, C)[:, None]
+    kern = fm.kernel_adapt(warmup=40, lb=[np.nan, np.nan, 0.0])
+    ans = fm.MCMC(init, ll, 900, nchains=C, seed=21, kernel=kern, conv_checker=fm.convergence_gelman(300, threshold=0.0))
+    assert ans.niter() == 900 and ans.as_array().shape == (C, 900, 3)
+    assert fm.get_logpost()[0].shape == (900,) and fm.get_draws()[2].shape == (900, 3)
+    assert kern[0].abs_iter == 3 * 299 and kern[C - 1].Sigma.shape == (3, 3)
+    # by hand: three runs of 300 rows, each restarting from the previous last row, one kernel object
+    k2 = fm.kernel_adapt(warmup=40, lb=[np.nan, np.nan, 0.0])
+    parts, cur = [], init
+    m = ll.device_model(0)
+    spec = k2.to_spec(3)
+    ist, dst = np.zeros((C, A.ISTATE_LEN), dtype=np.int64), np.zeros((C, A.state_len(A.KERNEL_ADAPT, 3, 3)))
+    for b in range(3):
+        o = m.run(spec, 300, C, initial=cur, istate=ist, dstate=dst, stream=A.marshal_stream(A.STREAM_PHILOX, seed=21, run_index=b))
+        parts.append(o["ans"])
+        cur = o["ans"][:, -1, :]
+    assert np.array_equal(ans.as_array(), np.concatenate(parts, axis=1))
+    assert np.array_equal(kern[3].Sigma, dst[3, :9].reshape(3, 3, order="F")) and kern[3].abs_iter == ist[3, 0]
+    ll.release()
