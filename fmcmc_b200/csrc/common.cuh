@@ -55,6 +55,7 @@ struct ModelParams {
   const double* sp_tab;  // logistic: (S_k, G_k) softplus table in global memory (softplus.h)
   const double* sp_tab4; // logistic: the 128-per-unit table of the split-integer kernel (softplus.h, FM_SP4_*)
   const double* sp_tab8; // logistic: its 256-per-unit table: (tau, T) of log(2 cosh(a / 2)) (softplus.h, fm_lcosh_table8_fill)
+  const double* sp_tab8m; // the same grid with T mean-corrected for the degree-3 core (softplus.h, fm_lcosh_table8m_fill)
 };
 
 // Per-run device buffers shared by both paths.

@@ -70,7 +70,7 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group, sp_tab, sp_tab4, sp_tab8, Xt, Xq, xq_bad, xq_aux;
+  DevBuf X, y, group, sp_tab, sp_tab4, sp_tab8, sp_tab8m, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
   int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (6; 7 for kernel_ram and for n < 65536)
@@ -244,6 +244,10 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
     MC(ensure(m->sp_tab8, tab8.size() * 8));
     MC(cudaMemcpy(m->sp_tab8.p, tab8.data(), tab8.size() * 8, cudaMemcpyHostToDevice));
     mp.sp_tab8 = m->sp_tab8.as<double>();
+    fm_lcosh_table8m_fill(tab8.data());
+    MC(ensure(m->sp_tab8m, tab8.size() * 8));
+    MC(cudaMemcpy(m->sp_tab8m.p, tab8.data(), tab8.size() * 8, cudaMemcpyHostToDevice));
+    mp.sp_tab8m = m->sp_tab8m.as<double>();
   }
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
@@ -268,7 +272,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->sp_tab4, &m->sp_tab8, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->sp_tab4, &m->sp_tab8, &m->sp_tab8m, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,

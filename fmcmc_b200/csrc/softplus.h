@@ -284,6 +284,38 @@ FM_HD double fm_lcosh_tab8_core(double d, double tau, double T) {
   const double Q = fma(d, P, tau);
   return fma(d, Q, T);
 }
+// ---- the degree-3 variant (the hot loop of the split-integer kernel when every chain of a CTA stays inside the table) ----
+// Dropping the d^4 term u (1/24 - u/4) d^4 saves two FP64 instructions of nine.  What it leaves out is at most 7.6e-14 (a = 0,
+// |d| = 1/512), EVEN in d, and the remainder of a sum over many observations is what matters: its mean over the uniformly
+// distributed remainder d, c4 delta^4 / 5, is folded into the table's T (fm_lcosh_table8m_fill), so the error per evaluation
+// is zero-mean with rms <= 2e-14 - fifty times below the kernel's own slicing error in eta (~1e-12 tau per evaluation) - and
+// averages out like it: ~3e-17 relative in a log-posterior over 1e6 observations (tests/test_softplus_cpu.py).
+static inline void fm_lcosh_table8m_fill(double* tab) {
+  const long double delta4_5 = powl(0.5L / FM_SP8_H, 4) / 5.0L;
+  for (int k = 0; k < FM_SP8_ENTRIES; k++) {
+    const long double x = (long double)k / FM_SP8_H;
+    const long double E = expl(-x);
+    const long double tau = 0.5L - E / (1.0L + E);
+    const long double u = 0.25L - tau * tau;
+    tab[2 * k] = (double)tau;
+    tab[2 * k + 1] = (double)(0.5L * x + log1pl(E) + u * (1.0L / 24.0L - u / 4.0L) * delta4_5);
+  }
+}
+FM_HD double fm_lcosh_tab8m_core(double d, double tau, double T) {
+  const double u = fma(-tau, tau, 0.25);
+  const double i3 = fma(d, tau * (-1.0 / 3.0), 0.5);
+  const double P = u * i3;
+  const double Q = fma(d, P, tau);
+  return fma(d, Q, T);
+}
+FM_HD double fm_lcosh_tab8m(double a, const double* tab) {   // host reference: 0 <= a < 40
+  const double MAGICH = 26388279066624.0;
+  const double t2 = a + MAGICH;
+  uint32_t k = (uint32_t)fm_double_to_bits(t2);
+  k = k > (uint32_t)(FM_SP8_ENTRIES - 1) ? (uint32_t)(FM_SP8_ENTRIES - 1) : k;
+  const double d = a + (MAGICH - t2);
+  return fm_lcosh_tab8m_core(d, tab[2 * k], tab[2 * k + 1]);
+}
 // reference composition (host tests): 0 <= a <= 40
 FM_HD double fm_lcosh_tab8(double a, const double* tab) {
   const double MAGICH = 26388279066624.0;  // 1.5 * 2^44: ulp = 1/256

@@ -45,6 +45,18 @@
 
 #define I8_CHAINS 128
 #define I8_MAX_EPI_WARPS 16
+// Epilogue warps in two groups, one per accumulator set: the four warps of a TMEM lane quarter are split 2 + 2, a group
+// only visits the blocks of ITS set and each of its warps takes 16 of the block's 32 columns (two chunks of 8) instead of
+// 8 columns of every block.  The per-block overhead - barrier wait, fences, release, loop control: ~25 warp instructions
+// - is then paid once per 16 evaluations instead of once per 8, in a kernel whose time is its issued instructions.
+// (B200, cfg3, per launch: un-grouped 1.663 ms; grouped 1.680; grouped with the two-chunk loop unrolled 1.651 - and at
+// K = 128, where the tensor pipe binds, 181.2 against 186.1 ms.)
+#ifndef I8_GROUPED
+#define I8_GROUPED 1
+#endif
+#if I8_GROUPED && !defined(I8_CC_UNROLL)
+#define I8_CC_UNROLL 1
+#endif
 
 template <int NS, int KB>
 struct I8Geom {
@@ -429,6 +441,21 @@ __device__ __forceinline__ double i8_lcosh_core(double d, double tau, double Tac
   const double Q = fma(d, P, tau);
   return fma(d, Q, Tacc);
 }
+// degree-3 core on the mean-corrected table (softplus.h, fm_lcosh_table8m_fill): 7 FP64 instructions including the accumulation
+__device__ __forceinline__ double i8_lcosh3_core(double d, double tau, double Tacc) {
+  const double u = fma(-tau, tau, 0.25);
+  const double i3 = fma(d, tau * (-1.0 / 3.0), 0.5);
+  const double P = u * i3;
+  const double Q = fma(d, P, tau);
+  return fma(d, Q, Tacc);
+}
+__device__ __forceinline__ void i8_logistic_lcosh3_fast(double t, double csc, double& acc_h, const double2* __restrict__ tab) {
+  constexpr double MAGICH = i8_magic_h<2>();
+  const double t2 = fma(fabs(t), csc, MAGICH);
+  const double d = fma(fabs(t), csc, MAGICH - t2);
+  const double2 tt = tab[__double2loint(t2)];
+  acc_h = i8_lcosh3_core(d, tt.x, acc_h + tt.y);
+}
 // FAST: the warp's chains bound |eta| <= 39.9 over ALL observations (i8 prologue: min(sum_j |theta_j| max_i |x_ij|,
 // |theta|_2 max_i |x_i|_2)), so round(256 |eta|) indexes the table as it is - no clamp of any kind: 12 FP64 + 7 (merge) +
 // address + LDS.128 per evaluation.
@@ -524,15 +551,10 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], EW);
+      mbar_init(&acc_empty[b], I8_GROUPED ? EW / 2 : EW);
     }
     mbar_init(tab_bar, 1);
     mbar_fence_init();
-    if (FAMILY == FMCMC_FAMILY_LOGISTIC) {  // softplus table: one bulk copy (up to 160 KB), overlapped with the Theta slicing
-      constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_bytes<NS, KB>(FAMILY);
-      mbar_expect_tx(tab_bar, TAB_BYTES);
-      bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? mp.sp_tab8 : mp.sp_tab4, TAB_BYTES, tab_bar);
-    }
   }
   if (warp == W_MMA) {  // the allocating warp also frees
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -573,7 +595,16 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const bool eta_small = __all_sync(FM_FULL, eth + 5 + (KB == 1 ? 0 : (KB == 2 ? 1 : 2)) <= 25);
   // level-2 table: |eta| <= 39.9 for every observation and every chain of the warp (idle lanes: 0; NaN fails the test) -
   // the un-clamped lcosh epilogue applies (the slicing error of eta, <= 2^-35 thmax, is far inside the 0.1 margin)
-  const bool eta_in_table = __all_sync(FM_FULL, !th_bad && fmin(eb1, sqrt(eb2 * mp.i8_cmax[p_x])) <= 39.9);
+  const bool in_table = !th_bad && fmin(eb1, sqrt(eb2 * mp.i8_cmax[p_x])) <= 39.9;
+  const bool eta_in_table = __all_sync(FM_FULL, in_table);
+  // ... and for every chain of the CTA: the hot loop runs the degree-3 core on the mean-corrected copy of the table
+  // (softplus.h).  The table is chosen per CTA because it is shared: one bulk copy (160 KB), overlapped with the Theta slicing.
+  const bool cta_in_table = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2) ? __all_sync(FM_FULL, __syncthreads_and(in_table) != 0) : false;  // (the vote tells ptxas it is warp-uniform)
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC && tid == 0) {
+    constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_bytes<NS, KB>(FAMILY);
+    mbar_expect_tx(tab_bar, TAB_BYTES);
+    bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? (cta_in_table ? mp.sp_tab8m : mp.sp_tab8) : mp.sp_tab4, TAB_BYTES, tab_bar);
+  }
   if (tid < I8_CHAINS) {
     for (int kb = 0; kb < KB; kb++) {
       uint32_t w[NS][8];
@@ -668,6 +699,10 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     double acc = 0.0, acc2 = 0.0;
     uint32_t blk = 0;
     long long it = 0;
+    constexpr bool GRP = I8_GROUPED != 0 && EW == 16;
+    constexpr int CWG = GRP ? 2 * CW : CW;          // columns of a block owned by this warp
+    const int grp = h & 1;                          // GRP: the accumulator set this warp serves
+    const int hcol = GRP ? (h >> 1) * CWG : h * CW;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
       const double* ymeta = mp.y + tile * G::TO;  // L1-resident broadcast loads (Gaussian / non-binary logistic only)
       const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
@@ -677,10 +712,15 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll 1
       for (int bpair = 0; bpair < G::NBLK; bpair += UNR) {
       const uint32_t par = (blk >> 1) & 1u;
+      // GRP with an even number of blocks per stage: ONE body per pair - this group's block of the pair (its set is a per-warp
+      // constant, so barrier and TMEM addresses are loop-invariant uniform values); otherwise every block is visited and the
+      // other group's are skipped
+      constexpr int NBB = (GRP && UNR == 2) ? 1 : UNR;
 #pragma unroll
-      for (int bb = 0; bb < UNR; bb++, blk++) {
-        const int b = bpair + bb;
-        const uint32_t buf = UNR == 2 ? (uint32_t)bb : (blk & 1u);
+      for (int bb = 0; bb < NBB; bb++, blk += (GRP && UNR == 2) ? 2 : 1) {
+        const int b = (GRP && UNR == 2) ? bpair + grp : bpair + bb;
+        const uint32_t buf = (GRP && UNR == 2) ? (uint32_t)grp : (UNR == 2 ? (uint32_t)bb : (blk & 1u));
+        if (GRP && UNR != 2 && buf != (uint32_t)grp) continue;  // the other group's set (warp-uniform)
         mbar_wait(&acc_full[buf], par);
         tc_fence_after();
 #ifdef I8_CC_UNROLL
@@ -688,8 +728,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #else
 #pragma unroll 1
 #endif
-        for (int cc = 0; cc < CW / CH; cc++) {
-          const int col0 = h * CW + cc * CH;
+        for (int cc = 0; cc < CWG / CH; cc++) {
+          const int col0 = hcol + cc * CH;
           uint32_t a[NS][CH];
 #ifdef FMCMC_I8_TUNE_HOOKS  // profiling experiments only (profiles/r01_i8_findings.md): results are garbage
           if (tb.tune & 1) {
@@ -704,7 +744,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             tc_ld_diagonals<NS, CH>(buf * G::ACC_COLS + col0 + lane_base, a);
           }
           tc_wait_ld<NS, CH>(a);
-          if (cc == CW / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
+          if (cc == CWG / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -716,9 +756,16 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             for (int e = 0; e < CH; e++) acc += (double)(int)(a[0][e] ^ a[NS - 1][e]);
           } else
 #endif
-          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && eta_in_table && obs0 + CH <= valid) {
+          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)  // the hot loop of cfg3
+              i8_logistic_lcosh3_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+          } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table) {
+            for (int e = 0; e < CH; e++)  // last, partial tile of a CTA on the mean-corrected table
+              if (obs0 + e < valid) i8_logistic_lcosh3_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+          } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && eta_in_table && obs0 + CH <= valid) {
+#pragma unroll
+            for (int e = 0; e < CH; e++)
               i8_logistic_lcosh_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 1 && eta_small && obs0 + CH <= valid) {
 #pragma unroll
