@@ -5,8 +5,9 @@ the C ABI in include/fmcmc_b200.h.  There is no CPU path in this package."""
 from ._lib import FmcmcError, build, lib  # noqa: F401
 from .api import MCMC, FedStream, check_initial  # noqa: F401
 from .coda import Mcmc, McmcList, append_chains  # noqa: F401
-from .convergence import (LAST_CONV_CHECK, convergence_data_get, convergence_data_set,  # noqa: F401
-                          convergence_gelman, convergence_msg_get, convergence_msg_set)
+from .convergence import (LAST_CONV_CHECK, convergence_auto, convergence_data_get, convergence_data_set,  # noqa: F401
+                          convergence_gelman, convergence_geweke, convergence_heildel, convergence_msg_get,
+                          convergence_msg_set)
 from .device import DeviceModel, cov_recursive, mean_recursive, reflect_on_boundaries  # noqa: F401
 from .families import DeviceFamily, ll_gaussian_lm, ll_hier_normal, ll_logistic  # noqa: F401
 from .kernels import (FmcmcKernel, kernel_adapt, kernel_am, kernel_new, kernel_nmirror,  # noqa: F401

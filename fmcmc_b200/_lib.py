@@ -71,6 +71,8 @@ def lib():
     L.fmcmc_model_trim.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t]
     L.fmcmc_kernel_state_fetch.restype = C.c_int
     L.fmcmc_kernel_state_fetch.argtypes = [vp, C.POINTER(A.KernelState), C.c_char_p, C.c_size_t]
+    L.fmcmc_store_ess.restype = C.c_int
+    L.fmcmc_store_ess.argtypes = [vp, C.c_int64, C.c_int64, u8p, C.c_int32, dp, C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]
     L.fmcmc_store_pooled.restype = C.c_int
     L.fmcmc_store_pooled.argtypes = [vp, u8p, dp, C.c_char_p, C.c_size_t]
     L.fmcmc_set_path.restype = C.c_int
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "fmcmc_version", "fmcmc_device_count", "fmcmc_model_nparams", "fmcmc_kernel_state_len",
     "fmcmc_rows_kept", "fmcmc_model_create", "fmcmc_model_create_device", "fmcmc_model_free", "fmcmc_model_trim", "fmcmc_event_mark", "fmcmc_event_elapsed_ms",
     "fmcmc_set_path", "fmcmc_run", "fmcmc_logpost", "fmcmc_store_reset", "fmcmc_store_rows",
-    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_gelman_window_begin", "fmcmc_store_pooled", "fmcmc_kernel_state_fetch", "fmcmc_host_sym_eigmax", "fmcmc_shard_alloc", "fmcmc_shard_attach", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
+    "fmcmc_gelman_partials", "fmcmc_gelman_finish", "fmcmc_gelman", "fmcmc_gelman_window_begin", "fmcmc_store_pooled", "fmcmc_store_ess", "fmcmc_kernel_state_fetch", "fmcmc_host_sym_eigmax", "fmcmc_shard_alloc", "fmcmc_shard_attach", "fmcmc_cov_recursive", "fmcmc_reflect", "fmcmc_measure_fp64_peak", "fmcmc_test_softplus",
 ]
 
 

@@ -14,7 +14,7 @@ import numpy as np
 from . import _abi as A
 from . import mcmc_info as info
 from .coda import Mcmc, McmcList, append_chains, append_mcpar
-from .convergence import (GelmanChecker, convergence_data_flush, convergence_msg_get, convergence_msg_set)
+from .convergence import (AutoChecker, GelmanChecker, convergence_data_flush, convergence_msg_get, convergence_msg_set)
 from .device import DeviceModel
 from .dist import current_sharding
 from .families import DeviceFamily
@@ -168,6 +168,8 @@ def MCMC(initial, fun, nsteps, *, seed=None, nchains=1, burnin=0, thin=1, kernel
         raise ValueError(f"-thin- ({thin}) cannot be > than -nsteps- ({nsteps}).")
     if thin < 1:
         raise ValueError("-thin- should be >= 1.")
+    if isinstance(conv_checker, AutoChecker):                  # R/convergence.R:383-386: picked by the number of chains
+        conv_checker = conv_checker.gelman if nchains > 1 else conv_checker.geweke
     if conv_checker is not None and isinstance(conv_checker, GelmanChecker) and nchains < 2:
         raise ValueError("Convergence test with the Gelman is only available when `nchains` > 1L.")
 

@@ -105,3 +105,110 @@ class GelmanChecker:
 
 def convergence_gelman(freq=1000, threshold=1.10, check_invariant=True):
     return GelmanChecker(freq, threshold, check_invariant)
+
+
+# ---- single-chain checkers (R/convergence.R:259-389): host-side, on the mcmc object MCMC() returns ----------------------
+
+def _rm_invariant_host(x):
+    """rm_invariant (R/convergence.R:169-186) on a host object: ONE pooled variance (quirk D9); column 1 goes when it is < 1e-10."""
+    from .coda import Mcmc
+    data = np.vstack([m.data for m in x]) if isinstance(x, McmcList) else np.asarray(x.data)
+    if data.size > 1 and np.var(data.ravel(), ddof=1) < 1e-10:
+        if data.shape[1] == 1:
+            return None                                           # the reference returns FALSE; the diag then errors
+        if isinstance(x, McmcList):
+            return x.select(list(range(1, x.nvar())))
+        return Mcmc(x.data[:, 1:], *x.mcpar, x.varnames[1:])
+    return x
+
+
+def _record(x, d):
+    dat = dict(LAST_CONV_CHECK.get("dat", {}))
+    dat[x.mcpar[1]] = d
+    convergence_data_set({"dat": dat})
+
+
+class _HostChecker:
+    freq = 1000
+
+    def _single_chain(self, x, what):
+        if (x.nchain() if hasattr(x, "nchain") else 1) > 1:
+            raise ValueError(what)
+
+
+class GewekeChecker(_HostChecker):
+    """convergence_geweke (R/convergence.R:259-303): TRUE iff H0 'equal means of the first 10 % and the last 50 %' is not
+    rejected at `threshold` for every parameter.  coda::geweke.diag is restated in diagnostics.py (third-party, unpinned)."""
+
+    def __init__(self, freq=1000, threshold=0.025, check_invariant=True):
+        self.freq, self.threshold, self.check_invariant = int(freq), float(threshold), bool(check_invariant)
+
+    def __call__(self, x):
+        from scipy.special import ndtr
+        from .diagnostics import geweke_z
+        self._single_chain(x, "The `geweke` convergence check is only available with runs of a single chain.")
+        niter = x.niter()
+        if self.check_invariant:
+            x = _rm_invariant_host(x)
+        try:
+            if x is None:
+                raise ValueError("every column is invariant")
+            z = geweke_z(x)
+        except Exception:                                       # R/convergence.R:274-282
+            warnings.warn(f"At {niter} `geweke.diag` failed to be computed. Will skip and try with the next batch.")
+            return False
+        _record(x, z)
+        fin = z[np.isfinite(z)]
+        convergence_msg_set("avg Geweke's Z: %.4f." % (fin.mean() if fin.size else float("nan")))
+        p = 1.0 - ndtr(-np.abs(z)) * 2.0
+        if np.any(~np.isfinite(p)):
+            return False
+        return bool(np.all(p > self.threshold))
+
+
+class HeidelChecker(_HostChecker):
+    """convergence_heildel (R/convergence.R:308-355): TRUE iff every parameter passes both the stationarity and the half-width
+    test of coda::heidel.diag (restated in diagnostics.py; third-party, unpinned)."""
+
+    def __init__(self, freq=1000, check_invariant=True, eps=0.1, pvalue=0.05):
+        self.freq, self.check_invariant, self.eps, self.pvalue = int(freq), bool(check_invariant), float(eps), float(pvalue)
+
+    def __call__(self, x):
+        from .diagnostics import heidel_diag
+        self._single_chain(x, "The -heidel- convergence check is only available with runs of a single chain.")
+        niter = x.niter()
+        if self.check_invariant:
+            x = _rm_invariant_host(x)
+        try:
+            if x is None:
+                raise ValueError("every column is invariant")
+            d = heidel_diag(x, self.eps, self.pvalue)
+        except Exception:                                       # R/convergence.R:321-333
+            warnings.warn(f"At {niter} -coda::heidel.diag- failed to be computed. Will skip and try with the next batch.")
+            return False
+        _record(x, d)
+        convergence_msg_set("Heidel's Avg. pval: %.2f" % np.mean(d[:, 2]))
+        tests = d[:, [0, 3]]
+        if np.any(~np.isfinite(tests)):
+            return False
+        return bool(np.all(tests == 1))
+
+
+class AutoChecker(_HostChecker):
+    """convergence_auto (R/convergence.R:365-389): Gelman-Rubin when nchains > 1 (on the device), Geweke otherwise."""
+
+    def __init__(self, freq=1000):
+        self.freq = int(freq)
+        self.gelman, self.geweke = GelmanChecker(freq), GewekeChecker(freq)
+
+
+def convergence_geweke(freq=1000, threshold=0.025, check_invariant=True):
+    return GewekeChecker(freq, threshold, check_invariant)
+
+
+def convergence_heildel(freq=1000, check_invariant=True, eps=0.1, pvalue=0.05):
+    return HeidelChecker(freq, check_invariant, eps, pvalue)
+
+
+def convergence_auto(freq=1000):
+    return AutoChecker(freq)

@@ -1567,6 +1567,46 @@ extern "C" int fmcmc_store_pooled(fmcmc_model* m, const uint8_t* free_mask, doub
   return FMCMC_OK;
 }
 
+// Effective sample size of every (chain, free parameter) series in rows [row_begin, row_end) of the store.
+extern "C" int fmcmc_store_ess(fmcmc_model* m, int64_t row_begin, int64_t row_end, const uint8_t* free_mask, int32_t max_lag,
+                               double* ess, int32_t* truncated, char* err, size_t errlen) {
+  if (!m || !ess) { set_err(err, errlen, "null argument"); return FMCMC_EINVAL; }
+  const int C = m->store_C, k = m->store_k;
+  const long long N = row_end - row_begin;
+  if (row_begin < 0 || row_end > m->store_rows || N < 4) {
+    set_err(err, errlen, "bad window [%lld, %lld) of %lld stored rows (at least 4 rows are needed)", (long long)row_begin, (long long)row_end, (long long)m->store_rows);
+    return FMCMC_EINVAL;
+  }
+  std::vector<int> fidx;
+  for (int j = 0; j < k; j++)
+    if (!free_mask || free_mask[j]) fidx.push_back(j);
+  const int kf = (int)fidx.size();
+  if (kf < 1) { set_err(err, errlen, "no free parameters"); return FMCMC_EINVAL; }
+  if (max_lag <= 0) max_lag = (int)std::min<long long>(N - 1, 2000);
+  const int L = (int)std::min<long long>(max_lag, N - 1);
+  const size_t smem = ((size_t)N + (size_t)L + 2) * 8;
+  CU_CHECK(cudaSetDevice(m->device));
+  if (smem > (size_t)m->smem_optin) {
+    set_err(err, errlen, "a window of %lld rows with %d lags needs %zu bytes of shared memory per series (limit %d): thin the window", N, L, smem, m->smem_optin);
+    return FMCMC_EUNSUP;
+  }
+  CU_CHECK(cudaFuncSetAttribute(store_ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU_CHECK(ensure(m->g_mask, kf * sizeof(int)));
+  CU_CHECK(cudaMemcpyAsync(m->g_mask.p, fidx.data(), kf * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  CU_CHECK(ensure(m->g_xbar, (size_t)C * kf * 8 + 16));
+  int* d_tr = reinterpret_cast<int*>(m->g_xbar.as<double>() + (size_t)C * kf);
+  CU_CHECK(cudaMemsetAsync(d_tr, 0, sizeof(int), m->stream));
+  store_ess_kernel<<<C * kf, 256, smem, m->stream>>>(m->store.as<double>(), C, k, row_begin, row_end, m->g_mask.as<int>(), kf, L,
+                                                    m->g_xbar.as<double>(), d_tr);
+  CU_CHECK(cudaGetLastError());
+  int tr = 0;
+  CU_CHECK(cudaMemcpyAsync(ess, m->g_xbar.p, (size_t)C * kf * 8, cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaMemcpyAsync(&tr, d_tr, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CU_CHECK(cudaStreamSynchronize(m->stream));
+  if (truncated) *truncated = tr;
+  return FMCMC_OK;
+}
+
 // 0-based first store row kept by coda::gelman.diag's autoburnin on an mcmc.list with mcpar = (start, start + (rows-1) thin, thin):
 //   if (autoburnin && start(x) < end(x)/2) x <- window(x, start = end(x)/2 + 1)
 // window.mcmc() snaps a start that is not on the iteration grid UP to the next kept iteration (ts.eps = 1e-5), then

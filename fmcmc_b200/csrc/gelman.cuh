@@ -271,3 +271,55 @@ gelman_pooled_kernel(const double* __restrict__ store, int C, int k, long long r
     part[blockIdx.x * 3 + 2] = bq;
   }
 }
+
+// ---- effective sample size on the device (the reference itself only prints coda's time-series SE) ----
+// One CTA per (chain, free parameter) series x_1..x_N taken from the sample store: centred series in shared memory,
+// autocovariances gamma(l) = (1/N) sum_t x_t x_{t+l} for l = 0 .. L (thread <-> lag, every product read from shared
+// memory), then Geyer's initial positive sequence on the pairs Gamma_m = rho(2m) + rho(2m + 1): tau = -1 + 2 sum_m Gamma_m
+// up to the first non-positive pair, ESS = N / tau.  O(N L) FP64 multiply-adds per series; L = min(N - 1, max_lag).
+// If the pairs are still positive at the last lag the estimate is truncated there (reported through `truncated`).
+__global__ void __launch_bounds__(256)
+store_ess_kernel(const double* __restrict__ store, int C, int k, long long row_begin, long long row_end,
+                 const int* __restrict__ fidx, int kf, int max_lag, double* __restrict__ ess, int* __restrict__ truncated) {
+  extern __shared__ double es_sh[];  // [N] centred series, then [L + 2] autocovariances
+  __shared__ double red[32];
+  const long long N = row_end - row_begin;
+  const int c = blockIdx.x / kf, a = blockIdx.x % kf;
+  const int L = (int)min((long long)max_lag, N - 1);
+  double* x = es_sh;
+  double* g = es_sh + N;
+  const size_t rowlen = (size_t)C * k;
+  const double* base = store + (size_t)row_begin * rowlen + (size_t)c * k + fidx[a];
+  double s = 0.0;
+  for (long long t = threadIdx.x; t < N; t += blockDim.x) { const double v = base[t * rowlen]; x[t] = v; s += v; }
+  const double mean = block_sum_256(s, red) / (double)N;
+  __syncthreads();
+  for (long long t = threadIdx.x; t < N; t += blockDim.x) x[t] -= mean;
+  __syncthreads();
+  for (int l = threadIdx.x; l <= L + 1; l += blockDim.x) {
+    double acc = 0.0;
+    if (l <= L)
+      for (long long t = 0; t + l < N; t++) acc = fma(x[t], x[t + l], acc);
+    g[l] = acc / (double)N;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double g0 = g[0];
+    double tau = -1.0;
+    int trunc = 0;
+    if (g0 > 0.0) {
+      int m = 0;
+      for (;; m++) {
+        if (2 * m + 1 > L) { trunc = 1; break; }
+        const double pair = (g[2 * m] + g[2 * m + 1]) / g0;
+        if (!(pair > 0.0)) break;
+        tau += 2.0 * pair;
+      }
+      if (tau < 1.0 / (double)N) tau = 1.0 / (double)N;
+      ess[(size_t)c * kf + a] = (double)N / tau;
+    } else {
+      ess[(size_t)c * kf + a] = 0.0;  // a constant series carries no information
+    }
+    if (trunc) atomicOr(truncated, 1);
+  }
+}

@@ -152,6 +152,16 @@ class DeviceModel:
         _lib.check(_lib.lib().fmcmc_store_pooled(self._h, A.ptr(mask, C.POINTER(C.c_uint8)), A.ptr(out), err, len(err)), err)
         return out
 
+    def store_ess(self, row_begin, row_end, free_mask, nchains, max_lag=0):
+        """fmcmc_store_ess: (ESS[nchains][kf], truncated) of the stored series, computed on the device."""
+        mask = np.ascontiguousarray(free_mask, dtype=np.uint8)
+        ess = np.empty((nchains, int(mask.sum())))
+        tr = C.c_int32()
+        err = _lib.errbuf()
+        _lib.check(_lib.lib().fmcmc_store_ess(self._h, row_begin, row_end, A.ptr(mask, C.POINTER(C.c_uint8)), int(max_lag),
+                                              A.ptr(ess), C.byref(tr), err, len(err)), err)
+        return ess, bool(tr.value)
+
     def gelman_partials(self, row_begin, row_end, free_mask, nchains, out=None):
         """Host arrays by default; with `out=(xbar_ptr, s2_ptr, wsum_ptr)` raw device pointers."""
         mask = np.ascontiguousarray(free_mask, dtype=np.uint8)

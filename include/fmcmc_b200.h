@@ -344,6 +344,15 @@ int64_t fmcmc_gelman_window_begin(int64_t start_iter, int64_t thin, int64_t rows
  * of the store; several GPUs combine the triples (Chan et al.) - fmcmc_b200/dist.py does. */
 int fmcmc_store_pooled(fmcmc_model* m, const uint8_t* free_mask, double* out, char* err, size_t errlen);
 
+/* Effective sample size of every (local chain, free parameter) series over rows [row_begin, row_end) of the store, on the
+ * device: autocovariances up to max_lag (<= 0: min(rows - 1, 2000)) and Geyer's initial positive sequence,
+ * ESS = N / (-1 + 2 sum_m [rho(2m) + rho(2m + 1)]) up to the first non-positive pair.  ess: host [nchains][kf].
+ * *truncated = 1 when some series still had positive pairs at max_lag (its ESS is then an over-estimate).  The reference
+ * has no ESS of its own (README.md:191-194 prints coda's time-series SE; coda::effectiveSize is third-party): this is the
+ * "ESS/sec" of BASELINE.json's metric and the MCSE of the distributional checks. */
+int fmcmc_store_ess(fmcmc_model* m, int64_t row_begin, int64_t row_end, const uint8_t* free_mask, int32_t max_lag,
+                    double* ess, int32_t* truncated, char* err, size_t errlen);
+
 /* Host-only helper of the Gelman finish, exported for the CPU test-suite: largest eigenvalue of a symmetric
  * p x p matrix (col-major; Householder tridiagonalisation + Sturm bisection). */
 int fmcmc_host_sym_eigmax(int32_t p, const double* A, double* emax);

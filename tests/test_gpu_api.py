@@ -231,3 +231,28 @@ def test_exported_helpers(oracle):
     o = np.stack([oracle.reflect(r, lo, hi) for r in big])
     np.testing.assert_allclose(g, o, rtol=1e-13, atol=1e-13)
     assert np.all(g >= lo) and np.all(g <= hi)
+
+
+def test_single_chain_checkers_through_mcmc(readme_data, capfd):
+    """inst/tinytest/test-convergence.R:19-121: auto / geweke / heidel auto-stop runs are reproducible for equal seeds; the
+    single-chain checkers refuse more than one chain, Gelman refuses one; convergence_auto picks by the number of chains."""
+    ll = _readme_ll(readme_data)
+    init = [3.0, 2.0, 4.0]
+
+    def go(chk, nchains=1, seed=31):
+        return fm.MCMC(init if nchains == 1 else np.tile(init, (nchains, 1)), ll, 3000, nchains=nchains, seed=seed,
+                       kernel=fm.kernel_normal_reflective(scale=.1, lb=[np.nan, np.nan, 0.0]), conv_checker=chk)
+
+    for make in (lambda: fm.convergence_geweke(500), lambda: fm.convergence_heildel(500), lambda: fm.convergence_auto(500)):
+        a, b = go(make()), go(make())
+        assert isinstance(a, fm.Mcmc) and a.niter() % 500 == 0 and np.array_equal(a.data, b.data)
+    err = capfd.readouterr().err
+    assert "avg Geweke's Z:" in err and "Heidel's Avg. pval:" in err
+    two = go(fm.convergence_auto(500), nchains=2)                 # auto with 2 chains = Gelman-Rubin on the device
+    assert isinstance(two, fm.McmcList) and "Gelman-Rubin's R:" in capfd.readouterr().err
+    with pytest.raises(ValueError, match="single chain"):
+        go(fm.convergence_heildel(500), nchains=2)
+    with pytest.raises(ValueError, match="single chain"):
+        go(fm.convergence_geweke(500), nchains=2)
+    with pytest.raises(ValueError, match="nchains` > 1L"):
+        go(fm.convergence_gelman(500), nchains=1)

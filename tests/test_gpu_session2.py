@@ -239,3 +239,51 @@ def test_mcmc_with_checker_returns_views_of_one_array(readme_data):
     assert np.array_equal(ans.as_array(), np.concatenate(parts, axis=1))
     assert np.array_equal(kern[3].Sigma, dst[3, :9].reshape(3, 3, order="F")) and kern[3].abs_iter == ist[3, 0]
     ll.release()
+
+
+def _ess_numpy(x):
+    """Per-series Geyer initial-positive-sequence ESS from direct-lag autocovariances (divisor N).  x: [C][N][k]."""
+    C, N, k = x.shape
+    out = np.empty((C, k))
+    for c in range(C):
+        for a in range(k):
+            v = x[c, :, a] - x[c, :, a].mean()
+            g = np.array([np.dot(v[:N - l], v[l:]) / N for l in range(N)])
+            if not g[0] > 0:
+                out[c, a] = 0.0
+                continue
+            tau, m = -1.0, 0
+            while 2 * m + 1 <= N - 1:
+                pair = (g[2 * m] + g[2 * m + 1]) / g[0]
+                if not pair > 0:
+                    break
+                tau += 2 * pair
+                m += 1
+            out[c, a] = N / max(tau, 1.0 / N)
+    return out
+
+
+def test_device_ess_matches_numpy(readme_data):
+    """fmcmc_store_ess (autocovariances + Geyer's initial positive sequence per (chain, parameter) on the device) against the
+    same estimator in numpy on the same samples; a fixed parameter (constant series) has ESS 0 and is masked out."""
+    ll = fm.ll_gaussian_lm(readme_data["X"], readme_data["y"], intercept=True, guard=True)
+    C, T = 12, 700
+    spec = fm.kernel_normal_reflective(scale=[0.1, 0.1, 0.1], lb=[np.nan, np.nan, 0.0], fixed=[False, True, False]).to_spec(3)
+    m = DeviceModel(ll)
+    try:
+        m.store_reset(C, T)
+        o = m.run(spec, T, C, initial=np.tile([3.0, 2.0, 4.0], (C, 1)), flags=A.RUN_APPEND,
+                  stream=A.marshal_stream(A.STREAM_PHILOX, seed=9))
+        ess, trunc = m.store_ess(100, T, [1, 0, 1], C)
+        want = _ess_numpy(o["ans"][:, 100:, :][:, :, [0, 2]])
+        assert not trunc and ess.shape == (C, 2)
+        np.testing.assert_allclose(ess, want, rtol=1e-9)
+        assert np.all(ess > 5) and np.all(ess < T)               # a random-walk chain: well below one sample per row
+        all3, _ = m.store_ess(100, T, [1, 1, 1], C)
+        assert np.all(all3[:, 1] == 0.0)                         # the fixed column never moves
+        short, tr2 = m.store_ess(100, T, [1, 0, 1], C, max_lag=3)
+        assert tr2 and np.all(short >= ess - 1e-9)               # truncated sums over-estimate
+        with pytest.raises(fm.FmcmcError, match="window"):
+            m.store_ess(0, 3, [1, 0, 1], C)
+    finally:
+        m.close()

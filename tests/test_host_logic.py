@@ -231,3 +231,96 @@ def test_host_sym_eigmax_against_numpy():
             want = np.linalg.eigvalsh(M)[-1]
             scale = max(np.abs(np.linalg.eigvalsh(M)).max(), 1e-300)
             assert abs(out.value - want) <= 1e-13 * scale, (p, kind, out.value, want)
+
+
+# ---- single-chain diagnostics (fmcmc_b200/diagnostics.py: coda::geweke.diag / heidel.diag / spectrum0.ar, stats::ar restated) ----
+
+def _ar1(n, phi, seed, drift=0.0):
+    rng = np.random.default_rng(seed)
+    e = rng.standard_normal(n)
+    x = np.zeros(n)
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    return x + drift * np.arange(n)
+
+
+def test_ar_yule_walker_against_toeplitz_solves():
+    """Levinson-Durbin + AIC selection == solving the Yule-Walker system of every order directly (scipy Toeplitz solver) and
+    picking the order with the smallest n log(v_k) + 2 k."""
+    from scipy.linalg import solve_toeplitz
+    from fmcmc_b200.diagnostics import ar_yule_walker
+    for seed, phi in ((1, 0.5), (2, 0.9), (3, -0.4)):
+        x = _ar1(1500, phi, seed)
+        n = x.size
+        xc = x - x.mean()
+        omax = int(min(n - 1, np.floor(10 * np.log10(n))))
+        r = np.array([xc[:n - l] @ xc[l:] / n for l in range(omax + 1)])
+        best = (n * np.log(r[0]) + 2.0, np.zeros(0), r[0])
+        for k in range(1, omax + 1):
+            a = solve_toeplitz(r[:k], r[1:k + 1])
+            v = r[0] - a @ r[1:k + 1]
+            aic = n * np.log(v) + 2 * k + 2.0
+            if aic < best[0]:
+                best = (aic, a, v)
+        ar, var_pred, order = ar_yule_walker(x)
+        assert order == best[1].size and order >= 1
+        np.testing.assert_allclose(ar, best[1], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(var_pred, best[2] * n / (n - (order + 1)), rtol=1e-10)
+
+
+def test_spectrum0_and_cramer_von_mises_known_values():
+    from fmcmc_b200.diagnostics import pcramer, spectrum0_ar
+    # AR(1) with unit innovations: spectral density at zero = 1 / (1 - phi)^2
+    s0 = np.mean([spectrum0_ar(_ar1(20000, 0.6, s))[0] for s in range(5)])
+    assert abs(s0 / (1 / 0.4 ** 2) - 1) < 0.08
+    assert spectrum0_ar(np.full(50, 3.0))[0] == 0.0 and spectrum0_ar(np.arange(50.0))[0] == 0.0   # no variation about the trend
+    # the asymptotic Cramer-von Mises law: 5 % and 1 % points 0.46136 and 0.74346 (Anderson & Darling 1952, table 1)
+    assert abs(pcramer(0.46136) - 0.95) < 1e-4 and abs(pcramer(0.74346) - 0.99) < 1e-4
+
+
+def test_geweke_and_heidel_on_stationary_and_drifting_chains():
+    import fmcmc_b200 as fm
+    from fmcmc_b200.diagnostics import geweke_z, heidel_diag
+    n = 4000
+    good = np.c_[_ar1(n, 0.5, 11) + 10.0, _ar1(n, 0.2, 12) - 3.0]
+    bad = np.c_[_ar1(n, 0.5, 13) + 10.0, _ar1(n, 0.5, 14, drift=2e-3)]
+    zg, zb = geweke_z(fm.Mcmc(good, 1, n, 1)), geweke_z(fm.Mcmc(bad, 1, n, 1))
+    assert np.all(np.abs(zg) < 3.5) and abs(zb[1]) > 6
+    # windows live on the iteration grid start + thin * row: starts snap up, ends snap down (coda's window.mcmc)
+    from fmcmc_b200.diagnostics import _window_rows
+    assert _window_rows(5, 32, 3, 10, wstart=10) == (2, 10)           # iterations 5, 8, 11, ...: the first >= 10 is row 2
+    assert _window_rows(5, 32, 3, 10, wend=20) == (0, 6)              # the last <= 20 is iteration 20 = row 5
+    assert _window_rows(5, 32, 3, 10, wstart=11, wend=11) == (2, 3)
+    zt = geweke_z(fm.Mcmc(good, 5, 5 + 3 * (n - 1), 3))
+    assert np.all(np.isfinite(zt)) and np.all(np.abs(zt - zg) < 0.1)  # a row more or less at the window edges
+    hg, hb = heidel_diag(fm.Mcmc(good, 1, n, 1)), heidel_diag(fm.Mcmc(bad, 1, n, 1))
+    assert np.all(hg[:, 0] == 1) and np.all(hg[:, 3] == 1) and np.all(hg[:, 1] >= 1)
+    np.testing.assert_allclose(hg[0, 4], good[int(hg[0, 1]) - 1:, 0].mean(), rtol=1e-12)   # mean of the part that passed
+    assert hb[1, 0] == 0 and np.isnan(hb[1, 3])                       # the drifting column fails the stationarity test
+
+
+def test_single_chain_checkers_follow_the_reference():
+    """R/convergence.R:259-389: messages, side channel, errors with more than one chain, the literal decision rule of
+    convergence_geweke (it compares 1 - p-value with the threshold), convergence_auto's choice."""
+    import warnings as W
+    import fmcmc_b200 as fm
+    n = 2000
+    one = fm.Mcmc(np.c_[_ar1(n, 0.5, 21) + 5.0, _ar1(n, 0.3, 22) + 1.0], 1, n, 1)
+    g = fm.convergence_geweke(500)
+    assert g.freq == 500 and isinstance(g(one), bool)
+    assert fm.convergence_msg_get().startswith("avg Geweke's Z: ")
+    assert n in fm.convergence_data_get("dat")
+    h = fm.convergence_heildel(500)
+    assert h(one) is True and fm.convergence_msg_get().startswith("Heidel's Avg. pval: ")
+    two = fm.McmcList([one, one])
+    with pytest.raises(ValueError, match="only available with runs of a single chain"):
+        g(two)
+    with pytest.raises(ValueError, match="only available with runs of a single chain"):
+        h(two)
+    const = fm.Mcmc(np.full((100, 1), 2.0), 1, 100, 1)                 # rm_invariant removes the only column -> warning + FALSE
+    with W.catch_warnings(record=True) as rec:
+        W.simplefilter("always")
+        assert g(const) is False and h(const) is False
+    assert any("failed to be computed" in str(r.message) for r in rec)
+    a = fm.convergence_auto(300)
+    assert a.freq == 300 and a.gelman.freq == 300 and a.geweke.freq == 300
