@@ -39,7 +39,7 @@ DATA_SEED = 20260317
 KERNEL_WARMUP = 500
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of this command (profiles/): a profiler figure, so it is a constant here, never measured in the timed run
-TRAFFIC_PER_LAUNCH = {("cfg3", 4): 197.1e6, ("cfg5", 4): 11.48e9, ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}
+TRAFFIC_PER_LAUNCH = {("cfg3", 4): None, ("cfg5", 4): None, ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}   # path 4: filled from the r02 captures
 
 
 def make_data(n=N_OBS, p=P_X, seed=DATA_SEED, block=0):
@@ -430,7 +430,16 @@ def measure(wl, args, env, brief=False, chains_total=None):
     for _ in range(0 if brief else 2):                 # run-to-run spread of the same region (reported, not used for `value`)
         barrier()
         repeats.append(region(K)[0] / K)
-    res = dict(dev_ms=dev_ms, step_ms=step_ms, hot_ms=hot_ms, launches=launches, accept=accept, path=path, t_wall=t_wall,
+    # ESS of the timed rows on the DEVICE (fmcmc_store_ess: autocovariances + Geyer's initial positive sequence per chain and
+    # parameter over the sample store the region just filled), summed over this rank's chains
+    ess_dev = None
+    if ce and not brief:
+        try:
+            e, trunc = model.store_ess(0, model.store_rows(), free, C)
+            ess_dev = {"per_param_sum_over_chains": e.sum(axis=0), "truncated": trunc, "rows": int(model.store_rows())}
+        except fm.FmcmcError as ex:
+            ess_dev = {"error": str(ex)}
+    res = dict(ess_dev=ess_dev, dev_ms=dev_ms, step_ms=step_ms, hot_ms=hot_ms, launches=launches, accept=accept, path=path, t_wall=t_wall,
                mpsrf=mpsrf, checks=nchk, check_ms=chk_ms / max(nchk, 1), check_timings=tm, repeats=repeats,
                t_data=t_data, t_model=t_model, C=C, k=k, K=K, ce=ce, ntot=ntot, fam=fam, host_data=host_data,
                model=model, sampler=sampler)
@@ -656,7 +665,7 @@ def main():
             d5, st5, h5 = reduce_max(r5["dev_ms"], r5["step_ms"], r5["hot_ms"])
             r5["model"].close()
             ev5 = float(w5.n) * w5.chains
-            macs5 = ev5 * 21 * 32 * 4
+            macs5 = ev5 * 15 * 32 * 4
             sm_clock5 = (clocks or {}).get("sm_mhz") or 1965.0
             t_t5 = macs5 / (148 * 7710.0 * sm_clock5 * 1e6)
             t_f5 = ev5 * 3 / 32.0 / (148 * 2 * sm_clock5 * 1e6)
@@ -669,7 +678,7 @@ def main():
                     "rhat_500_row_window": rhat_at_scale(env),
                     "roofline": {"bound": "tensor", "kernel": "tiled_loglik_i8_kernel", "launch_ms": h5,
                                  "floor_ms": 1e3 * (t_t5 + t_f5), "frac": (t_t5 + t_f5) / (h5 * 1e-3),
-                                 "note": "two-engine floor: 21 slice pairs x 128 int8 MACs per eval / measured int8 peak + 3 FP64 slots "
+                                 "note": "two-engine floor: 15 slice pairs x 128 int8 MACs per eval / measured int8 peak + 3 FP64 slots "
                                          "per eval / FP64 pipe rate (time-additive on B200)"}}
         except Exception as e:                          # never lose the headline line over the secondary workload
             cfg5 = {"unavailable": f"{type(e).__name__}: {e}"}
@@ -683,7 +692,7 @@ def main():
         if obs_shard:
             n = int(fam.n)                                                      # rank 0's rows: what ITS kernel streams per launch
         alg_bytes = 8.0 * n * (p_x + 1) + 8.0 * C * (3 * k + 2)               # SURVEY §8d, per launch (= per step per GPU)
-        i8_ns = 6                                                             # int8 slices per operand of path 4 (7 for kernel_ram)
+        i8_ns = 5                                                             # 8-bit int8 slices per operand of path 4 (6 for kernel_ram / n < 65 536)
         i8_kb = 1 if p_x <= 32 else (2 if p_x <= 64 else 4)
         if path == 4:   # path 4 streams NS int8 slices of X (K padded to 32 / 64 / 128) instead of FP64 X; y only for the Gaussian
             alg_bytes = float(n) * (i8_ns * 32 * i8_kb + (8 if wl.family == "gaussian" else 0)) + 8.0 * C * (3 * k + 2)
@@ -703,7 +712,7 @@ def main():
         achieved_tf = flops / (hot_ms * 1e-3) / 1e12
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
-        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (12 if wl.family == "logistic" else 3)
+        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (10 if wl.family == "logistic" else 3)
         pipe_util = evals * fp64_instr / 32.0 / (hot_ms * 1e-3) / pipe_slots
         kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 4: "tiled_loglik_i8_kernel", 1: "mh_resident_kernel"}[path]
         line = {
@@ -728,11 +737,20 @@ def main():
                              "repeat_ms_per_step": r["repeats"]},
             "stepping_only": {"value": total_chain_steps / (step_ms * 1e-3), "ms_per_step": step_ms / K,
                               "note": "the same timed region counting only the stepping kernels' CUDA-event time (what round 1 reported as `value`)"},
-            "ess_per_s": float(ess.min()) * cw / e2e_sec if ess is not None else None,
-            "ess": {"min_over_params": float(ess.min()), "median_over_params": float(np.median(ess)),
-                    "rows_per_chain": r["e2e_rows"] - 1, "chains": C,
-                    "method": "per-chain Geyer initial-positive-sequence, summed over rank 0's chains (x n_gpus in ess_per_s); "
-                              "time = the e2e call"} if ess is not None else None,
+            "ess_per_s": (float(r["ess_dev"]["per_param_sum_over_chains"].min()) * cw / (dev_ms * 1e-3)
+                          if r.get("ess_dev") and "error" not in r["ess_dev"] else
+                          (float(ess.min()) * cw / e2e_sec if ess is not None else None)),
+            "ess": ({"min_over_params": float(r["ess_dev"]["per_param_sum_over_chains"].min()),
+                     "median_over_params": float(np.median(r["ess_dev"]["per_param_sum_over_chains"])),
+                     "rows_per_chain": r["ess_dev"]["rows"], "chains": C, "truncated": r["ess_dev"]["truncated"],
+                     "method": "fmcmc_store_ess on the device: per (chain, parameter) autocovariances + Geyer's initial positive sequence "
+                               "over the rows of the timed region (bulk boundaries repeat a row, quirk D2), summed over rank 0's chains "
+                               "(x n_gpus in ess_per_s); time = the timed region"}
+                    if r.get("ess_dev") and "error" not in r["ess_dev"] else
+                    ({"min_over_params": float(ess.min()), "median_over_params": float(np.median(ess)),
+                      "rows_per_chain": r["e2e_rows"] - 1, "chains": C,
+                      "method": "host numpy, per-chain Geyer initial-positive-sequence on the e2e call's output; time = the e2e call"}
+                     if ess is not None else None)),
             "e2e": {"value": C * cw * K / e2e_sec, "unit": "chain-steps/s",
                     "h2d_bytes_per_step": r["h2d"] / K, "d2h_bytes_per_step": r["d2h"] / K,
                     "call": (f"fm.MCMC(initial, family, nsteps={r['e2e_rows']}, nchains={C * cw}, kernel=<state past warm-up>, "
@@ -808,7 +826,7 @@ def main():
                 # every instruction of the epilogue runs on a 16-lane datapath (FP64, IMAD / IMAD.WIDE, SHF, I2F, LDS): the
                 # scheduler issues one warp instruction per 2 clk whatever the pipe (ncu: issue-active 47 % of cycles with
                 # not-selected warps waiting), so the instruction count, not the FP64 count alone, is what bounds the kernel
-                instr = 21                                                      # 12 FP64 + 6 IMAD(.WIDE) + SHF + I2F + LDS.128
+                instr = 18                                                      # 10 FP64 + 2 IMAD + 2 IMAD.WIDE + SHF + I2F + LEA + LDS.128
                 t_issue = evals * instr / 32.0 * 2.0 / (148 * 4 * sm_clock * 1e6)
                 line["roofline_two_engine"].update({
                     "instr_per_eval": instr, "issue_floor_ms": 1e3 * (t_tensor + t_issue),

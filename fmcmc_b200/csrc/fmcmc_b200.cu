@@ -73,7 +73,7 @@ struct fmcmc_model {
   DevBuf X, y, group, sp_tab, sp_tab4, sp_tab8, sp_tab8m, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
-  int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (6; 7 for kernel_ram and for n < 65536)
+  int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (5 8-bit digits; 6 for kernel_ram and for n < 65536)
                           // (FMCMC_I8_SLICES = 6 | 7 overrides; tiled_i8.cuh has the error bound)
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;        // output rows leave the device while later rows are still being computed
@@ -256,7 +256,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
-  if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= 6 && atoi(v) <= 7) m->i8_slices = atoi(v); }
+  if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= I8_NS_LO && atoi(v) <= I8_NS_LO + 1) m->i8_slices = atoi(v); }
   *out = m;
   return FMCMC_OK;
 }
@@ -646,7 +646,11 @@ static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 gri
 // ---- path 4: split-integer tensor-core kernel (tiled_i8.cuh) ------------------------------------------
 static int i8_kblocks(int p_x) { return p_x <= 32 ? 1 : (p_x <= 64 ? 2 : 4); }
 static int i8_tile_rows(int KB) { return KB == 1 ? 128 : (KB == 2 ? 64 : 32); }
+#if I8_DIGIT_BITS == 8
+#define I8_FOR_SHAPES(X) X(5, 1) X(5, 2) X(5, 4) X(6, 1) X(6, 2) X(6, 4)
+#else
 #define I8_FOR_SHAPES(X) X(6, 1) X(6, 2) X(6, 4) X(7, 1) X(7, 2) X(7, 4)
+#endif
 // Builds the int8 slice tiles of X once per model.  Returns cudaErrorNotSupported when X holds non-finite
 // values (or magnitudes beyond the exponent window): the caller falls back to the FP64 kernels.
 static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
@@ -914,9 +918,9 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
   // 6 slices leave ~1e-12 |theta x|max in eta: averaged over >= 65536 observations the log-posterior is ~1e-14 relative.
   // kernel_ram (its adaptation consumes f itself) and short data (less averaging, and the tensor work is negligible
   // there anyway) run on 7 slices: ~1e-14 in eta, ~1e-15 relative in f.
-  const int i8_NS = m->i8_slices ? m->i8_slices : ((is_ram || mp.n_total < 65536) ? 7 : 6), i8_KB = i8_kblocks(mp.p_x);
+  const int i8_NS = m->i8_slices ? m->i8_slices : ((is_ram || mp.n_total < 65536) ? I8_NS_LO + 1 : I8_NS_LO), i8_KB = i8_kblocks(mp.p_x);
   if (m->trimmed_to == 4 && (m->xq_NS != i8_NS || m->xq_KB != i8_KB)) {
-    set_err(err, errlen, "the model was trimmed to path 4 with %d int8 slices; this run needs %d (kernel_ram / short data use 7) and X is gone", m->xq_NS, i8_NS);
+    set_err(err, errlen, "the model was trimmed to path 4 with %d int8 slices; this run needs %d (kernel_ram / short data use one more) and X is gone", m->xq_NS, i8_NS);
     return FMCMC_EUNSUP;
   }
   if (path == 4) {  // int8 slice tiles of X (once per model); X with non-finite entries cannot be sliced
@@ -992,6 +996,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     }
     TiledBuffers tb{};
     tb.ncols = is_ram ? 2 * C : C;
+    tb.exact_core = is_ram ? 1 : 0;
     const int chain_blocks = (tb.ncols + cpb - 1) / cpb;
     const long long ntiles = (mp.ld + tile_rows - 1) / tile_rows;
     // One observation slice per SM, whatever the number of chains: chain_blocks waves of sm_count CTAs.  Keeping

@@ -53,6 +53,7 @@ struct TiledBuffers {
   int cb;           // chain blocks (DMMA kernel: 1-D grid of gx * cb CTAs, chain block fastest)
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
   int tune;         // only read when built with -DFMCMC_I8_TUNE_HOOKS (profiling experiments, tiled_i8.cuh)
+  int exact_core;   // path 4: keep the degree-4 log-cosh core (kernel_ram: its adaptation consumes f itself and amplifies 1e-14)
 };
 
 // barriers | TL_STAGES x (PB columns + y) x TL_TILE doubles | logistic: softplus table (softplus.h)

@@ -58,8 +58,18 @@
 #define I8_CC_UNROLL 1
 #endif
 
+// Digit width of the integer slices.  8 (default): balanced base-256 digits in [-128, 127] - the whole int8 range - with the
+// leading digit scaled by 2^7: NS = 5 slices carry 39 bits (dropped pairs s + s' >= 5: <= 6 2^-40 = 5.5e-12 of the largest
+// term), 15 slice pairs instead of 21, five diagonals to merge instead of six, and at K = 128 every Theta slice fits tensor
+// memory next to the two accumulator sets.  NS = 6 (kernel_ram, short data): 7 2^-48 = 2.5e-14.  7 (round 1's scheme, NS = 6 /
+// 7, digits in [-64, 64], 1.6e-12 / 1.4e-14): -DI8_DIGIT_BITS=7.
+#ifndef I8_DIGIT_BITS
+#define I8_DIGIT_BITS 8
+#endif
+#define I8_NS_LO (I8_DIGIT_BITS == 8 ? 5 : 6)   // slices of the default accuracy tier; kernel_ram and n < 65 536 use one more
 template <int NS, int KB>
 struct I8Geom {
+  static constexpr int DB = I8_DIGIT_BITS;
   static constexpr int BLK = 32;                                    // observations per MMA block (instruction N)
   static constexpr int TO = KB == 1 ? 128 : (KB == 2 ? 64 : 32);    // observations per pipeline stage
   static constexpr int NBLK = TO / BLK;
@@ -74,7 +84,7 @@ struct I8Geom {
   static constexpr int A_TKB = ((512 - A_COL0) / (NS * 8)) < KB ? ((512 - A_COL0) / (NS * 8)) : KB;
   static constexpr int A_SKB = KB - A_TKB;
   static constexpr int A_SMEM_BYTES = NS * A_SKB * 4096;
-  static constexpr int SHIFT = 12 + 7 * (NS - 1);                   // eta = t * 2^(eth - SHIFT)
+  static constexpr int SHIFT = 2 * (DB - 1) + DB * (NS - 1);        // eta = t * 2^(eth - SHIFT)
 };
 
 // table of the logistic epilogue (softplus.h): level 2 = 256 entries per unit (160 KB, (tau, T) of log(2 cosh(a / 2)), one degree-4
@@ -110,15 +120,31 @@ __host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
 
 // ---- slicing -----------------------------------------------------------------------------------------
 #define I8_EMAX 480
-// smallest exponent e (clamped) with m < 2^e
+// smallest exponent e (clamped) with m < 2^e - 8-bit digits: with m 2^-e < 127 / 128, so that the leading digit, carry
+// included, stays <= 127
 __device__ __forceinline__ int i8_exponent(double m) {
   if (!(m > 0.0)) return 0;
-  const int e = ilogb(m) + 1;
+  int e = ilogb(m) + 1;
+#if I8_DIGIT_BITS == 8
+  if (!(scalbn(m, -e) < 127.0 / 128.0)) e += 1;
+#endif
   return max(-I8_EMAX, min(I8_EMAX, e));
 }
-// |u| <= 1  ->  u = sum_s s[s] 2^(-6 - 7 s) + O(2^(-7 NS + 1)), every step exact in FP64
+// |u| <= 1 (8-bit digits: |u| < 127 / 128)  ->  u = sum_s s[s] 2^(-(DB - 1) - DB s) + O(2^(-DB NS + 1)), every step exact in FP64
 template <int NS>
 __device__ __forceinline__ void i8_slices(double u, int (&s)[NS]) {
+#if I8_DIGIT_BITS == 8
+  double r = u * 128.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double q = rint(r);          // in [-128, 128]: a remainder of +-1/2 becomes +-128
+    s[i] = (int)q;
+    r = (r - q) * 256.0;
+  }
+#pragma unroll
+  for (int i = NS - 1; i >= 1; i--)    // balanced digits in [-128, 127]: +128 (+129 with a carry) is -128 (-127) and one more above
+    if (s[i] >= 128) { s[i] -= 256; s[i - 1] += 1; }
+#else
   double r = u * 64.0;
 #pragma unroll
   for (int i = 0; i < NS; i++) {
@@ -126,6 +152,7 @@ __device__ __forceinline__ void i8_slices(double u, int (&s)[NS]) {
     s[i] = (int)q;
     r = (r - q) * 128.0;
   }
+#endif
 }
 
 // Tile-major int8 copy of X (+ y and the row exponents), built once per model: tile t of TO observations is
@@ -340,22 +367,36 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
 // (Measured alternatives, clk per warp-evaluation of the merge alone - profiles/microbench/i8_epilogue_rate.cu:
 //  I2F.F64.S64 27.9 | magic-number int64 30.1 | int32 pairs + 3 I2F.S32 + 2 DFMA 28.8 | 3 magic32 + 2 DFMA 30.9 |
 //  6 magic32 + 5 DFMA 42.3.)
-template <int NS, int CH>
+template <int NS, int CH, int KB = 1>
 __device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e, int tune = 0) {
-  int v[(NS + 1) / 2];
-#pragma unroll
-  for (int p = 0; p < NS / 2; p++) v[p] = (int)a[2 * p][e] * 128 + (int)a[2 * p + 1][e];
-  if (NS & 1) v[NS / 2] = (int)a[NS - 1][e];
+  constexpr int DB = I8_DIGIT_BITS;
+  // |a_d| <= (d + 1) 32 KB 2^(2 DB - 2); a merged pair a_{2p} 2^DB + a_{2p+1} stays in int32 while that is below 2^31
+  constexpr long long UNIT = 32LL * KB * (1LL << (2 * DB - 2));
   if (NS <= 6) {
     constexpr int NV = (NS + 1) / 2;
-    long long w = v[NV - 1];
+    long long w;
+    if (NS & 1) {
+      w = (int)a[NS - 1][e];
+    } else if ((NS - 1) * UNIT * (1LL << DB) + NS * UNIT < (1LL << 31)) {
+      w = (int)a[NS - 2][e] * (1 << DB) + (int)a[NS - 1][e];
+    } else {  // 8-bit digits, NS = 6, K = 128: the last pair needs 64 bits
+      w = (long long)(int)a[NS - 2][e] * (1 << DB) + (int)a[NS - 1][e];
+    }
 #pragma unroll
-    for (int p = NV - 2; p >= 0; p--) w += (long long)v[p] * (int)(1u << (7 * (NS - 2 - 2 * p)));
+    for (int p = NV - 2; p >= 0; p--) {
+      static_assert((NS - 2) * UNIT * (1LL << DB) + (NS - 1) * UNIT < (1LL << 31) || NS == 6, "inner pairs fit int32");
+      const int v = (int)a[2 * p][e] * (1 << DB) + (int)a[2 * p + 1][e];
+      w += (long long)v * (1LL << (DB * (NS - 2 - 2 * p)));
+    }
 #ifdef FMCMC_I8_TUNE_HOOKS
     if (tune & 8) return __hiloint2double(0x43300000 | (int)((w >> 32) & 0xfffff), (int)w) - 4503599627370496.0;  // no XU op (value is garbage)
 #endif
     return __ll2double_rn(w);
-  } else {  // 7, 8: two groups
+  } else {  // 7, 8 slices of 7 bits: two groups
+    int v[(NS + 1) / 2];
+#pragma unroll
+    for (int p = 0; p < NS / 2; p++) v[p] = (int)a[2 * p][e] * 128 + (int)a[2 * p + 1][e];
+    if (NS & 1) v[NS / 2] = (int)a[NS - 1][e];
     const long long hi = (long long)v[0] * 16384LL + v[1];
     const long long lo = (long long)v[2] * ((NS & 1) ? 128LL : 16384LL) + v[3];
     return fma(__ll2double_rn(hi), (NS & 1) ? 2097152.0 : 268435456.0, __ll2double_rn(lo));
@@ -515,6 +556,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
                        TiledBuffers tb, const int* __restrict__ err) {
   using G = I8Geom<NS, KB>;
   static_assert(NS >= 2 && NS <= 8, "2..8 slices");
+  static_assert(I8_DIGIT_BITS == 7 || (I8_DIGIT_BITS == 8 && NS <= 6), "8-bit digits: at most 6 slices (int64 merge)");
   static_assert(EW == 8 || EW == 16, "2 or 4 epilogue warps per TMEM lane quarter");
   constexpr int CW = G::BLK / (EW / 4);  // columns (observations) of a block owned by one epilogue warp
   static_assert(CW % CH == 0, "whole chunks");
@@ -599,7 +641,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   const bool eta_in_table = __all_sync(FM_FULL, in_table);
   // ... and for every chain of the CTA: the hot loop runs the degree-3 core on the mean-corrected copy of the table
   // (softplus.h).  The table is chosen per CTA because it is shared: one bulk copy (160 KB), overlapped with the Theta slicing.
-  const bool cta_in_table = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2) ? __all_sync(FM_FULL, __syncthreads_and(in_table) != 0) : false;  // (the vote tells ptxas it is warp-uniform)
+  const bool cta_in_table = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2) ? __all_sync(FM_FULL, __syncthreads_and(in_table && !tb.exact_core) != 0) : false;  // (the vote tells ptxas it is warp-uniform)
   if (FAMILY == FMCMC_FAMILY_LOGISTIC && tid == 0) {
     constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_bytes<NS, KB>(FAMILY);
     mbar_expect_tx(tab_bar, TAB_BYTES);
@@ -759,22 +801,22 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)  // the hot loop of cfg3
-              i8_logistic_lcosh3_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+              i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table) {
             for (int e = 0; e < CH; e++)  // last, partial tile of a CTA on the mean-corrected table
-              if (obs0 + e < valid) i8_logistic_lcosh3_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+              if (obs0 + e < valid) i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && eta_in_table && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)
-              i8_logistic_lcosh_fast(i8_assemble<NS, CH>(a, e, tb.tune), csc, acc2, sp_tab);
+              i8_logistic_lcosh_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 1 && eta_small && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)
-              i8_logistic_even_t<1, false>(i8_assemble<NS, CH>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+              i8_logistic_even_t<1, false>(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
           } else if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {
-              const double t = i8_assemble<NS, CH>(a, e, tb.tune);
+              const double t = i8_assemble<NS, CH, KB>(a, e, tb.tune);
               if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
                 const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);  // warp-uniform address: broadcast
                 acc = fma(r, r, acc);
@@ -788,7 +830,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll
             for (int e = 0; e < CH; e++) {
               if (obs0 + e < valid) {
-                const double t = i8_assemble<NS, CH>(a, e, tb.tune);
+                const double t = i8_assemble<NS, CH, KB>(a, e, tb.tune);
                 if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM) {
                   const double r = __ldg(ymeta + obs0 + e) - fma(t, csc, b0);
                   acc = fma(r, r, acc);

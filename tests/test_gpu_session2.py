@@ -94,9 +94,9 @@ def test_model_trim_keeps_the_path_and_frees_the_rest():
             m.run(spec, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
         with pytest.raises(fm.FmcmcError, match="released"):
             m.logpost(init[:2])
-        ram = dict(type=A.KERNEL_RAM, k=24)          # kernel_ram needs 7 slices: X is gone, so this must be refused, not mis-run
+        ram = dict(type=A.KERNEL_RAM, k=24)          # kernel_ram needs one more slice: X is gone, so this must be refused, not mis-run
         m.set_path(4)
-        with pytest.raises(fm.FmcmcError, match="7"):
+        with pytest.raises(fm.FmcmcError, match="needs 6"):
             m.run(ram, T, C, initial=init, stream=A.marshal_stream(A.STREAM_PHILOX, seed=1))
     finally:
         m.close()
