@@ -826,7 +826,7 @@ def main():
                 # every instruction of the epilogue runs on a 16-lane datapath (FP64, IMAD / IMAD.WIDE, SHF, I2F, LDS): the
                 # scheduler issues one warp instruction per 2 clk whatever the pipe (ncu: issue-active 47 % of cycles with
                 # not-selected warps waiting), so the instruction count, not the FP64 count alone, is what bounds the kernel
-                instr = 18                                                      # 10 FP64 + 2 IMAD + 2 IMAD.WIDE + SHF + I2F + LEA + LDS.128
+                instr = 17                                                      # 10 FP64 + 2 IMAD + LEA.HI.SX32 + IMAD.WIDE + I2F + LEA + LDS.128
                 t_issue = evals * instr / 32.0 * 2.0 / (148 * 4 * sm_clock * 1e6)
                 line["roofline_two_engine"].update({
                     "instr_per_eval": instr, "issue_floor_ms": 1e3 * (t_tensor + t_issue),

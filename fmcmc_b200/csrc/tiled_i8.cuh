@@ -372,7 +372,19 @@ __device__ __forceinline__ double i8_assemble(const uint32_t (&a)[NS][CH], int e
   constexpr int DB = I8_DIGIT_BITS;
   // |a_d| <= (d + 1) 32 KB 2^(2 DB - 2); a merged pair a_{2p} 2^DB + a_{2p+1} stays in int32 while that is below 2^31
   constexpr long long UNIT = 32LL * KB * (1LL << (2 * DB - 2));
-  if (NS <= 6) {
+  if constexpr (NS == 5 && DB == 8 && 4 * UNIT * 256 + 5 * UNIT < (1LL << 31)) {
+    // five diagonals, K <= 64: pairs (a1, a2) and (a3, a4) in int32, the unpaired diagonal on TOP - a0 2^32 is an add into the
+    // high word, where an unpaired a4 at the bottom needs a sign extension and a register move to become a 64-bit addend:
+    // 2 IMAD + SHF + IMAD.WIDE + IADD + I2F
+    const int v1 = (int)a[1][e] * 256 + (int)a[2][e];
+    const int v2 = (int)a[3][e] * 256 + (int)a[4][e];
+    // the 64-bit addend of the multiply-add is (v2, sign(v2) + a0): a0 2^32 rides on the sign extension of v2
+    const int hi0 = (v2 >> 31) + (int)a[0][e];
+    long long addend;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(addend) : "r"(v2), "r"(hi0));
+    const long long w = (long long)v1 * 65536LL + addend;
+    return __ll2double_rn(w);
+  } else if (NS <= 6) {
     constexpr int NV = (NS + 1) / 2;
     long long w;
     if (NS & 1) {
@@ -490,12 +502,15 @@ __device__ __forceinline__ double i8_lcosh3_core(double d, double tau, double Ta
   const double Q = fma(d, P, tau);
   return fma(d, Q, Tacc);
 }
-__device__ __forceinline__ void i8_logistic_lcosh3_fast(double t, double csc, double& acc_h, const double2* __restrict__ tab) {
+// tab_s: the table's 32-bit shared-window address (computed once per kernel: through a generic pointer ptxas re-derives the
+// window base - S2UR SR_CgaCtaId + 3 uniform instructions - in every chunk)
+__device__ __forceinline__ void i8_logistic_lcosh3_fast(double t, double csc, double& acc_h, uint32_t tab_s) {
   constexpr double MAGICH = i8_magic_h<2>();
   const double t2 = fma(fabs(t), csc, MAGICH);
   const double d = fma(fabs(t), csc, MAGICH - t2);
-  const double2 tt = tab[__double2loint(t2)];
-  acc_h = i8_lcosh3_core(d, tt.x, acc_h + tt.y);
+  double tx, ty;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tab_s + ((uint32_t)__double2loint(t2) << 4)));
+  acc_h = i8_lcosh3_core(d, tx, acc_h + ty);
 }
 // FAST: the warp's chains bound |eta| <= 39.9 over ALL observations (i8 prologue: min(sum_j |theta_j| max_i |x_ij|,
 // |theta|_2 max_i |x_i|_2)), so round(256 |eta|) indexes the table as it is - no clamp of any kind: 12 FP64 + 7 (merge) +
@@ -741,6 +756,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     double acc = 0.0, acc2 = 0.0;
     uint32_t blk = 0;
     long long it = 0;
+    const uint32_t sp_tab_s = smem_u32(sp_tab);
     constexpr bool GRP = I8_GROUPED != 0 && EW == 16;
     constexpr int CWG = GRP ? 2 * CW : CW;          // columns of a block owned by this warp
     const int grp = h & 1;                          // GRP: the accumulator set this warp serves
@@ -801,10 +817,10 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)  // the hot loop of cfg3
-              i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab);
+              i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab_s);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table) {
             for (int e = 0; e < CH; e++)  // last, partial tile of a CTA on the mean-corrected table
-              if (obs0 + e < valid) i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab);
+              if (obs0 + e < valid) i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab_s);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && eta_in_table && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)
