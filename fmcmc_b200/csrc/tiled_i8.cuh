@@ -66,6 +66,10 @@
 #ifndef I8_DIGIT_BITS
 #define I8_DIGIT_BITS 8
 #endif
+#ifndef I8_TRIPLE
+#define I8_TRIPLE 0   // 1: three accumulator sets where they fit (I8Geom::NACC).  Measured on B200 (cfg3): 1.537 ms against 1.517
+#endif                // with two - the waiting it removes comes back as math-pipe stalls (profiles/r02_findings.md, section 9)
+
 #define I8_NS_LO (I8_DIGIT_BITS == 8 ? 5 : 6)   // slices of the default accuracy tier; kernel_ram and n < 65 536 use one more
 template <int NS, int KB>
 struct I8Geom {
@@ -78,12 +82,24 @@ struct I8Geom {
   static constexpr int SLICE_BYTES = NBLK * BLOCK_BYTES;
   static constexpr int STAGE_BYTES = SLICE_BYTES;                   // a stage is pure MMA operand: only the tensor pipe holds it
   static constexpr int ACC_COLS = NS * BLK;                         // TMEM columns of one accumulator set
-  // A operand (Theta slices): as many K blocks as fit tensor memory next to the two accumulator sets (8 columns per
-  // slice and K block), the rest in shared memory - every MMA whose A comes from shared memory re-reads 4 KB
-  static constexpr int A_COL0 = 2 * ACC_COLS;
-  static constexpr int A_TKB = ((512 - A_COL0) / (NS * 8)) < KB ? ((512 - A_COL0) / (NS * 8)) : KB;
+  // Accumulator sets: two - or, with -DI8_TRIPLE=1, THREE when they fit tensor memory with all but the last Theta slice beside
+  // them (K = 32, 5 slices: 3 x 160 + 4 x 8 = 512 columns exactly).  With two sets a group of epilogue warps waits for the MMAs of
+  // its next block (12 % of the warps' time in round 2's profile); with three the MMA warp runs a block ahead - correct
+  // (all parity tests), but not faster: while the tensor pipe works the FP64 pipe does not, wherever the warps happen to wait.
+  static constexpr int NACC = (I8_TRIPLE != 0 && KB == 1 && 3 * ACC_COLS + (NS - 1) * 8 <= 512) ? 3 : 2;
+  // A operand (Theta slices): 8 columns per (slice, K block) unit.  NACC == 2: as many K blocks as fit beside the two sets
+  // live in tensor memory (all slices of those K blocks), the rest in shared memory; NACC == 3: slices 0 .. NS-2 in tensor
+  // memory, the last slice (one MMA of N = 32 per block) in shared memory.  An MMA whose A comes from shared memory re-reads 4 KB.
+  static constexpr int A_COL0 = NACC * ACC_COLS;
+  static constexpr int A_TS = NACC == 3 ? NS - 1 : NS;
+  static constexpr int A_TKB = NACC == 3 ? 1 : (((512 - A_COL0) / (NS * 8)) < KB ? ((512 - A_COL0) / (NS * 8)) : KB);
   static constexpr int A_SKB = KB - A_TKB;
-  static constexpr int A_SMEM_BYTES = NS * A_SKB * 4096;
+  static constexpr int A_SMEM_BYTES = (NS * A_SKB + (NS - A_TS) * A_TKB) * 4096;
+  __host__ __device__ static constexpr bool a_in_tmem(int i, int kb) { return kb < A_TKB && i < A_TS; }
+  __host__ __device__ static constexpr int a_tmem_col(int i, int kb) { return A_COL0 + (i * A_TKB + kb) * 8; }
+  __host__ __device__ static constexpr int a_smem_unit(int i, int kb) {
+    return kb < A_TKB ? NS * A_SKB + (i - A_TS) * A_TKB + kb : i * A_SKB + (kb - A_TKB);
+  }
   static constexpr int SHIFT = 2 * (DB - 1) + DB * (NS - 1);        // eta = t * 2^(eth - SHIFT)
 };
 
@@ -578,11 +594,12 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   constexpr int STAGES = i8_stages<NS, KB>(FAMILY);
-  static_assert(STAGES >= 2 && 2 * STAGES + 5 <= 31, "barriers live in the first 256 bytes");
+  constexpr int NACC = G::NACC;
+  static_assert(STAGES >= 2 && 2 * STAGES + 2 * NACC + 2 <= 32, "barriers live in the first 256 bytes");
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* tab_bar = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint64_t* tab_bar = acc_empty + NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_bar + 1);
   unsigned char* stage0 = smem_raw + 256;
   unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
@@ -606,7 +623,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);  // released by the MMA warp's tcgen05.commit alone
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < NACC; b++) {
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], I8_GROUPED ? EW / 2 : EW);
     }
@@ -680,17 +697,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       }
 #pragma unroll
       for (int i = 0; i < NS; i++) {
-        if (kb < G::A_TKB) {
-          tc_st_x8(tmem + G::A_COL0 + (i * G::A_TKB + kb) * 8 + ((uint32_t)(warp * 32) << 16), w[i]);
+        if (G::a_in_tmem(i, kb)) {
+          tc_st_x8(tmem + G::a_tmem_col(i, kb) + ((uint32_t)(warp * 32) << 16), w[i]);
         } else {
-          unsigned char* p = sA + (size_t)(i * G::A_SKB + (kb - G::A_TKB)) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
+          unsigned char* p = sA + (size_t)G::a_smem_unit(i, kb) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
           *reinterpret_cast<uint4*>(p) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
           *reinterpret_cast<uint4*>(p + 128) = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
         }
       }
     }
     if (G::A_TKB > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (G::A_SKB > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (G::A_SMEM_BYTES > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -715,7 +732,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed int8, K-major, N >> 3, M >> 4
     constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_CHAINS >> 4) << 24);
     const uint32_t sA_addr = smem_u32(sA);
-    uint32_t blk = 0;
+    uint32_t buf = 0, par = 0;  // accumulator set of the next block and the phase of its barriers (block n: n % NACC, (n / NACC) & 1)
     long long it = 0;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
       const int s = (int)(it % STAGES);
@@ -723,9 +740,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       tc_fence_after();
       const uint32_t sbase = smem_u32(stage0 + (size_t)s * G::STAGE_BYTES);
 #pragma unroll 1
-      for (int b = 0; b < G::NBLK; b++, blk++) {
-        const uint32_t buf = blk & 1u;
-        mbar_wait_sleep(&acc_empty[buf], ((blk >> 1) & 1u) ^ 1u, 32);
+      for (int b = 0; b < G::NBLK; b++) {
+        mbar_wait_sleep(&acc_empty[buf], par ^ 1u, 32);
         tc_fence_after();
         const uint32_t bblk = sbase + (uint32_t)b * G::BLOCK_BYTES;
         const uint32_t dbase = tmem + buf * G::ACC_COLS;
@@ -737,13 +753,14 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
               const uint32_t idesc = IDESC0 | ((uint32_t)((G::BLK * (NS - j)) >> 3) << 17);
               const uint64_t bdesc = tc_smem_desc(bblk + (uint32_t)(kb * NS) * G::SLAB_BYTES, 128u, 256u);
               const uint32_t accum = (j > 0 || kb > 0) ? 1u : 0u;
-              if (kb < G::A_TKB) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::A_COL0 + (j * G::A_TKB + kb) * 8, bdesc, idesc, accum);
-              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)(j * G::A_SKB + (kb - G::A_TKB)) * 4096u, 128u, 256u), bdesc, idesc, accum);
+              if (G::a_in_tmem(j, kb)) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::a_tmem_col(j, kb), bdesc, idesc, accum);
+              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)G::a_smem_unit(j, kb) * 4096u, 128u, 256u), bdesc, idesc, accum);
             }
           }
           tc_commit(&acc_full[buf]);
         }
         __syncwarp();
+        if (++buf == (uint32_t)NACC) { buf = 0; par ^= 1u; }
       }
       if (elect_one()) tc_commit(&empty[s]);  // the stage's slices are free once every MMA that reads them has retired
       __syncwarp();
@@ -754,31 +771,23 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     const uint32_t lane_base = ((uint32_t)(q * 32) << 16) + __reduce_min_sync(FM_FULL, tmem);
     if (FAMILY == FMCMC_FAMILY_LOGISTIC) mbar_wait(tab_bar, 0u);  // the softplus table has landed
     double acc = 0.0, acc2 = 0.0;
-    uint32_t blk = 0;
     long long it = 0;
     const uint32_t sp_tab_s = smem_u32(sp_tab);
     constexpr bool GRP = I8_GROUPED != 0 && EW == 16;
     constexpr int CWG = GRP ? 2 * CW : CW;          // columns of a block owned by this warp
-    const int grp = h & 1;                          // GRP: the accumulator set this warp serves
+    const int grp = h & 1;                          // GRP: this warp's group; it visits every other block
     const int hcol = GRP ? (h >> 1) * CWG : h * CW;
+    constexpr int BSTEP = GRP ? 2 : 1;              // blocks between two visits
+    // accumulator set and barrier phase of the next block this warp visits (block n: n % NACC, (n / NACC) & 1)
+    uint32_t buf = GRP ? (uint32_t)grp : 0u, par = 0u;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
       const double* ymeta = mp.y + tile * G::TO;  // L1-resident broadcast loads (Gaussian / non-binary logistic only)
       const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
-      // two blocks per trip when a stage holds an even number: the accumulator set (hence the barrier and the TMEM
-      // address) is then known at compile time and the phase bit is shared by the pair
-      constexpr int UNR = (G::NBLK % 2 == 0) ? 2 : 1;
+      // the first block of this stage that belongs to the warp's group (blocks are numbered across stages)
+      const int bfirst = GRP ? ((G::NBLK & 1) ? (int)((grp - (int)(it & 1)) & 1) : grp) : 0;
 #pragma unroll 1
-      for (int bpair = 0; bpair < G::NBLK; bpair += UNR) {
-      const uint32_t par = (blk >> 1) & 1u;
-      // GRP with an even number of blocks per stage: ONE body per pair - this group's block of the pair (its set is a per-warp
-      // constant, so barrier and TMEM addresses are loop-invariant uniform values); otherwise every block is visited and the
-      // other group's are skipped
-      constexpr int NBB = (GRP && UNR == 2) ? 1 : UNR;
-#pragma unroll
-      for (int bb = 0; bb < NBB; bb++, blk += (GRP && UNR == 2) ? 2 : 1) {
-        const int b = (GRP && UNR == 2) ? bpair + grp : bpair + bb;
-        const uint32_t buf = (GRP && UNR == 2) ? (uint32_t)grp : (UNR == 2 ? (uint32_t)bb : (blk & 1u));
-        if (GRP && UNR != 2 && buf != (uint32_t)grp) continue;  // the other group's set (warp-uniform)
+      for (int b = bfirst; b < G::NBLK; b += BSTEP) {
+      {
         mbar_wait(&acc_full[buf], par);
         tc_fence_after();
 #ifdef I8_CC_UNROLL
@@ -794,7 +803,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll
             for (int d = 0; d < NS; d++)
 #pragma unroll
-              for (int e = 0; e < CH; e++) a[d][e] = (uint32_t)(lane * 37 + d * 11 + e + (int)blk);
+              for (int e = 0; e < CH; e++) a[d][e] = (uint32_t)(lane * 37 + d * 11 + e + (int)buf);
           } else
 #endif
           {
@@ -859,6 +868,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             }
           }
         }
+        buf += BSTEP;
+        if (buf >= (uint32_t)NACC) { buf -= (uint32_t)NACC; par ^= 1u; }
       }
       }
     }
