@@ -90,7 +90,7 @@ def _paths(c):
     if fam == "hier_normal":
         return [0]
     p_x = np.atleast_2d(c["fam"]["X"]).shape[1] if c["fam"]["X"].ndim > 1 else 1
-    return [0, 1, 3] + ([2] if p_x <= 32 else [])
+    return [0, 1, 3, 4] + ([2] if p_x <= 32 else [])     # 4: the split-integer tcgen05 kernel, forced (auto picks it above 128 chains)
 
 
 @pytest.mark.gpu
