@@ -56,6 +56,7 @@ struct ModelParams {
   const double* sp_tab4; // logistic: the 128-per-unit table of the split-integer kernel (softplus.h, FM_SP4_*)
   const double* sp_tab8; // logistic: its 256-per-unit table: (tau, T) of log(2 cosh(a / 2)) (softplus.h, fm_lcosh_table8_fill)
   const double* sp_tab8m; // the same grid with T mean-corrected for the degree-3 core (softplus.h, fm_lcosh_table8m_fill)
+  const double* sp_tab6r; // 64-per-unit least-squares cubics, 256 B per point: (c1, c0) x 8 then (c2, c3) x 8 - one copy per shared-memory bank group (fm_lcosh_table6r_fill)
 };
 
 // Per-run device buffers shared by both paths.
@@ -183,6 +184,14 @@ __device__ __forceinline__ void set_error(int* err, int code, long long chain, l
     err[2] = (int)row;
   }
 }
+
+// ---- programmatic dependent launch (griddepcontrol): the two kernels of an MH row are chained on one stream; with the launch
+// attribute cudaLaunchAttributeProgrammaticStreamSerialization the next kernel's CTAs may become resident - and run everything
+// that does not read the previous kernel's results: barrier / tensor-memory set-up, the first X stages - while the previous
+// kernel is still running.  pdl_wait() returns when the previous kernel has completed and its writes are visible; without
+// the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -43,6 +43,7 @@ static void set_err(char* err, size_t errlen, const char* fmt, ...) {
   } while (0)
 
 #define FM_HOT_EVENTS 64
+#define FM_HOT_EVERY 16   // one likelihood launch in 16 is bracketed by CUDA events (and runs without launch overlap)
 
 struct DevBuf {
   void* p = nullptr;
@@ -70,7 +71,7 @@ struct fmcmc_model {
   int device = 0;
   ModelParams mp{};
   bool borrowed = false;
-  DevBuf X, y, group, sp_tab, sp_tab4, sp_tab8, sp_tab8m, Xt, Xq, xq_bad, xq_aux;
+  DevBuf X, y, group, sp_tab, sp_tab4, sp_tab8, sp_tab8m, sp_tab6r, Xt, Xq, xq_bad, xq_aux;
   int xt_PB = 0;          // padded width the tile-major copy Xt was built for (0 = not built)
   int xq_NS = 0, xq_KB = 0;  // slices / 32-column blocks the int8 tile copy Xq was built for (0 = not built; -1 = X not sliceable)
   int i8_slices = 0;      // int8 slices per operand of path 4: 0 = automatic (5 8-bit digits; 6 for kernel_ram and for n < 65536)
@@ -86,6 +87,7 @@ struct fmcmc_model {
   int trimmed_to = 0;     // fmcmc_model_trim: the only stepping path whose copy of X is still resident (0 = all)
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
   int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
+  bool pdl = true;        // programmatic dependent launch between the two kernels of an MH row (FMCMC_PDL=0 disables; A/B measurements)
   int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
   // run buffers (grow-only)
   DevBuf ans, draws, logpost, cur_theta, cur_f, prop, prop_u, istate, dstate, colsum, ubuf, work, cflags,
@@ -248,12 +250,18 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
     MC(ensure(m->sp_tab8m, tab8.size() * 8));
     MC(cudaMemcpy(m->sp_tab8m.p, tab8.data(), tab8.size() * 8, cudaMemcpyHostToDevice));
     mp.sp_tab8m = m->sp_tab8m.as<double>();
+    std::vector<double> tab6((size_t)FM_LC6_ENTRIES_MAX * (FM_LC6_POINT_BYTES / 8));
+    fm_lcosh_table6r_fill(tab6.data());
+    MC(ensure(m->sp_tab6r, tab6.size() * 8));
+    MC(cudaMemcpy(m->sp_tab6r.p, tab6.data(), tab6.size() * 8, cudaMemcpyHostToDevice));
+    mp.sp_tab6r = m->sp_tab6r.as<double>();
   }
   MC(ensure(m->errbuf, 4 * sizeof(int)));
   MC(ensure(m->nacc, sizeof(unsigned long long)));
 #undef MC
   if (const char* v = getenv("FMCMC_TILED_VARIANT")) { if (atoi(v) == 2 || atoi(v) == 3) m->tiled_default = atoi(v); }
   if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
+  if (const char* v = getenv("FMCMC_PDL")) m->pdl = atoi(v) != 0;
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
   if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= I8_NS_LO && atoi(v) <= I8_NS_LO + 1) m->i8_slices = atoi(v); }
@@ -272,7 +280,7 @@ extern "C" int fmcmc_model_create_device(const fmcmc_model_desc* d, int device, 
 extern "C" void fmcmc_model_free(fmcmc_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
-  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->sp_tab4, &m->sp_tab8, &m->sp_tab8m, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
+  DevBuf* bufs[] = {&m->X, &m->y, &m->group, &m->sp_tab, &m->sp_tab4, &m->sp_tab8, &m->sp_tab8m, &m->sp_tab6r, &m->Xt, &m->Xq, &m->xq_bad, &m->xq_aux, &m->ans, &m->draws, &m->logpost, &m->cur_theta, &m->cur_f, &m->prop,
                     &m->prop_u, &m->istate, &m->dstate, &m->colsum, &m->ubuf, &m->work, &m->cflags, &m->errbuf,
                     &m->nacc, &m->spec, &m->fed_logu, &m->fed_z, &m->initial, &m->partial, &m->out_ans,
                     &m->out_draws, &m->out_lp, &m->tmp, &m->store, &m->g_xbar, &m->g_s2, &m->g_wsum, &m->g_wpart,
@@ -535,8 +543,22 @@ struct Blob {  // host staging of the small kernel-spec arrays -> one H2D copy
   }
 };
 
+// Launch with (pdl) or without the programmatic-stream-serialization attribute: with it the kernel's CTAs may become resident
+// while the previous kernel of the stream is still running; they order themselves behind it with griddepcontrol.wait (pdl_wait,
+// common.cuh) before touching anything it wrote.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int FAMILY, bool YBIN>
-static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
+static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb, bool pdl) {
   const size_t smem = tiled_smem_bytes(PB, FAMILY);
 #define TL_CASE(P)                                                                                               \
   case P: {                                                                                                      \
@@ -547,8 +569,9 @@ static cudaError_t launch_tiled_loglik(fmcmc_model* m, int PB, dim3 grid, const 
       if (e != cudaSuccess) return e;                                                                            \
       attr_done[m->device] = true;                                                                               \
     }                                                                                                            \
-    tiled_loglik_kernel<FAMILY, P, YBIN><<<grid, TL_THREADS, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u,       \
-                                                                                 rb.nchains, tb, rb.err);        \
+    { cudaError_t e = launch_chained(tiled_loglik_kernel<FAMILY, P, YBIN>, grid, dim3(TL_THREADS), smem, m->stream, pdl, \
+                                     m->mp, rb.prop, rb.prop_u, rb.nchains, tb, rb.err);                          \
+      if (e != cudaSuccess) return e; }                                                                          \
     break;                                                                                                       \
   }
   switch (PB) {
@@ -609,7 +632,7 @@ static cudaError_t ensure_packed_tiles(fmcmc_model* m, int PB) {
 
 template <int FAMILY, bool YBIN>
 static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 grid, const RunBuffers& rb,
-                                    const TiledBuffers& tb) {
+                                    const TiledBuffers& tb, bool pdl) {
 #define TM_CASE(P, W, N, O, S, PP)                                                                                      \
   if (sh.PB == P && sh.warps == W && sh.NT == N && sh.MO == O && sh.osplit == (S ? 1 : 0) && sh.pipe == (PP ? 1 : 0)) {                                                             \
     const size_t smem = tiled_mma_smem_bytes<P>(FAMILY);                                                         \
@@ -620,9 +643,8 @@ static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 gri
       if (e != cudaSuccess) return e;                                                                            \
       attr_done[m->device] = true;                                                                               \
     }                                                                                                            \
-    tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S, PP><<<grid, W * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, \
-                                                                                       rb.nchains, tb, rb.err);  \
-    return cudaGetLastError();                                                                                   \
+    return launch_chained(tiled_loglik_mma_kernel<FAMILY, P, YBIN, W, N, O, S, PP>, grid, dim3(W * 32), smem, m->stream, pdl, \
+                          m->mp, rb.prop, rb.prop_u, rb.nchains, tb, rb.err);                                    \
   }
   TM_CASE(32, 8, 1, 2, true, false)
   TM_CASE(32, 8, 2, 2, true, false)
@@ -712,10 +734,10 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
                           // on the final 1.79 ms kernel: 8 warps 2.01 ms, 8 warps with the chunk loop unrolled 1.92 ms)
 #endif
 template <int FAMILY, bool YBIN>
-static cudaError_t launch_tiled_i8(fmcmc_model* m, int NS, int KB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb) {
+static cudaError_t launch_tiled_i8(fmcmc_model* m, int NS, int KB, dim3 grid, const RunBuffers& rb, const TiledBuffers& tb, bool pdl) {
 #define I8_CASE(N, K)                                                                                             \
   if (NS == N && KB == K) {                                                                                       \
-    const size_t smem = tiled_i8_smem_bytes<N, K>(FAMILY);                                                        \
+    const size_t smem = tiled_i8_smem_bytes<N, K>(FAMILY, YBIN);                                                        \
     static bool attr_done[64] = {};                                                                               \
     if (!attr_done[m->device]) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(tiled_loglik_i8_kernel<FAMILY, YBIN, N, K, I8_EPI_WARPS, I8_EPI_CHUNK>, \
@@ -723,9 +745,8 @@ static cudaError_t launch_tiled_i8(fmcmc_model* m, int NS, int KB, dim3 grid, co
       if (e != cudaSuccess) { cudaGetLastError(); return e; }                                                     \
       attr_done[m->device] = true;                                                                                \
     }                                                                                                             \
-    tiled_loglik_i8_kernel<FAMILY, YBIN, N, K, I8_EPI_WARPS, I8_EPI_CHUNK>                                        \
-        <<<grid, (I8_EPI_WARPS + 2) * 32, smem, m->stream>>>(m->mp, rb.prop, rb.prop_u, rb.nchains, tb, rb.err);  \
-    return cudaGetLastError();                                                                                    \
+    return launch_chained(tiled_loglik_i8_kernel<FAMILY, YBIN, N, K, I8_EPI_WARPS, I8_EPI_CHUNK>, grid,          \
+                          dim3((I8_EPI_WARPS + 2) * 32), smem, m->stream, pdl, m->mp, rb.prop, rb.prop_u, rb.nchains, tb, rb.err); \
   }
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
@@ -1036,6 +1057,11 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const int mat_doubles = (mat_bytes && mat_bytes <= (size_t)40 * 1024) ? mat_mats * kf * kf : 0;
     const size_t hsmem = (size_t)TL_HEAD_WARPS * (4 * k + mat_doubles) * 8;
     const int kclass = kernel_class(ks->type);
+    // Programmatic dependent launch chains head(row) -> likelihood(row) -> head(row + 1) ...: each kernel's CTAs may set
+    // themselves up while the previous one drains (pdl_wait() in the kernels orders the data).  Not when sharded over
+    // observations (the peer-flag protocol paces the kernels there), and not across the event records of a timed launch.
+    const bool pdl_ok = m->pdl && !(m->shard_world > 1);
+    bool pdl_head = false;
     auto head_launch = [&](long long row) -> cudaError_t {
 #define HEAD_CASE(K)                                                                                              \
   case K:                                                                                                          \
@@ -1043,7 +1069,9 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       cudaError_t e_ = cudaFuncSetAttribute(tiled_head_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem); \
       if (e_ != cudaSuccess) return e_;                                                                            \
     }                                                                                                              \
-    tiled_head_kernel<K><<<hblocks, TL_HEAD_WARPS * 32, hsmem, m->stream>>>(mp, kp, sp, rb, tb, d_initial, row, mat_doubles); \
+    { cudaError_t e_ = launch_chained(tiled_head_kernel<K>, dim3(hblocks), dim3(TL_HEAD_WARPS * 32), hsmem, m->stream, pdl_head, \
+                                      mp, kp, sp, rb, tb, d_initial, row, mat_doubles);                            \
+      if (e_ != cudaSuccess) return e_; }                                                                          \
     break;
       switch (kclass) {
         HEAD_CASE(KC_ADAPT)
@@ -1081,17 +1109,21 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         }
       }
     }
-    long long next_chunk = 0;
+    long long next_chunk = 0, hot_seen = 0;
     for (long long row = 1; row <= T + 1; row++) {
+      bool head_direct = true;   // no event record between this row's head kernel and its likelihood launch
       { cudaError_t he = head_launch(row); if (he != cudaSuccess) { set_err(err, errlen, "CUDA error %s (tiled_head)", cudaGetErrorString(he)); return FMCMC_ECUDA; } }
       launches += 1;
       if (next_chunk < stream_nchunks) {  // head(row) finalises source row row - 2 (0-based): is chunk `next_chunk` complete?
         const long long r1 = std::min<long long>(keep, (next_chunk + 1) * stream_chunk);
         const long long last_src = run->burnin + r1 * run->thin - 1;
-        if (row - 2 >= last_src) { cudaEventRecord(m->chunk_ev[next_chunk], m->stream); next_chunk++; }
+        if (row - 2 >= last_src) { cudaEventRecord(m->chunk_ev[next_chunk], m->stream); next_chunk++; head_direct = false; }
       }
       if (row <= T && !(row == 1 && !d_initial)) {  // f(theta0) of a continued run is already on the device
-        const bool timed = hot_timed < FM_HOT_EVENTS;
+        // the hot kernel is bracketed by events on every 16th launch of a call (the first included): a timed launch runs
+        // alone - its time is the kernel's own -, the others overlap their set-up with the head kernel
+        const bool timed = hot_timed < FM_HOT_EVENTS && (hot_seen++ % FM_HOT_EVERY) == 0;
+        const bool pdl = pdl_ok && !timed && head_direct;
         if (sharded) {
           tb.sx.step = ++m->shard_step;
           tb.partial = m->shard_partial + (size_t)(tb.sx.step & 1ULL) * tb.sx.parity_stride;
@@ -1100,21 +1132,22 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
         cudaError_t e;
         if (path == 4)
           e = (mp.family == FMCMC_FAMILY_LOGISTIC)
-                  ? (mp.y_binary ? launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, true>(m, i8_NS, i8_KB, lgrid, rb, tb)
-                                 : launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, false>(m, i8_NS, i8_KB, lgrid, rb, tb))
-                  : launch_tiled_i8<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, i8_NS, i8_KB, lgrid, rb, tb);
+                  ? (mp.y_binary ? launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, true>(m, i8_NS, i8_KB, lgrid, rb, tb, pdl)
+                                 : launch_tiled_i8<FMCMC_FAMILY_LOGISTIC, false>(m, i8_NS, i8_KB, lgrid, rb, tb, pdl))
+                  : launch_tiled_i8<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, i8_NS, i8_KB, lgrid, rb, tb, pdl);
         else if (path == 3)
           e = (mp.family == FMCMC_FAMILY_LOGISTIC)
-                  ? (mp.y_binary ? launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, true>(m, msh, lgrid, rb, tb)
-                                 : launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, false>(m, msh, lgrid, rb, tb))
-                  : launch_tiled_mma<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, msh, lgrid, rb, tb);
+                  ? (mp.y_binary ? launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, true>(m, msh, lgrid, rb, tb, pdl)
+                                 : launch_tiled_mma<FMCMC_FAMILY_LOGISTIC, false>(m, msh, lgrid, rb, tb, pdl))
+                  : launch_tiled_mma<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, msh, lgrid, rb, tb, pdl);
         else
           e = (mp.family == FMCMC_FAMILY_LOGISTIC)
-                  ? (mp.y_binary ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, true>(m, PB, lgrid, rb, tb)
-                                 : launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, false>(m, PB, lgrid, rb, tb))
-                  : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, PB, lgrid, rb, tb);
+                  ? (mp.y_binary ? launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, true>(m, PB, lgrid, rb, tb, pdl)
+                                 : launch_tiled_loglik<FMCMC_FAMILY_LOGISTIC, false>(m, PB, lgrid, rb, tb, pdl))
+                  : launch_tiled_loglik<FMCMC_FAMILY_GAUSSIAN_LM, false>(m, PB, lgrid, rb, tb, pdl);
         if (e != cudaSuccess) { set_err(err, errlen, "CUDA launch error %s (tiled_loglik)", cudaGetErrorString(e)); return FMCMC_ECUDA; }
         if (timed) cudaEventRecord(m->hot_ev[2 * hot_timed + 1], m->stream), hot_timed++;
+        pdl_head = pdl;   // the next head kernel follows this launch directly unless an event record sits between them
         launches += 1;
       }
     }

@@ -316,6 +316,63 @@ FM_HD double fm_lcosh_tab8m(double a, const double* tab) {   // host reference: 
   const double d = a + (MAGICH - t2);
   return fm_lcosh_tab8m_core(d, tab[2 * k], tab[2 * k + 1]);
 }
+// ---- the bank-group-replicated cubic table: two conflict-free loads instead of three FP64 instructions ----
+// The hot loop's time is its issued instructions (profiles/r01_i8_findings.md, section 4b), and three of the ten FP64
+// instructions of the degree-3 core only rebuild the quadratic and cubic coefficients from tau (u = 1/4 - tau^2, -tau/3, their
+// product).  Reading them from the table instead costs a second LDS.128 - which the shared-memory data pipe (128 B per clock
+// and SM) only affords if the gather is free of bank conflicts: an LDS.128 is served a quarter-warp (8 lanes) at a time, 8
+// random 16-byte entries fall on the 8 four-bank groups with a maximum load of ~2.6, ~10 wavefronts instead of 4.  Here every
+// table point k is 256 bytes: eight copies of (c1, c0) followed by eight copies of (c2, c3); lane l reads copy l % 8 of each,
+// i.e. bank group l % 8 whatever k is - each load is exactly 4 wavefronts.  184 KB of shared memory hold 721 points: a
+// 64-per-unit grid up to a = 11.25; chains whose bound on |eta| is larger use the 256-per-unit tables above.
+// With four free coefficients per cell the cubic is the LEAST-SQUARES fit of h on the cell (uniform weight; Legendre projection
+// of the degree-6 Taylor expansion: d^4 -> 6/7 D^2 d^2 - 3/35 D^4, d^5 -> 10/9 D^2 d^3 - 5/21 D^4 d, d^6 -> 5/7 D^4 d^2 - 2/21 D^6,
+// D = 1/128 the half-width), so the error is orthogonal to 1, d, d^2, d^3 over the cell - zero-mean in particular - and equals
+// (8/35) c4 D^4 P4(d / D): <= 4.5e-12 at the cell edges for a = 0, rms <= 1.5e-12, decaying like sech^2(a / 2); that is the size
+// of the slicing error the same evaluation already carries in eta (5.5e-12 of the largest term) and averages out like it.
+#define FM_LC6_H 64
+#define FM_LC6_REP 8
+#define FM_LC6_POINT_BYTES (2 * 16 * FM_LC6_REP)
+#define FM_LC6_ENTRIES_MAX 721
+static inline void fm_lcosh_cubic_coeffs(long double x, long double D, long double c[4]) {   // LSQ cubic of h on [x - D, x + D]
+  const long double E = expl(-x);
+  const long double tau = 0.5L - E / (1.0L + E), u = 0.25L - tau * tau;
+  const long double c0 = 0.5L * x + log1pl(E), c1 = tau, c2 = u / 2.0L, c3 = -tau * u / 3.0L;
+  const long double c4 = u * (1.0L - 6.0L * u) / 24.0L, c5 = -2.0L * tau * u * (1.0L - 12.0L * u) / 120.0L;
+  const long double c6 = -2.0L * (u * u * (1.0L - 12.0L * u) - 2.0L * tau * tau * u * (1.0L - 24.0L * u)) / 720.0L;
+  const long double D2 = D * D, D4 = D2 * D2, D6 = D4 * D2;
+  c[0] = c0 - (3.0L / 35.0L) * c4 * D4 - (2.0L / 21.0L) * c6 * D6;
+  c[1] = c1 - (5.0L / 21.0L) * c5 * D4;
+  c[2] = c2 + (6.0L / 7.0L) * c4 * D2 + (5.0L / 7.0L) * c6 * D4;
+  c[3] = c3 + (10.0L / 9.0L) * c5 * D2;
+}
+static inline void fm_lcosh_table6r_fill(double* tab) {   // tab: FM_LC6_ENTRIES_MAX * FM_LC6_POINT_BYTES / 8 doubles
+  for (int k = 0; k < FM_LC6_ENTRIES_MAX; k++) {
+    long double c[4];
+    fm_lcosh_cubic_coeffs((long double)k / FM_LC6_H, 0.5L / FM_LC6_H, c);
+    double* pt = tab + (size_t)k * (FM_LC6_POINT_BYTES / 8);
+    for (int r = 0; r < FM_LC6_REP; r++) {
+      pt[2 * r] = (double)c[1];
+      pt[2 * r + 1] = (double)c[0];
+      pt[2 * FM_LC6_REP + 2 * r] = (double)c[2];
+      pt[2 * FM_LC6_REP + 2 * r + 1] = (double)c[3];
+    }
+  }
+}
+FM_HD double fm_lcosh_tab6r_core(double d, double c1, double c0, double c2, double c3) {
+  const double q1 = fma(d, c3, c2);
+  const double q2 = fma(d, q1, c1);
+  return fma(d, q2, c0);
+}
+FM_HD double fm_lcosh_tab6r(double a, const double* tab, int r) {   // host reference: 0 <= a <= 11.25, copy r
+  const double MAGICH = 105553116266496.0;  // 1.5 * 2^46: ulp = 1/64
+  const double t2 = a + MAGICH;
+  uint32_t k = (uint32_t)fm_double_to_bits(t2);
+  k = k > (uint32_t)(FM_LC6_ENTRIES_MAX - 1) ? (uint32_t)(FM_LC6_ENTRIES_MAX - 1) : k;
+  const double d = a + (MAGICH - t2);
+  const double* pt = tab + (size_t)k * (FM_LC6_POINT_BYTES / 8) + 2 * (size_t)(r & (FM_LC6_REP - 1));
+  return fm_lcosh_tab6r_core(d, pt[0], pt[1], pt[2 * FM_LC6_REP], pt[2 * FM_LC6_REP + 1]);
+}
 // reference composition (host tests): 0 <= a <= 40
 FM_HD double fm_lcosh_tab8(double a, const double* tab) {
   const double MAGICH = 26388279066624.0;  // 1.5 * 2^44: ulp = 1/256

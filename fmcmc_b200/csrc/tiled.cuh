@@ -81,6 +81,8 @@ tiled_loglik_kernel(ModelParams mp, const double* __restrict__ prop, const doubl
   double* stage0 = reinterpret_cast<double*>(smem_raw + 128);
   constexpr int STAGE_DOUBLES = PB * TL_TILE + TL_TILE;
   const int tid = threadIdx.x, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (err[0] != 0) return;
   double2* sp_tab = reinterpret_cast<double2*>(stage0 + (size_t)TL_STAGES * STAGE_DOUBLES);
   if (FAMILY == FMCMC_FAMILY_LOGISTIC) {  // 32 KB, L2-resident after the first CTA; read by generic loads only
@@ -218,6 +220,10 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long c = (long long)blockIdx.x * TL_HEAD_WARPS + warp;
+  // the likelihood kernel of this row may set itself up beside us (it reads the proposals only after its own pdl_wait);
+  // everything below reads what the previous likelihood launch wrote
+  pdl_launch_dependents();
+  pdl_wait();
   if (c >= rb.nchains || rb.err[0] != 0) return;
   const int k = kp.k;
   double* scr = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (4 * k + mat_doubles);

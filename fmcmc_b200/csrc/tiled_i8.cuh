@@ -116,21 +116,34 @@ __host__ __device__ constexpr int i8_table_level() {
 }
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_table_entries() { return i8_table_level<NS, KB>() == 2 ? FM_SP8_ENTRIES : FM_SP4_ENTRIES; }
+// level 3 (binary logistic with the level-2 table only): the bank-group-replicated cubic table (softplus.h,
+// fm_lcosh_table6r_fill; 256 B per point) - as many points as fit beside TWO pipeline stages, i.e. |eta| up to ~11; chosen per
+// CTA when every chain of the CTA bounds |eta| below the table's end, else the CTA loads a level-2 table into the same region.
+#ifndef I8_REP_TABLE
+#define I8_REP_TABLE 1
+#endif
 template <int NS, int KB>
-__host__ __device__ constexpr int i8_table_bytes(int family) {
-  return family == FMCMC_FAMILY_LOGISTIC ? i8_table_entries<NS, KB>() * 16 : 0;
+__host__ __device__ constexpr int i8_rep_entries() {
+  const int fit = (232448 - i8_smem_fixed<NS, KB>(0) - 2 * I8Geom<NS, KB>::STAGE_BYTES) / FM_LC6_POINT_BYTES;
+  const int e = fit > FM_LC6_ENTRIES_MAX ? FM_LC6_ENTRIES_MAX : fit;
+  return (I8_REP_TABLE != 0 && i8_table_level<NS, KB>() == 2 && e >= 5 * FM_LC6_H + 1) ? e : 0;  // worth it from |eta| <= 5 on
+}
+template <int NS, int KB>
+__host__ __device__ constexpr int i8_table_bytes(int family, bool ybin) {
+  const int plain = i8_table_entries<NS, KB>() * 16, rep = ybin ? i8_rep_entries<NS, KB>() * FM_LC6_POINT_BYTES : 0;
+  return family == FMCMC_FAMILY_LOGISTIC ? (plain > rep ? plain : rep) : 0;
 }
 // pipeline depth: as many stages as fit beside the Theta slices and the softplus table, at most 6.
 template <int NS, int KB>
-__host__ __device__ constexpr int i8_stages(int family) {
-  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family))) / I8Geom<NS, KB>::STAGE_BYTES;
+__host__ __device__ constexpr int i8_stages(int family, bool ybin) {
+  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin))) / I8Geom<NS, KB>::STAGE_BYTES;
   return fit > 6 ? 6 : fit;
 }
 template <int NS, int KB>
-__host__ __device__ inline size_t tiled_i8_smem_bytes(int family) {
+__host__ __device__ inline size_t tiled_i8_smem_bytes(int family, bool ybin) {
   using G = I8Geom<NS, KB>;
-  size_t b = 256 + (size_t)i8_stages<NS, KB>(family) * G::STAGE_BYTES + G::A_SMEM_BYTES +
-             (size_t)i8_table_bytes<NS, KB>(family) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
+  size_t b = 256 + (size_t)i8_stages<NS, KB>(family, ybin) * G::STAGE_BYTES + G::A_SMEM_BYTES +
+             (size_t)i8_table_bytes<NS, KB>(family, ybin) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
 
@@ -528,6 +541,21 @@ __device__ __forceinline__ void i8_logistic_lcosh3_fast(double t, double csc, do
   asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(tab_s + ((uint32_t)__double2loint(t2) << 4)));
   acc_h = i8_lcosh3_core(d, tx, acc_h + ty);
 }
+// level 3, the bank-group-replicated cubic table: tab_lane = table address + 16 (lane % 8), points 256 B apart, (c1, c0) in
+// the first 128 bytes and (c2, c3) in the second - lane l always reads bank group l % 8, so each of the two loads costs
+// 4 wavefronts whatever the indices are.  7 FP64 instructions per evaluation (3 range reduction + 4) instead of 10.
+__device__ __forceinline__ void i8_logistic_cubic_rep(double t, double csc, double& acc_h, uint32_t tab_lane) {
+  constexpr double MAGICH = 105553116266496.0;   // 1.5 * 2^46: ulp = 1 / 64
+  const double t2 = fma(fabs(t), csc, MAGICH);
+  const double d = fma(fabs(t), csc, MAGICH - t2);
+  const uint32_t addr = tab_lane + ((uint32_t)__double2loint(t2) << 8);
+  double c1, c0, c2, c3;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c1), "=d"(c0) : "r"(addr));
+  asm("ld.shared.v2.f64 {%0, %1}, [%2+128];" : "=d"(c2), "=d"(c3) : "r"(addr));
+  const double q1 = fma(d, c3, c2);
+  const double q2 = fma(d, q1, c1);
+  acc_h = fma(d, q2, acc_h + c0);
+}
 // FAST: the warp's chains bound |eta| <= 39.9 over ALL observations (i8 prologue: min(sum_j |theta_j| max_i |x_ij|,
 // |theta|_2 max_i |x_i|_2)), so round(256 |eta|) indexes the table as it is - no clamp of any kind: 12 FP64 + 7 (merge) +
 // address + LDS.128 per evaluation.
@@ -593,7 +621,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   static_assert(CW % CH == 0, "whole chunks");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-  constexpr int STAGES = i8_stages<NS, KB>(FAMILY);
+  constexpr int STAGES = i8_stages<NS, KB>(FAMILY, YBIN);
   constexpr int NACC = G::NACC;
   static_assert(STAGES >= 2 && 2 * STAGES + 2 * NACC + 2 <= 32, "barriers live in the first 256 bytes");
   uint64_t* empty = full + STAGES;
@@ -605,14 +633,13 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   unsigned char* sA = stage0 + (size_t)STAGES * G::STAGE_BYTES;
   double2* sp_tab = reinterpret_cast<double2*>(sA + G::A_SMEM_BYTES);
   double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sp_tab) +
-                                          (size_t)i8_table_bytes<NS, KB>(FAMILY));
+                                          (size_t)i8_table_bytes<NS, KB>(FAMILY, YBIN));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W_TMA = EW, W_MMA = EW + 1;
   // the warp index through redux.sync (CREDUX writes a uniform register): ptxas then KNOWS that the role branches below are
   // warp-uniform and keeps warp-uniform values - the TMEM addresses of the epilogue's tcgen05.ld's above all - in uniform
   // registers (otherwise: one R2UR per load; a shuffle broadcast does not convince it)
   const int warp_u = (int)__reduce_min_sync(FM_FULL, (unsigned)warp);
-  if (err[0] != 0) return;
   const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
   const long long ntiles = (mp.n + G::TO - 1) / G::TO;
   const long long first = slice, step = tb.gx;
@@ -638,6 +665,26 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // X does not depend on the head kernel of this row: the producer requests the first stages BEFORE waiting for it
+  // (programmatic dependent launch: this CTA may be resident while the head kernel still runs)
+  int n_early = 0;
+  if (warp_u == W_TMA) {
+    for (long long tile = first; tile < ntiles && n_early < STAGES; tile += step, n_early++) {
+      if (elect_one()) {
+        mbar_expect_tx(&full[n_early], (uint32_t)G::STAGE_BYTES);
+        bulk_g2s(stage0 + (size_t)n_early * G::STAGE_BYTES, mp.Xq + (size_t)tile * G::STAGE_BYTES, (uint32_t)G::STAGE_BYTES, &full[n_early]);
+      }
+      __syncwarp();
+    }
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  if (err[0] != 0) {  // a previous row failed: let the copies in flight land, free tensor memory, leave
+    if (warp_u == W_TMA)
+      for (int s = 0; s < n_early; s++) mbar_wait(&full[s], 0u);
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    return;
+  }
 
   // ---- this thread's chain: exponent, intercept; threads 0..127 also slice Theta into the A operand ----
   const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
@@ -674,10 +721,16 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   // ... and for every chain of the CTA: the hot loop runs the degree-3 core on the mean-corrected copy of the table
   // (softplus.h).  The table is chosen per CTA because it is shared: one bulk copy (160 KB), overlapped with the Theta slicing.
   const bool cta_in_table = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2) ? __all_sync(FM_FULL, __syncthreads_and(in_table && !tb.exact_core) != 0) : false;  // (the vote tells ptxas it is warp-uniform)
+  // ... and below the end of the replicated table (level 3) for every chain of the CTA: the conflict-free gather
+  constexpr int REP_ENTRIES = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) ? i8_rep_entries<NS, KB>() : 0;
+  constexpr double REP_BOUND = REP_ENTRIES > 0 ? (double)(REP_ENTRIES - 1) / FM_LC6_H - 0.1 : -1.0;
+  const bool in_rep = !th_bad && fmin(eb1, sqrt(eb2 * mp.i8_cmax[p_x])) <= REP_BOUND;
+  const bool cta_rep = REP_ENTRIES > 0 ? __all_sync(FM_FULL, __syncthreads_and(in_rep && !tb.exact_core) != 0) : false;
   if (FAMILY == FMCMC_FAMILY_LOGISTIC && tid == 0) {
-    constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_bytes<NS, KB>(FAMILY);
-    mbar_expect_tx(tab_bar, TAB_BYTES);
-    bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? (cta_in_table ? mp.sp_tab8m : mp.sp_tab8) : mp.sp_tab4, TAB_BYTES, tab_bar);
+    constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_entries<NS, KB>() * 16u, REP_BYTES = (uint32_t)REP_ENTRIES * FM_LC6_POINT_BYTES;
+    mbar_expect_tx(tab_bar, cta_rep ? REP_BYTES : TAB_BYTES);
+    if (cta_rep) bulk_g2s(sp_tab, mp.sp_tab6r, REP_BYTES, tab_bar);
+    else bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? (cta_in_table ? mp.sp_tab8m : mp.sp_tab8) : mp.sp_tab4, TAB_BYTES, tab_bar);
   }
   if (tid < I8_CHAINS) {
     for (int kb = 0; kb < KB; kb++) {
@@ -715,8 +768,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 
   if (warp_u == W_TMA) {
     // ===== producer: one bulk copy per stage (whole warp in the loop, one elected lane issues) =====
-    long long it = 0;
-    for (long long tile = first; tile < ntiles; tile += step, it++) {
+    long long it = n_early;  // the first stages are already on their way
+    for (long long tile = first + (long long)n_early * step; tile < ntiles; tile += step, it++) {
       const int s = (int)(it % STAGES);
       const uint32_t ph = (uint32_t)((it / STAGES) & 1);
       mbar_wait_sleep(&empty[s], ph ^ 1u, 256);
@@ -773,6 +826,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     double acc = 0.0, acc2 = 0.0;
     long long it = 0;
     const uint32_t sp_tab_s = smem_u32(sp_tab);
+    const uint32_t sp_tab_lane = sp_tab_s + (uint32_t)(lane & (FM_LC6_REP - 1)) * 16u;  // level 3: this lane's copy / bank group
     constexpr bool GRP = I8_GROUPED != 0 && EW == 16;
     constexpr int CWG = GRP ? 2 * CW : CW;          // columns of a block owned by this warp
     const int grp = h & 1;                          // GRP: this warp's group; it visits every other block
@@ -823,9 +877,16 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
             for (int e = 0; e < CH; e++) acc += (double)(int)(a[0][e] ^ a[NS - 1][e]);
           } else
 #endif
-          if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table && obs0 + CH <= valid) {
+          if (REP_ENTRIES > 0 && cta_rep && obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++)  // the hot loop of cfg3
+              i8_logistic_cubic_rep(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab_lane);
+          } else if (REP_ENTRIES > 0 && cta_rep) {
+            for (int e = 0; e < CH; e++)  // last, partial tile of a CTA
+              if (obs0 + e < valid) i8_logistic_cubic_rep(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab_lane);
+          } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table && obs0 + CH <= valid) {
+#pragma unroll
+            for (int e = 0; e < CH; e++)  // |eta| beyond the replicated table: 256-per-unit, mean-corrected
               i8_logistic_lcosh3_fast(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, acc2, sp_tab_s);
           } else if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN && i8_table_level<NS, KB>() == 2 && cta_in_table) {
             for (int e = 0; e < CH; e++)  // last, partial tile of a CTA on the mean-corrected table

@@ -97,7 +97,6 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   double* stage0 = reinterpret_cast<double*>(smem_raw + 128);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  if (err[0] != 0) return;
   // 1-D grid of gx * cb CTAs, chain block fastest: CTAs that run at the same time stream the SAME
   // observation slices, so X comes from HBM once per step and from L2 for the other chain blocks
   const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
@@ -125,6 +124,22 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
     bulk_g2s(stage0 + (size_t)s * STAGE_DOUBLES, mp.Xt + (size_t)tile * STAGE_DOUBLES, BYTES, &full[s]);
   };
 
+  // ---- pipeline prologue: X does not depend on the head kernel, so the first stages are requested BEFORE waiting for it
+  // (programmatic dependent launch: this CTA may be resident while the head kernel of the row still runs) ----
+  const long long first = slice, step = tb.gx;
+  int n_issued = 0;
+  if (tid == 0) {
+    long long tl = first;
+    for (int s = 0; s < TL_STAGES && tl < ntiles; s++, tl += step, n_issued++) issue(tl, s);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  if (err[0] != 0) {  // a previous row failed: let the copies in flight land, then leave
+    if (tid == 0)
+      for (int s = 0; s < n_issued; s++) mbar_wait(&full[s], 0u);
+    return;
+  }
+
   // ---- B fragments: Theta of this warp's NT chain tiles, in registers for the whole launch ----
   const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
   const int chain0 = chain_block * CPB + (OSPLIT ? 0 : warp * (NT * 8));
@@ -148,13 +163,6 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
       const double* thc = theta_of(chain0 + ct * 8 + 2 * t + h);
       cinit[ct][h] = (icpt && thc) ? thc[0] : 0.0;
     }
-  }
-
-  // ---- pipeline prologue -----------------------------------------------------------
-  const long long first = slice, step = tb.gx;
-  if (tid == 0) {
-    long long tl = first;
-    for (int s = 0; s < TL_STAGES && tl < ntiles; s++, tl += step) issue(tl, s);
   }
 
   double acc[NT][2];

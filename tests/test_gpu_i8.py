@@ -210,6 +210,42 @@ def test_i8_mixed_bounded_and_unbounded_warps(oracle):
     assert_parity(g[0], o[0], RTOL)
 
 
+def test_i8_table_selection_per_chain_block(oracle):
+    """The hot loop's table is chosen per CTA (= block of 128 chains) from the chains' bound on |eta|: below the end of the
+    bank-group-replicated cubic table (level 3; |eta| <= 10.74 with six slices, 11.15 with five) the two conflict-free loads, up to
+    39.9 the 256-per-unit mean-corrected table, beyond that the exact table with the clamped epilogue.  Block 0: every chain
+    parallel to the longest row of X with |eta| reaching 0.995 of the level-3 bound - the top of the replicated table is really
+    indexed; block 1: bounds 2 % above 11.15; block 2: bounds ~30; block 3: a mix of all of them and one chain at |eta| ~ 300."""
+    from fmcmc_b200 import ll_logistic
+    rng = np.random.default_rng(77)
+    n, p, C = 1300, 12, 4 * 128
+    X = rng.standard_normal((n, p)) / np.sqrt(p); X[:, 0] = 1.0
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ rng.standard_normal(p)))).astype(np.float64)
+    fam = ll_logistic(X, y, prior_sd=2.0)
+    norms = np.sqrt((X * X).sum(axis=1))
+    imax, rmax, cmax = int(norms.argmax()), norms.max(), np.abs(X).max(axis=0)
+
+    def with_bound(v, b):
+        return v * b / min(np.abs(v) @ cmax, np.linalg.norm(v) * rmax)
+
+    init = np.empty((C, p))
+    for c in range(128):
+        init[c] = with_bound(X[imax] * (1 if c % 2 else -1) + rng.normal(0, 1e-3, p), 0.995 * (694 / 64.0 - 0.1))
+    for c in range(128, 256):
+        init[c] = with_bound(rng.normal(0, 1.0, p), 1.02 * 11.15)
+    for c in range(256, 384):
+        init[c] = with_bound(rng.normal(0, 1.0, p), rng.uniform(25.0, 35.0))
+    for c in range(384, 512):
+        init[c] = with_bound(rng.normal(0, 1.0, p), (3.0, 10.7, 11.3, 39.0)[c % 4])
+    init[500] = rng.normal(0, 120.0, p)
+    spec = dict(type=A.KERNEL_NORMAL, k=p, mu=0.0, scale=0.002)
+    g, o, _ = run_both(oracle, fam, spec, init, 20, C, rng=rng, path=4)
+    assert g[0]["report"].path == 4
+    eta = X @ init[:128].T
+    assert 10.5 < np.abs(eta).max() < 694 / 64.0 - 0.1
+    assert_parity(g[0], o[0], RTOL)
+
+
 @pytest.mark.parametrize("family", ["logistic", "gaussian"])
 def test_i8_tiny_problem(oracle, family):
     """Forced path 4 far below its intended regime: fewer observations than one 128-row tile, one covariate (31 of the 32

@@ -152,6 +152,59 @@ def test_lcosh_degree3_on_the_mean_corrected_table_vs_mpmath():
     assert abs(err[:28000].sum()) / o[:28000].sum() < 1e-16
 
 
+def test_lcosh_replicated_cubic_table_vs_mpmath():
+    """The bank-group-replicated cubic table of the hot loop (softplus.h, fm_lcosh_table6r_fill / fm_lcosh_tab6r): 64 points per
+    unit up to a = 11.25, every point 256 bytes - eight identical copies of (c1, c0), then eight of (c2, c3) - holding the
+    LEAST-SQUARES cubic of h on its cell.  Against mpmath: every evaluation within 4.6e-12 (the cell edges at a = 0), rms
+    <= 1.6e-12, and - what a log-posterior sees - the error is orthogonal to constants on every cell: |mean| < 3e-14 on every
+    unit interval, a log-likelihood-sized sum within 5e-15 relative."""
+    from mpmath import exp, log1p, mp, mpf
+    mp.dps = 50
+    src = '#include "%s/fmcmc_b200/csrc/softplus.h"\n' % ROOT + \
+          'static double tab[FM_LC6_ENTRIES_MAX * FM_LC6_POINT_BYTES / 8];\n' \
+          'extern "C" const double* lc6_table() { fm_lcosh_table6r_fill(tab); return tab; }\n' \
+          'extern "C" void lc6_eval(const double* a, double* o, long n, int r) { fm_lcosh_table6r_fill(tab); ' \
+          'for (long i = 0; i < n; i++) o[i] = fm_lcosh_tab6r(a[i], tab, r < 0 ? (int)(i & 7) : r); }\n' \
+          'extern "C" int lc6_entries() { return FM_LC6_ENTRIES_MAX; }\n'
+    rng = np.random.default_rng(12)
+    with tempfile.TemporaryDirectory() as td:
+        cpp, so = os.path.join(td, "lc6.cpp"), os.path.join(td, "liblc6.so")
+        open(cpp, "w").write(src)
+        subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
+        L = C.CDLL(so)
+        L.lc6_table.restype = C.POINTER(C.c_double)
+        ne = L.lc6_entries()
+        tab = np.ctypeslib.as_array(L.lc6_table(), shape=(ne, 2, 8, 2)).copy()
+        amax = (ne - 1) / 64.0
+        a = np.concatenate([rng.uniform(lo, lo + 1, 4000) for lo in (0, 1, 2, 4, 8, 10)] +
+                           [np.arange(0, ne - 1) / 64.0 + 1.0 / 128.0 - 1e-12, [0.0, amax, amax - 1e-9]])
+        o = np.empty_like(a)
+        L.lc6_eval(a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_long(a.size), C.c_int(-1))
+        o3 = np.empty_like(a)
+        L.lc6_eval(a.ctypes.data_as(C.c_void_p), o3.ctypes.data_as(C.c_void_p), C.c_long(a.size), C.c_int(3))
+    assert amax == 11.25
+    for r in range(1, 8):                              # the copies are identical: which one a lane reads cannot matter
+        assert np.array_equal(tab[:, :, r, :], tab[:, :, 0, :])
+    assert np.array_equal(o, o3)
+    err = np.array([float(mpf(float(g)) - (mpf(float(x)) / 2 + log1p(exp(-mpf(float(x)))))) for g, x in zip(o, a)])
+    assert np.abs(err).max() < 4.6e-12, np.abs(err).max()
+    for i in range(6):
+        seg = err[4000 * i:4000 * (i + 1)]
+        assert abs(seg.mean()) < 3e-14, (i, seg.mean())
+        assert seg.std() < 1.6e-12, (i, seg.std())
+    assert abs(err[:24000].sum()) / o[:24000].sum() < 5e-15
+    # the fit really is the least-squares one: on a dense uniform grid of ONE cell the error is orthogonal to 1, d, d^2, d^3
+    k = 40
+    d = (np.arange(2000) + 0.5) / 2000 * (1 / 64.0) - 1 / 128.0
+    c1, c0 = tab[k, 0, 0]
+    c2, c3 = tab[k, 1, 0]
+    e = np.array([float(mpf(c0) + mpf(float(x)) * (mpf(c1) + mpf(float(x)) * (mpf(c2) + mpf(float(x)) * mpf(c3)))
+                        - ((mpf(k) / 64 + mpf(float(x))) / 2 + log1p(exp(-(mpf(k) / 64 + mpf(float(x))))))) for x in d])
+    scale = np.abs(e).max()
+    for pw in range(4):
+        assert abs(np.mean(e * (d * 128) ** pw)) < 2e-3 * scale, (pw, np.mean(e * (d * 128) ** pw), scale)
+
+
 @pytest.mark.gpu
 def test_softplus_device_vs_mpmath():
     import fmcmc_b200 as fm
