@@ -110,6 +110,11 @@ template <int NS, int KB>
 __host__ __device__ constexpr int i8_smem_fixed(int table_bytes) {
   return 256 + I8Geom<NS, KB>::A_SMEM_BYTES + table_bytes + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
 }
+// prologue scratch: per (part, chain) partial maxima / sums of the chain's parameters, 5 doubles each.  The logistic family
+// passes them through the table region before the table is loaded; the Gaussian family has no table and gets a region of its own
+__host__ __device__ constexpr int i8_scratch_bytes(int family) {
+  return family == FMCMC_FAMILY_LOGISTIC ? 0 : (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 5 * 8;
+}
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_table_level() {
   return (232448 - i8_smem_fixed<NS, KB>(FM_SP8_ENTRIES * 16)) / I8Geom<NS, KB>::STAGE_BYTES >= 2 ? 2 : 1;
@@ -136,14 +141,14 @@ __host__ __device__ constexpr int i8_table_bytes(int family, bool ybin) {
 // pipeline depth: as many stages as fit beside the Theta slices and the softplus table, at most 6.
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_stages(int family, bool ybin) {
-  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin))) / I8Geom<NS, KB>::STAGE_BYTES;
+  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin)) - i8_scratch_bytes(family)) / I8Geom<NS, KB>::STAGE_BYTES;
   return fit > 6 ? 6 : fit;
 }
 template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family, bool ybin) {
   using G = I8Geom<NS, KB>;
   size_t b = 256 + (size_t)i8_stages<NS, KB>(family, ybin) * G::STAGE_BYTES + G::A_SMEM_BYTES +
-             (size_t)i8_table_bytes<NS, KB>(family, ybin) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double);
+             (size_t)i8_table_bytes<NS, KB>(family, ybin) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double) + i8_scratch_bytes(family);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
 
@@ -313,6 +318,15 @@ __device__ __forceinline__ void tc_st_x8(uint32_t taddr, const uint32_t (&w)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(w[0]), "r"(w[1]),
                "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
+}
+template <int NW>
+__device__ __forceinline__ void tc_st(uint32_t taddr, const uint32_t (&w)[NW]) {
+  static_assert(NW == 2 || NW == 4 || NW == 8, "2, 4 or 8 columns per store");
+  if constexpr (NW == 8) tc_st_x8(taddr, w);
+  else if constexpr (NW == 4)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(w[0]), "r"(w[1]) : "memory");
 }
 template <int CH>
 __device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&v)[CH]) {
@@ -686,27 +700,70 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     return;
   }
 
-  // ---- this thread's chain: exponent, intercept; threads 0..127 also slice Theta into the A operand ----
+  // ---- this thread's chain: exponent, bounds, intercept.  The EW / 4 warps of a TMEM lane quarter hold the same 32 chains:
+  // each takes 32 / NPART columns of every K block (loads batched by the unrolled loops), the partial maxima / sums meet in
+  // shared memory (the table region, which is not loaded yet; a scratch region of its own for the Gaussian family) ----
   const int icpt = (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && (mp.flags & FMCMC_MODEL_INTERCEPT)) ? 1 : 0;
   const int lchain = tid & (I8_CHAINS - 1);
   const int col = chain_block * I8_CHAINS + lchain;
+  constexpr int NPART = EW / 4, CQ = 32 / NPART;   // parts a chain's columns are split into; columns of a K block per part
+  const int part = warp_u >> 2;                   // (producer / MMA warps: no chain)
   const double* th = nullptr;
   if (warp < EW && col < tb.ncols) th = col < C ? prop + (size_t)col * mp.k : prop_u + (size_t)(col - C) * mp.k;
   double thmax = 0.0, b0 = 0.0, lin = 0.0, eb1 = 0.0, eb2 = 0.0;
   bool th_nan = false, th_big = false;
-  if (th) {
-    for (int j = 0; j < p_x; j++) {
-      const double v = th[icpt + j];
-      const double a = fabs(scalbn(v, mp.i8_cexp[j]));  // theta'_j = theta_j 2^cexp[j]
-      if (a != a) th_nan = true;
-      else if (!(a < 0x1p480)) th_big = true;
-      thmax = fmax(thmax, a);
-      eb1 = fma(fabs(v), mp.i8_cmax[j], eb1);  // |eta_i| <= sum_j |theta_j| max_i |x_ij|
-      eb2 = fma(v, v, eb2);                    // |eta_i| <= |theta|_2 max_i |x_i|_2
-      if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) lin = fma(v, mp.i8_sxy[j], lin);
+  double* pscr = reinterpret_cast<double*>(FAMILY == FMCMC_FAMILY_LOGISTIC ? reinterpret_cast<unsigned char*>(sp_tab)
+                                                                           : reinterpret_cast<unsigned char*>(red) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double));
+  if (warp < EW) {
+    double p_max = 0.0, p_e1 = 0.0, p_e2 = 0.0, p_lin = 0.0;
+    int p_flags = 0;
+    if (th) {
+#pragma unroll
+      for (int kb = 0; kb < KB; kb++) {
+        double v[CQ];
+        int ce[CQ];
+#pragma unroll
+        for (int q = 0; q < CQ; q++) {   // CQ independent loads in flight
+          const int j = kb * 32 + part * CQ + q;
+          v[q] = j < p_x ? th[icpt + j] : 0.0;
+          ce[q] = j < p_x ? mp.i8_cexp[j] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < CQ; q++) {
+          const int j = kb * 32 + part * CQ + q;
+          if (j < p_x) {
+            const double a = fabs(v[q] * __hiloint2double((1023 + ce[q]) << 20, 0));  // theta'_j = theta_j 2^cexp[j], |cexp| <= 480
+            if (a != a) p_flags |= 1;
+            else if (!(a < 0x1p480)) p_flags |= 2;
+            p_max = fmax(p_max, a);
+            p_e1 = fma(fabs(v[q]), mp.i8_cmax[j], p_e1);  // |eta_i| <= sum_j |theta_j| max_i |x_ij|
+            p_e2 = fma(v[q], v[q], p_e2);                 // |eta_i| <= |theta|_2 max_i |x_i|_2
+            if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) p_lin = fma(v[q], mp.i8_sxy[j], p_lin);
+          }
+        }
+      }
+      if (icpt) b0 = th[0];
     }
-    if (icpt) b0 = th[0];
+    double* ps = pscr + (size_t)(part * I8_CHAINS + lchain) * 5;
+    ps[0] = p_max; ps[1] = p_e1; ps[2] = p_e2; ps[3] = p_lin; ps[4] = __hiloint2double(0, p_flags);
   }
+  __syncthreads();
+  if (warp < EW) {
+    int fl = 0;
+#pragma unroll
+    for (int pp = 0; pp < NPART; pp++) {   // fixed order: every warp of the quarter forms the same values
+      const double* ps = pscr + (size_t)(pp * I8_CHAINS + lchain) * 5;
+      thmax = fmax(thmax, ps[0]);
+      eb1 += ps[1];
+      eb2 += ps[2];
+      lin += ps[3];
+      fl |= __double2loint(ps[4]);
+    }
+    th_nan = (fl & 1) != 0;
+    th_big = (fl & 2) != 0;
+  }
+  // the region the partial sums went through is about to be written by the table's bulk copy (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const bool th_bad = th_nan || th_big;
   const int eth = th_bad ? 0 : i8_exponent(thmax);
   const double csc = __hiloint2double((1023 - G::SHIFT + eth) << 20, 0);  // eta = t * 2^(eth - SHIFT)
@@ -726,23 +783,35 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   constexpr double REP_BOUND = REP_ENTRIES > 0 ? (double)(REP_ENTRIES - 1) / FM_LC6_H - 0.1 : -1.0;
   const bool in_rep = !th_bad && fmin(eb1, sqrt(eb2 * mp.i8_cmax[p_x])) <= REP_BOUND;
   const bool cta_rep = REP_ENTRIES > 0 ? __all_sync(FM_FULL, __syncthreads_and(in_rep && !tb.exact_core) != 0) : false;
+  // (every thread's reads of the partial sums in the table region precede a block-wide barrier: the votes above, or this one)
+  if (FAMILY == FMCMC_FAMILY_LOGISTIC && !(YBIN && i8_table_level<NS, KB>() == 2)) __syncthreads();
   if (FAMILY == FMCMC_FAMILY_LOGISTIC && tid == 0) {
     constexpr uint32_t TAB_BYTES = (uint32_t)i8_table_entries<NS, KB>() * 16u, REP_BYTES = (uint32_t)REP_ENTRIES * FM_LC6_POINT_BYTES;
     mbar_expect_tx(tab_bar, cta_rep ? REP_BYTES : TAB_BYTES);
     if (cta_rep) bulk_g2s(sp_tab, mp.sp_tab6r, REP_BYTES, tab_bar);
     else bulk_g2s(sp_tab, i8_table_level<NS, KB>() == 2 ? (cta_in_table ? mp.sp_tab8m : mp.sp_tab8) : mp.sp_tab4, TAB_BYTES, tab_bar);
   }
-  if (tid < I8_CHAINS) {
+  if (warp < EW) {   // Theta slices into the A operand: every epilogue warp writes its CQ columns of its lane quarter's chains
+    const uint32_t lane_quarter = (uint32_t)((warp_u & 3) * 32) << 16;
+#pragma unroll
     for (int kb = 0; kb < KB; kb++) {
-      uint32_t w[NS][8];
+      uint32_t w[NS][CQ / 4];
 #pragma unroll
       for (int i = 0; i < NS; i++)
 #pragma unroll
-        for (int q = 0; q < 8; q++) w[i][q] = 0u;
+        for (int q = 0; q < CQ / 4; q++) w[i][q] = 0u;
+      double v[CQ];
+      int ce[CQ];
 #pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int j = kb * 32 + q;
-        const double u = (th && !th_bad && j < p_x) ? scalbn(th[icpt + j], mp.i8_cexp[j] - eth) : 0.0;
+      for (int q = 0; q < CQ; q++) {
+        const int j = kb * 32 + part * CQ + q;
+        const bool live = th && !th_bad && j < p_x;
+        v[q] = live ? th[icpt + j] : 0.0;
+        ce[q] = live ? mp.i8_cexp[j] : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < CQ; q++) {
+        const double u = v[q] * __hiloint2double((1023 + ce[q] - eth) << 20, 0);  // exact: |cexp - eth| <= 960, |u| < 1
         int s[NS];
         i8_slices<NS>(u, s);
 #pragma unroll
@@ -751,11 +820,12 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll
       for (int i = 0; i < NS; i++) {
         if (G::a_in_tmem(i, kb)) {
-          tc_st_x8(tmem + G::a_tmem_col(i, kb) + ((uint32_t)(warp * 32) << 16), w[i]);
-        } else {
-          unsigned char* p = sA + (size_t)G::a_smem_unit(i, kb) * 4096 + (tid / 8) * 256 + (tid % 8) * 16;
-          *reinterpret_cast<uint4*>(p) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
-          *reinterpret_cast<uint4*>(p + 128) = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
+          tc_st<CQ / 4>(tmem + G::a_tmem_col(i, kb) + part * (CQ / 4) + lane_quarter, w[i]);
+        } else {   // row = chain: 16-byte chunks of 16 columns, the second half of the K block 128 B further
+          unsigned char* p = sA + (size_t)G::a_smem_unit(i, kb) * 4096 + (lchain / 8) * 256 + (lchain % 8) * 16 +
+                             ((part * CQ) / 16) * 128 + (part * CQ) % 16;
+#pragma unroll
+          for (int q = 0; q < CQ / 4; q++) reinterpret_cast<uint32_t*>(p)[q] = w[i][q];
         }
       }
     }
