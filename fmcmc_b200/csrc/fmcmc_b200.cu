@@ -87,6 +87,7 @@ struct fmcmc_model {
   int trimmed_to = 0;     // fmcmc_model_trim: the only stepping path whose copy of X is still resident (0 = all)
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
   int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
+  bool head_cta = true;   // few chains + kernel_adapt: one CTA per chain in the head kernel (FMCMC_HEAD_CTA=0: the warp-per-chain head; A/B measurements)
   bool pdl = true;        // programmatic dependent launch between the two kernels of an MH row (FMCMC_PDL=0 disables; A/B measurements)
   int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
   // run buffers (grow-only)
@@ -187,7 +188,8 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   MC(cudaEventCreate(&m->ev1));
   MC(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   MC(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  if (device_ptrs && ld == n) {  // borrow
+  const bool aligned16 = (((uintptr_t)d->X | (uintptr_t)d->y) & 15) == 0;   // TMA bulk copies and vector loads need 16-byte aligned columns
+  if (device_ptrs && ld == n && aligned16) {  // borrow
     m->borrowed = true;
     mp.X = d->X; mp.y = d->y; mp.group = d->group;
   } else {
@@ -262,6 +264,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   if (const char* v = getenv("FMCMC_TILED_VARIANT")) { if (atoi(v) == 2 || atoi(v) == 3) m->tiled_default = atoi(v); }
   if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
   if (const char* v = getenv("FMCMC_PDL")) m->pdl = atoi(v) != 0;
+  if (const char* v = getenv("FMCMC_HEAD_CTA")) m->head_cta = atoi(v) != 0;
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
   if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= I8_NS_LO && atoi(v) <= I8_NS_LO + 1) m->i8_slices = atoi(v); }
@@ -667,22 +670,29 @@ static cudaError_t launch_tiled_mma(fmcmc_model* m, const MmaShape& sh, dim3 gri
 
 // ---- path 4: split-integer tensor-core kernel (tiled_i8.cuh) ------------------------------------------
 static int i8_kblocks(int p_x) { return p_x <= 32 ? 1 : (p_x <= 64 ? 2 : 4); }
-static int i8_tile_rows(int KB) { return KB == 1 ? 128 : (KB == 2 ? 64 : 32); }
 #if I8_DIGIT_BITS == 8
 #define I8_FOR_SHAPES(X) X(5, 1) X(5, 2) X(5, 4) X(6, 1) X(6, 2) X(6, 4)
 #else
 #define I8_FOR_SHAPES(X) X(6, 1) X(6, 2) X(6, 4) X(7, 1) X(7, 2) X(7, 4)
 #endif
+// observations per pipeline stage / tile of Xq (the Gaussian family at K = 128 packs 64-observation blocks: tiled_i8.cuh, i8_blk)
+static int i8_tile_rows(int family, int NS, int KB) {
+#define I8_CASE(N, K) if (NS == N && KB == K) return family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::TO : I8Geom<N, K>::TO;
+  I8_FOR_SHAPES(I8_CASE)
+#undef I8_CASE
+  return 32;
+}
 // Builds the int8 slice tiles of X once per model.  Returns cudaErrorNotSupported when X holds non-finite
 // values (or magnitudes beyond the exponent window): the caller falls back to the FP64 kernels.
 static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   if (m->xq_NS == NS && m->xq_KB == KB) return cudaSuccess;
   if (m->xq_NS == -1) return cudaErrorNotSupported;
   const ModelParams& mp = m->mp;
-  const int TO = i8_tile_rows(KB);
+  const bool gauss = mp.family == FMCMC_FAMILY_GAUSSIAN_LM;
+  const int TO = i8_tile_rows(mp.family, NS, KB);
   const long long ntiles = (mp.n + TO - 1) / TO;
   size_t stage_bytes = 0;
-#define I8_CASE(N, K) if (NS == N && KB == K) stage_bytes = I8Geom<N, K>::STAGE_BYTES;
+#define I8_CASE(N, K) if (NS == N && KB == K) stage_bytes = gauss ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::STAGE_BYTES : I8Geom<N, K>::STAGE_BYTES;
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
   if (!stage_bytes) return cudaErrorInvalidValue;
@@ -708,7 +718,12 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   i8_colexp_kernel<<<(mp.p_x + 127) / 128, 128, 0, m->stream>>>(colmax, mp.p_x, cexp);
   i8_rownorm_kernel<<<(unsigned)std::min<long long>(4096, (mp.n + 255) / 256), 256, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, colmax + px);
   i8_sxy_kernel<<<(unsigned)mp.p_x, 1024, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, sxy);
-#define I8_CASE(N, K) if (NS == N && KB == K) pack_i8_kernel<N, K><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);
+#define I8_CASE(N, K)                                                                                                      \
+  if (NS == N && KB == K) {                                                                                                \
+    constexpr int BW = i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM);                                                             \
+    if (gauss && BW != 32) pack_i8_kernel<N, K, BW><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq); \
+    else pack_i8_kernel<N, K, 32><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);            \
+  }
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
   e = cudaGetLastError();
@@ -1009,7 +1024,7 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const int ncols_all = is_ram ? 2 * C : C;
     const MmaShape msh = mma_shape(mp.p_x, ncols_all, m->mma_wide);
     const int cpb = path == 4 ? I8_CHAINS : (path == 3 ? (msh.osplit ? msh.NT * 8 : msh.warps * msh.NT * 8) : TL_CHAINS);   // chains per CTA
-    const int tile_rows = path == 4 ? i8_tile_rows(i8_KB) : (path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE);
+    const int tile_rows = path == 4 ? i8_tile_rows(mp.family, i8_NS, i8_KB) : (path == 3 ? (msh.PB <= 32 ? 128 : (msh.PB == 64 ? 64 : 32)) : TL_TILE);
     if (path == 3) {
       cudaError_t pe = ensure_packed_tiles(m, msh.PB);
       if (pe == cudaErrorMemoryAllocation) { set_err(err, errlen, "out of device memory for the tile-major copy of X"); return FMCMC_ENOMEM; }
@@ -1062,7 +1077,12 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     // observations (the peer-flag protocol paces the kernels there), and not across the event records of a timed launch.
     const bool pdl_ok = m->pdl && !(m->shard_world > 1);
     bool pdl_head = false;
+    // few chains, kernel_adapt with the Cholesky draw: a CTA per chain (tiled.cuh, tiled_head_adapt_cta_kernel) - same results bit for bit
+    const bool head_cta = m->head_cta && kclass == KC_ADAPT && ks->mvn_method != FMCMC_MVN_EIGEN && ks->bw <= 0 && kf <= 32 && C <= m->sm_count;
     auto head_launch = [&](long long row) -> cudaError_t {
+      if (head_cta)
+        return launch_chained(tiled_head_adapt_cta_kernel, dim3(C), dim3(TL_HEADC_THREADS), 0, m->stream, pdl_head,
+                              mp, kp, sp, rb, tb, d_initial, row);
 #define HEAD_CASE(K)                                                                                              \
   case K:                                                                                                          \
     if (hsmem > 48 * 1024) {                                                                                       \

@@ -312,3 +312,203 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
     if (rc && lane == 0) set_error(rb.err, rc, c + 1, row);
   }
 }
+
+// ---- the few-chain head of kernel_adapt: one CTA per chain ---------------------------------------------------------------
+// With a handful of chains (the reference's typical usage) the warp-per-chain head above is a single warp walking the
+// covariance recurrence and a 32 x 32 left-looking Cholesky factorisation: ~30 us of dependent instructions per MH row, as long
+// as the HBM-bound likelihood launch next to it.  Here a chain owns a CTA of 1 024 threads, thread (i, j) = (lane, warp) one
+// entry of the k_f x k_f matrices: the recurrence is one multiply-add per thread, and the factorisation runs RIGHT-looking in
+// registers - after column p is final (warp p: square root and divisions), every entry (i, j > p) subtracts L[i][p] L[j][p].
+// Each entry still sees its subtractions in the order p = 0, 1, 2 ... with the same unfused operations, so the factor - hence
+// every draw - is bit-identical to the left-looking loop (chol_lower_warp) and to the oracle; the critical path is 32 steps of
+// (sqrt, divide, multiply, subtract, one barrier) instead of 496 dependent multiply-subtracts.
+// Finishing the previous row (partial sums, accept / reject, output rows) is warp 0's job, exactly as above.
+// Chosen by fmcmc_run for kernel_adapt with the Cholesky draw, bw = 0, k_f <= 32 and at most one CTA per SM of chains.
+#define TL_HEADC_THREADS 1024
+__global__ void __launch_bounds__(TL_HEADC_THREADS)
+tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, TiledBuffers tb,
+                            const double* initial, long long row) {
+  __shared__ double s_x[32], s_m[32], s_mp[32], s_z[32];
+  __shared__ double s_L[32][33];   // s_L[p][i] = L[i][p]
+  __shared__ int s_stop;           // != 0: the chain stops here (error recorded, or nothing left to do)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (rb.err[0] != 0) return;
+  const int k = kp.k, kf = kp.kf;
+  double* th0 = rb.cur_theta + (size_t)c * k;
+  double* th1 = rb.prop + (size_t)c * k;
+  double* th1u = rb.prop_u + (size_t)c * k;
+  if (row == 1) {  // R/mcmc.R:737-743
+    if (warp == 0) {
+      const double* src = initial ? initial + (size_t)c * k : th0;
+      for (int j = lane; j < k; j += FM_WARP) {
+        const double v = src[j];
+        th0[j] = v; th1[j] = v; th1u[j] = v;
+      }
+      if (lane == 0) {
+        rb.istate[c * FMCMC_ISTATE_LEN + 3] = 0;
+        rb.chain_flags[c] = 0;
+      }
+    }
+    return;
+  }
+  if (tid == 0) s_stop = 0;
+  __syncthreads();
+
+  // ---- finish row r = row - 1 (warp 0; same steps as tiled_head_kernel) ----
+  if (warp == 0) {
+    const long long r = row - 1;
+    bool stop = false;
+    if (tb.sx.world > 1 && !(r == 1 && !initial)) {
+      bool ok = true;
+      if (lane < tb.sx.world) {
+        const volatile unsigned long long* fl = tb.sx.peer_flags[tb.sx.rank] + lane;
+        unsigned long long t0 = 0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*fl < tb.sx.step) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (now - t0 > 60000000000ULL || rb.err[0] != 0) { ok = false; break; }
+          __nanosleep(200);
+        }
+      }
+      ok = __all_sync(FM_FULL, ok);
+      __threadfence_system();
+      if (!ok) { if (lane == 0) set_error(rb.err, FMCMC_EPEER, c + 1, r); stop = true; }
+    }
+    if (!stop) {
+      double f1;
+      if (r == 1 && !initial) f1 = rb.cur_f[c];
+      else f1 = family_finish(mp, th1, reduce_partials(tb, c, lane));
+      if (r == 1) {
+        for (int j = lane; j < k; j += FM_WARP) { rb.ans[(size_t)c * k + j] = th0[j]; rb.draws[(size_t)c * k + j] = th0[j]; }
+        for (int a = lane; a < kf; a += FM_WARP) {
+          rb.colsum[((size_t)c * kf + a) * 2] = th0[kp.free_idx[a]];
+          rb.colsum[((size_t)c * kf + a) * 2 + 1] = 0.0;
+        }
+        if (lane == 0) { rb.logpost[c] = f1; rb.cur_f[c] = f1; }
+      } else {
+        double f0 = rb.cur_f[c];
+        bool failed = false;
+        unsigned long long n_acc = 0;
+        f0 = accept_row_warp(kp, sp, rb, c, r, th0, th1, f0, f1, lane, n_acc, failed);
+        if (failed) stop = true;
+        else if (lane == 0) {
+          rb.cur_f[c] = f0;
+          if (n_acc) atomicAdd(rb.n_accept, n_acc);
+        }
+      }
+    }
+    if (row > rb.T) stop = true;   // the last launch only finishes row T
+    if (stop && lane == 0) s_stop = 1;
+  }
+  __syncthreads();   // (also publishes warp 0's global writes - theta0, the ans row, colsum - to the CTA)
+  if (s_stop) return;
+
+  // ---- propose row `row`: R/kernel_adapt.R:84-182, the steps of propose_warp<KC_ADAPT> ----
+  const long long i = row;
+  long long* ist = rb.istate + c * FMCMC_ISTATE_LEN;
+  long long abs_iter = ist[0], flags = ist[1];
+  double* Sigma = rb.dstate + (size_t)c * kp.dlen;
+  double* Mean_prev = Sigma + (size_t)kf * kf;
+  double* L = rb.work + (size_t)c * rb.worklen;
+  int* cflag = rb.chain_flags + c;
+  bool dirty = !(*cflag & 2);
+  __syncthreads();   // every thread has read the chain's state words before anyone updates them below
+  ChainCtx cx;
+  cx.c = c; cx.i = i; cx.theta0 = th0; cx.theta1 = th1; cx.theta1u = th1u; cx.scr = nullptr; cx.f0 = 0.0;
+  cx.ans = rb.ans; cx.ans_stride = (long long)rb.nchains * k; cx.mat = nullptr;
+  if (!(flags & FMCMC_STATE_INIT)) {  // :87-115
+    for (int e = tid; e < kf * kf; e += TL_HEADC_THREADS) Sigma[e] = ((e % kf) == (e / kf)) ? kp.eps : 0.0;
+    flags |= FMCMC_STATE_INIT;
+    dirty = true;
+  }
+  if (kp.until > (double)abs_iter && abs_iter > kp.warmup && i > 2 && (i % kp.freq) == 0) {  // :118
+    if (!(flags & FMCMC_STATE_HAS_MEAN)) {  // :130-131 (colMeans from the compensated running sums, as in propose_warp)
+      if (warp == 0) {
+        const double* cs = rb.colsum + (size_t)c * 2 * kf;
+        const double nn = (double)(i - 1);
+        for (int a = lane; a < kf; a += FM_WARP) {
+          const double hi = cs[2 * a], lo = cs[2 * a + 1];
+          const double q = xdiv(hi, nn);
+          const double rr = fma(-q, nn, hi);
+          Mean_prev[a] = xadd(q, xdiv(xadd(rr, lo), nn));
+        }
+      }
+      flags |= FMCMC_STATE_HAS_MEAN;
+    }
+    const double t = (double)(abs_iter - kp.freq);  // :144
+    if (i - kp.freq < 1 || t == 0.0) {              // the reference indexes row <= 0 / divides by zero here
+      if (tid == 0) set_error(rb.err, FMCMC_EUNSUP, c + 1, row);
+      return;
+    }
+    __syncthreads();
+    for (long long jj = 0; jj < kp.freq; jj++) {  // rows (i-freq):(i-1), R/recursive.R:78-110
+      const double tj = t + (double)jj;
+      if (warp == 0) {
+        const double* xr = ans_row(cx, kp, i - kp.freq + jj);
+        for (int a = lane; a < kf; a += FM_WARP) {
+          const double xa = xr[kp.free_idx[a]];
+          const double mpa = Mean_prev[a];
+          s_x[a] = xa;
+          s_mp[a] = mpa;
+          s_m[a] = xdiv(xadd(xmul(mpa, tj), xa), tj + 1.0);  // mean_recursive :126
+        }
+      }
+      __syncthreads();
+      const double c1 = xdiv(tj - 1.0, tj), c2 = xdiv(1.0, tj);
+      for (int e = tid; e < kf * kf; e += TL_HEADC_THREADS) {  // cov_recursive :112-118, Sd = 1, eps = 1e-5
+        const int a = e % kf, b = e / kf;
+        double inner = xsub(xmul(tj, xmul(s_mp[a], s_mp[b])), xmul(tj + 1.0, xmul(s_m[a], s_m[b])));
+        inner = xadd(inner, xmul(s_x[a], s_x[b]));
+        inner = xadd(inner, xmul(1e-5, a == b ? kp.eps : 0.0));
+        Sigma[e] = xadd(xmul(c1, Sigma[e]), xmul(c2, inner));
+      }
+      if (warp == 0)
+        for (int a = lane; a < kf; a += FM_WARP) Mean_prev[a] = s_m[a];
+      __syncthreads();
+    }
+    dirty = true;
+  }
+  abs_iter += 1;  // :170
+  if (dirty) {
+    __syncthreads();   // Sigma complete (its entries were written by other threads when k_f < 32)
+    const int ri = lane, cj = warp;
+    const bool active = ri < kf && cj < kf && ri >= cj;
+    double v = active ? Sigma[ri + cj * kf] : 0.0;
+    for (int p = 0; p < kf; p++) {
+      if (warp == p) {  // column p is final: pivot, square root, divisions (chol_lower_warp's second pass)
+        const double s = __shfl_sync(FM_FULL, v, p);
+        if (!(s > 0.0)) {
+          if (lane == 0) s_stop = p + 1;
+        } else {
+          const double ljj = sqrt(s);
+          v = (lane == p) ? ljj : xdiv(v, ljj);
+          if (lane >= p && lane < kf) s_L[p][lane] = v;
+        }
+      }
+      __syncthreads();
+      if (s_stop) break;
+      if (active && cj > p) v = xsub(v, xmul(s_L[p][ri], s_L[p][cj]));
+    }
+    if (s_stop) {  // mvrnorm: "'Sigma' is not positive definite"
+      if (tid == 0) set_error(rb.err, FMCMC_ENOTPD, c + 1, row);
+      return;
+    }
+    if (ri < kf && cj < kf) L[ri + cj * kf] = active ? v : 0.0;   // cached for the rows that do not re-adapt
+    if (tid == 0) *cflag |= 2;
+  }
+  if (warp == 0) {
+    for (int a = lane; a < kf; a += FM_WARP) s_z[a] = draw_z(sp, rb, cx, a);
+    for (int j = lane; j < k; j += FM_WARP) th1[j] = th0[j];
+    __syncwarp();
+    for (int a = lane; a < kf; a += FM_WARP) {  // :173-180
+      double s = 0.0;
+      for (int b = 0; b <= a; b++) s = xadd(s, xmul(dirty ? s_L[b][a] : L[a + b * kf], s_z[b]));
+      const int w = kp.free_idx[a];
+      th1[w] = reflect1(xadd(th0[w], xadd(kp.mu[w], s)), kp.lb[w], kp.ub[w]);
+    }
+    if (lane == 0) { ist[0] = abs_iter; ist[1] = flags; }
+  }
+}

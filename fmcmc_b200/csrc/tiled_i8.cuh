@@ -71,13 +71,34 @@
 #endif                // with two - the waiting it removes comes back as math-pipe stalls (profiles/r02_findings.md, section 9)
 
 #define I8_NS_LO (I8_DIGIT_BITS == 8 ? 5 : 6)   // slices of the default accuracy tier; kernel_ram and n < 65 536 use one more
+// Observations per MMA block.  32 by default.  At K = 128 (four K blocks) the kernel is bound by the tensor pipe, which needs
+// >= 64 clk per M = 128 int8 MMA whatever its N <= 96 (profiles/r01_i8_findings.md, section 5): the triangle N = 160 .. 32 of a
+// 32-observation block costs 347 clk per K block against 255 at peak.  With 64-observation blocks (Gaussian family, K = 128,
+// five slices) the triangle is N = 160 + 160, 256, 192, 128, 64: 542 clk per 64 observations, 22 % less tensor time.  The five
+// diagonals of 64 observations take 320 accumulator columns, so there is ONE accumulator set (320 + 160 columns of Theta
+// slices = 480): MMAs and epilogue alternate - which costs nothing here, the two were time-additive already (the tensor pipe
+// and the FP64 pipe share their datapath).
+#ifndef I8_WIDE_BLOCKS
+#define I8_WIDE_BLOCKS 1   // measured on B200 (cfg5): 135.2 ms per launch against 138.7 with 32-observation blocks and two sets
+#endif
+// Gaussian, K = 128, two accumulator sets only (-DI8_WIDE_BLOCKS=0): the integer half of the epilogue for all of a warp's columns
+// first, the FP64 half after, so that the integer half could overlap the other set's MMAs.  Built, parity-green, measured:
+// 138.65 ms against 138.7 - no gain (the MMA sequence alone takes 111.5 ms with its issue floors; what the epilogue adds on
+// top is not the FP64 / integer interleaving).  Off.
+#ifndef I8_PHASE_SPLIT
+#define I8_PHASE_SPLIT 0
+#endif
 template <int NS, int KB>
+__host__ __device__ constexpr int i8_blk(int family) {
+  return (I8_WIDE_BLOCKS != 0 && family == FMCMC_FAMILY_GAUSSIAN_LM && KB == 4 && NS == 5 && I8_DIGIT_BITS == 8) ? 64 : 32;
+}
+template <int NS, int KB, int BLK_ = 32>
 struct I8Geom {
   static constexpr int DB = I8_DIGIT_BITS;
-  static constexpr int BLK = 32;                                    // observations per MMA block (instruction N)
-  static constexpr int TO = KB == 1 ? 128 : (KB == 2 ? 64 : 32);    // observations per pipeline stage
+  static constexpr int BLK = BLK_;                                  // observations per MMA block
+  static constexpr int TO = KB == 1 ? 128 : (KB == 2 ? 64 : BLK);   // observations per pipeline stage
   static constexpr int NBLK = TO / BLK;
-  static constexpr int SLAB_BYTES = BLK * 32;                        // one slice x one K block of a 32-observation block: 4 groups x 2 chunks x 128 B
+  static constexpr int SLAB_BYTES = BLK * 32;                        // one slice x one K block of a block: BLK / 8 row groups x 2 chunks x 128 B
   static constexpr int BLOCK_BYTES = KB * NS * SLAB_BYTES;           // [kb][slice][group][chunk][8 rows][16 B]
   static constexpr int SLICE_BYTES = NBLK * BLOCK_BYTES;
   static constexpr int STAGE_BYTES = SLICE_BYTES;                   // a stage is pure MMA operand: only the tensor pipe holds it
@@ -86,7 +107,8 @@ struct I8Geom {
   // them (K = 32, 5 slices: 3 x 160 + 4 x 8 = 512 columns exactly).  With two sets a group of epilogue warps waits for the MMAs of
   // its next block (12 % of the warps' time in round 2's profile); with three the MMA warp runs a block ahead - correct
   // (all parity tests), but not faster: while the tensor pipe works the FP64 pipe does not, wherever the warps happen to wait.
-  static constexpr int NACC = (I8_TRIPLE != 0 && KB == 1 && 3 * ACC_COLS + (NS - 1) * 8 <= 512) ? 3 : 2;
+  // Wide blocks (BLK = 64): one set.
+  static constexpr int NACC = BLK > 32 ? 1 : ((I8_TRIPLE != 0 && KB == 1 && 3 * ACC_COLS + (NS - 1) * 8 <= 512) ? 3 : 2);
   // A operand (Theta slices): 8 columns per (slice, K block) unit.  NACC == 2: as many K blocks as fit beside the two sets
   // live in tensor memory (all slices of those K blocks), the rest in shared memory; NACC == 3: slices 0 .. NS-2 in tensor
   // memory, the last slice (one MMA of N = 32 per block) in shared memory.  An MMA whose A comes from shared memory re-reads 4 KB.
@@ -106,9 +128,9 @@ struct I8Geom {
 // table of the logistic epilogue (softplus.h): level 2 = 256 entries per unit (160 KB, (tau, T) of log(2 cosh(a / 2)), one degree-4
 // Taylor core: 9 FP64 instructions) when it leaves room for two pipeline stages, else level 1 = 128 per unit (80 KB, (S, G) of
 // log1p(exp(-a)), two degree-4 polynomials: 13)
-template <int NS, int KB>
+template <int NS, int KB, int BLK = 32>
 __host__ __device__ constexpr int i8_smem_fixed(int table_bytes) {
-  return 256 + I8Geom<NS, KB>::A_SMEM_BYTES + table_bytes + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
+  return 256 + I8Geom<NS, KB, BLK>::A_SMEM_BYTES + table_bytes + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * 8 + 1024;
 }
 // prologue scratch: per (part, chain) partial maxima / sums of the chain's parameters, 5 doubles each.  The logistic family
 // passes them through the table region before the table is loaded; the Gaussian family has no table and gets a region of its own
@@ -141,13 +163,18 @@ __host__ __device__ constexpr int i8_table_bytes(int family, bool ybin) {
 // pipeline depth: as many stages as fit beside the Theta slices and the softplus table, at most 6.
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_stages(int family, bool ybin) {
-  const int fit = (232448 - i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin)) - i8_scratch_bytes(family)) / I8Geom<NS, KB>::STAGE_BYTES;
+  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM);   // (only the Gaussian family has wide blocks)
+  const int stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB>::STAGE_BYTES;
+  const int fixed = family == FMCMC_FAMILY_GAUSSIAN_LM ? i8_smem_fixed<NS, KB, B>(0) : i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin));
+  const int fit = (232448 - fixed - i8_scratch_bytes(family)) / stage;
   return fit > 6 ? 6 : fit;
 }
 template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family, bool ybin) {
-  using G = I8Geom<NS, KB>;
-  size_t b = 256 + (size_t)i8_stages<NS, KB>(family, ybin) * G::STAGE_BYTES + G::A_SMEM_BYTES +
+  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM);
+  const size_t stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB>::STAGE_BYTES;
+  const size_t asmem = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::A_SMEM_BYTES : I8Geom<NS, KB>::A_SMEM_BYTES;
+  size_t b = 256 + (size_t)i8_stages<NS, KB>(family, ybin) * stage + asmem +
              (size_t)i8_table_bytes<NS, KB>(family, ybin) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double) + i8_scratch_bytes(family);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
 }
@@ -258,10 +285,10 @@ __global__ void __launch_bounds__(1024) i8_sxy_kernel(const double* __restrict__
   if (t == 0) sxy[j] = red[0];
 }
 
-template <int NS, int KB>
+template <int NS, int KB, int BLK>
 __global__ void pack_i8_kernel(const double* __restrict__ X, long long n, long long ld, int p_x,
                                const int* __restrict__ cexp, unsigned char* __restrict__ Xq) {
-  using G = I8Geom<NS, KB>;
+  using G = I8Geom<NS, KB, BLK>;
   const long long tile = blockIdx.x;
   const int t = threadIdx.x;  // blockDim.x == TO
   const long long row = tile * G::TO + t;
@@ -344,9 +371,9 @@ __device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&v)[CH]) {
 }
 // all NS accumulators of 8 columns (diagonal d sits 32 d columns further right) in ONE asm statement: the address reaches
 // the uniform datapath once (one R2UR) and the NS loads carry immediate offsets, instead of one R2UR per load
-template <int NS, int CH>
+template <int NS, int CH, int BLK = 32>
 __device__ __forceinline__ void tc_ld_diagonals(uint32_t taddr, uint32_t (&a)[NS][CH]) {
-  if constexpr (CH == 8 && NS == 6) {
+  if constexpr (CH == 8 && NS == 6 && BLK == 32) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%48];\n"
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%48+32];\n"
@@ -357,7 +384,7 @@ __device__ __forceinline__ void tc_ld_diagonals(uint32_t taddr, uint32_t (&a)[NS
         : "=r"(a[0][0]), "=r"(a[0][1]), "=r"(a[0][2]), "=r"(a[0][3]), "=r"(a[0][4]), "=r"(a[0][5]), "=r"(a[0][6]), "=r"(a[0][7]), "=r"(a[1][0]), "=r"(a[1][1]), "=r"(a[1][2]), "=r"(a[1][3]), "=r"(a[1][4]), "=r"(a[1][5]), "=r"(a[1][6]), "=r"(a[1][7]), "=r"(a[2][0]), "=r"(a[2][1]), "=r"(a[2][2]), "=r"(a[2][3]), "=r"(a[2][4]), "=r"(a[2][5]), "=r"(a[2][6]), "=r"(a[2][7]), "=r"(a[3][0]), "=r"(a[3][1]), "=r"(a[3][2]), "=r"(a[3][3]), "=r"(a[3][4]), "=r"(a[3][5]), "=r"(a[3][6]), "=r"(a[3][7]), "=r"(a[4][0]), "=r"(a[4][1]), "=r"(a[4][2]), "=r"(a[4][3]), "=r"(a[4][4]), "=r"(a[4][5]), "=r"(a[4][6]), "=r"(a[4][7]), "=r"(a[5][0]), "=r"(a[5][1]), "=r"(a[5][2]), "=r"(a[5][3]), "=r"(a[5][4]), "=r"(a[5][5]), "=r"(a[5][6]), "=r"(a[5][7])
         : "r"(taddr)
         : "memory");
-  } else if constexpr (CH == 8 && NS == 7) {
+  } else if constexpr (CH == 8 && NS == 7 && BLK == 32) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%56];\n"
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%56+32];\n"
@@ -371,7 +398,7 @@ __device__ __forceinline__ void tc_ld_diagonals(uint32_t taddr, uint32_t (&a)[NS
         : "memory");
   } else {
 #pragma unroll
-    for (int d = 0; d < NS; d++) tc_ld<CH>(taddr + d * 32, a[d]);
+    for (int d = 0; d < NS; d++) tc_ld<CH>(taddr + d * BLK, a[d]);
   }
 }
 // wait for this thread's tcgen05.ld's; the registers are threaded through so no use can be scheduled above it
@@ -405,6 +432,11 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
   }
 }
 
+// scheduling fence for 16 doubles: every later use of tv[] depends on this statement, and it on all of tv[]
+__device__ __forceinline__ void i8_pin16(double (&t)[16]) {
+  asm volatile("" : "+d"(t[0]), "+d"(t[1]), "+d"(t[2]), "+d"(t[3]), "+d"(t[4]), "+d"(t[5]), "+d"(t[6]), "+d"(t[7]), "+d"(t[8]),
+                    "+d"(t[9]), "+d"(t[10]), "+d"(t[11]), "+d"(t[12]), "+d"(t[13]), "+d"(t[14]), "+d"(t[15]));
+}
 // t = sum_d a_d 2^(7 (NS - 1 - d)), exact: adjacent diagonals are merged in int32 (|a_d| <= (d+1) * 32 KB * 4096 < 2^24),
 // up to three merged pairs in int64 (32 x 32 -> 64-bit multiply-adds), then ONE conversion per group.
 // (Measured alternatives, clk per warp-evaluation of the merge alone - profiles/microbench/i8_epilogue_rate.cu:
@@ -627,7 +659,7 @@ template <int FAMILY, bool YBIN, int NS, int KB, int EW, int CH>
 __global__ void __launch_bounds__((EW + 2) * 32, 1)
 tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const double* __restrict__ prop_u, int C,
                        TiledBuffers tb, const int* __restrict__ err) {
-  using G = I8Geom<NS, KB>;
+  using G = I8Geom<NS, KB, i8_blk<NS, KB>(FAMILY)>;
   static_assert(NS >= 2 && NS <= 8, "2..8 slices");
   static_assert(I8_DIGIT_BITS == 7 || (I8_DIGIT_BITS == 8 && NS <= 6), "8-bit digits: at most 6 slices (int64 merge)");
   static_assert(EW == 8 || EW == 16, "2 or 4 epilogue warps per TMEM lane quarter");
@@ -666,7 +698,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     }
     for (int b = 0; b < NACC; b++) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], I8_GROUPED ? EW / 2 : EW);
+      mbar_init(&acc_empty[b], (I8_GROUPED != 0 && EW == 16 && NACC >= 2) ? EW / 2 : EW);
     }
     mbar_init(tab_bar, 1);
     mbar_fence_init();
@@ -873,11 +905,17 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           for (int kb = 0; kb < KB; kb++) {
 #pragma unroll
             for (int j = 0; j < NS; j++) {  // Theta slice j times X slices 0 .. NS-1-j at once: diagonals j .. NS-1
-              const uint32_t idesc = IDESC0 | ((uint32_t)((G::BLK * (NS - j)) >> 3) << 17);
-              const uint64_t bdesc = tc_smem_desc(bblk + (uint32_t)(kb * NS) * G::SLAB_BYTES, 128u, 256u);
+              constexpr int NMAX = 256;      // an instruction's N; a wider operand (wide blocks, j = 0: 320 rows) goes in two halves
+              const int nrows = G::BLK * (NS - j), nparts = nrows > NMAX ? 2 : 1, npart = nrows / nparts;
               const uint32_t accum = (j > 0 || kb > 0) ? 1u : 0u;
-              if (G::a_in_tmem(j, kb)) tc_mma_i8_ts(dbase + j * G::BLK, tmem + G::a_tmem_col(j, kb), bdesc, idesc, accum);
-              else tc_mma_i8_ss(dbase + j * G::BLK, tc_smem_desc(sA_addr + (uint32_t)G::a_smem_unit(j, kb) * 4096u, 128u, 256u), bdesc, idesc, accum);
+#pragma unroll
+              for (int hh = 0; hh < nparts; hh++) {  // rows hh npart ..: 32 bytes per row in 8-row groups of 256 B; their products land npart columns further right
+                const uint32_t idesc = IDESC0 | ((uint32_t)(npart >> 3) << 17);
+                const uint64_t bdesc = tc_smem_desc(bblk + (uint32_t)(kb * NS) * G::SLAB_BYTES + (uint32_t)(hh * npart) * 32u, 128u, 256u);
+                const uint32_t dcol = dbase + j * G::BLK + hh * npart;
+                if (G::a_in_tmem(j, kb)) tc_mma_i8_ts(dcol, tmem + G::a_tmem_col(j, kb), bdesc, idesc, accum);
+                else tc_mma_i8_ss(dcol, tc_smem_desc(sA_addr + (uint32_t)G::a_smem_unit(j, kb) * 4096u, 128u, 256u), bdesc, idesc, accum);
+              }
             }
           }
           tc_commit(&acc_full[buf]);
@@ -897,11 +935,12 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     long long it = 0;
     const uint32_t sp_tab_s = smem_u32(sp_tab);
     const uint32_t sp_tab_lane = sp_tab_s + (uint32_t)(lane & (FM_LC6_REP - 1)) * 16u;  // level 3: this lane's copy / bank group
-    constexpr bool GRP = I8_GROUPED != 0 && EW == 16;
+    constexpr bool GRP = I8_GROUPED != 0 && EW == 16 && NACC >= 2;   // (one accumulator set: every warp visits every block)
     constexpr int CWG = GRP ? 2 * CW : CW;          // columns of a block owned by this warp
     const int grp = h & 1;                          // GRP: this warp's group; it visits every other block
     const int hcol = GRP ? (h >> 1) * CWG : h * CW;
     constexpr int BSTEP = GRP ? 2 : 1;              // blocks between two visits
+    constexpr bool PHASES = I8_PHASE_SPLIT != 0 && FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && KB == 4 && CWG == 16;
     // accumulator set and barrier phase of the next block this warp visits (block n: n % NACC, (n / NACC) & 1)
     uint32_t buf = GRP ? (uint32_t)grp : 0u, par = 0u;
     for (long long tile = first; tile < ntiles; tile += step, it++) {
@@ -914,6 +953,48 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       {
         mbar_wait(&acc_full[buf], par);
         tc_fence_after();
+        if constexpr (PHASES) {
+          // Gaussian family at K = 128, where the tensor pipe is busy most of the time: the integer half of the epilogue -
+          // tcgen05.ld, merge of the diagonals, int64 -> double - runs for ALL of the warp's columns first (it shares no
+          // datapath with the tensor pipe, so it overlaps the MMAs of the other accumulator set), then the FP64 half, which
+          // only gets the pipe while no MMA executes.  Interleaved, every evaluation stalls at its first FP64 instruction.
+          double tv[CWG];
+#pragma unroll
+          for (int cc = 0; cc < CWG / CH; cc++) {
+            uint32_t a[NS][CH];
+            tc_ld_diagonals<NS, CH, G::BLK>(buf * G::ACC_COLS + hcol + cc * CH + lane_base, a);
+            tc_wait_ld<NS, CH>(a);
+            if (cc == CWG / CH - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+#pragma unroll
+            for (int e = 0; e < CH; e++) tv[cc * CH + e] = i8_assemble<NS, CH, KB>(a, e, tb.tune);
+          }
+          i8_pin16(tv);   // nothing of the FP64 half is scheduled above this point
+#pragma unroll
+          for (int cc = 0; cc < CWG / CH; cc++) {
+            const int obs0 = b * G::BLK + hcol + cc * CH;
+            if (obs0 + CH <= valid) {
+              double2 yy[CH / 2];
+#pragma unroll
+              for (int e = 0; e < CH / 2; e++) yy[e] = __ldg(reinterpret_cast<const double2*>(ymeta + obs0) + e);
+#pragma unroll
+              for (int e = 0; e < CH; e++) {
+                const double r = ((e & 1) ? yy[e / 2].y : yy[e / 2].x) - fma(tv[cc * CH + e], csc, b0);
+                acc = fma(r, r, acc);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < CH; e++)
+                if (obs0 + e < valid) {
+                  const double r = __ldg(ymeta + obs0 + e) - fma(tv[cc * CH + e], csc, b0);
+                  acc = fma(r, r, acc);
+                }
+            }
+          }
+        } else
 #ifdef I8_CC_UNROLL
 #pragma unroll
 #else
@@ -931,8 +1012,7 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
           } else
 #endif
           {
-            static_assert(G::BLK == 32, "tc_ld_diagonals: 32 columns between diagonals");
-            tc_ld_diagonals<NS, CH>(buf * G::ACC_COLS + col0 + lane_base, a);
+            tc_ld_diagonals<NS, CH, G::BLK>(buf * G::ACC_COLS + col0 + lane_base, a);   // diagonal d sits d BLK columns further right
           }
           tc_wait_ld<NS, CH>(a);
           if (cc == CWG / CH - 1) {  // this warp's share of the accumulator set is in registers: hand the buffer back
@@ -969,6 +1049,15 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 #pragma unroll
             for (int e = 0; e < CH; e++)
               i8_logistic_even_t<1, false>(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, hi_clamp, acc, acc2, sp_tab, tb.tune);
+          } else if (FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && obs0 + CH <= valid) {
+            double2 yy[CH / 2];   // warp-uniform addresses: broadcast loads, two responses each (y is 16-byte aligned, obs0 a multiple of 8)
+#pragma unroll
+            for (int e = 0; e < CH / 2; e++) yy[e] = __ldg(reinterpret_cast<const double2*>(ymeta + obs0) + e);
+#pragma unroll
+            for (int e = 0; e < CH; e++) {
+              const double r = ((e & 1) ? yy[e / 2].y : yy[e / 2].x) - fma(i8_assemble<NS, CH, KB>(a, e, tb.tune), csc, b0);
+              acc = fma(r, r, acc);
+            }
           } else if (obs0 + CH <= valid) {
 #pragma unroll
             for (int e = 0; e < CH; e++) {

@@ -1,0 +1,9 @@
+python -m pytest tests/test_gpu_i8.py tests/test_gpu_fullsize.py tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/s11_tests.log 2>&1; tail -3 gpurun_out/s11_tests.log
+python bench.py --no-cpu-baseline > gpurun_out/s11_cfg3.json 2> gpurun_out/s11_cfg3.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/s11_cfg3.json"))
+print("cfg3 value %.4g ms/step %.4f stepping %.4f launch %.4f e2e %.4g" % (d["value"], d["ms_per_step"], d["stepping_only"]["ms_per_step"], d["roofline"]["launch_ms"], d["e2e"]["value"]))
+c=d.get("cfg5") or {}
+print("cfg5 value", c.get("value"), "ms/step", c.get("ms_per_step"), "launch", (c.get("roofline") or {}).get("launch_ms"))
+PY
