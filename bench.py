@@ -39,7 +39,9 @@ DATA_SEED = 20260317
 KERNEL_WARMUP = 500
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of this command (profiles/): a profiler figure, so it is a constant here, never measured in the timed run
-TRAFFIC_PER_LAUNCH = {("cfg3", 4): None, ("cfg5", 4): None, ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}   # path 4: filled from the r02 captures
+TRAFFIC_PER_LAUNCH = {("cfg3", 4): 164.9e6,   # profiles/r02_v13_cfg3_tiled_i8_ncu.txt: 160.5 MB read + 4.4 MB written
+                      ("cfg5", 4): 9.64e9,    # profiles/r02_v11_cfg5_tiled_i8_ncu.txt (32-observation blocks; the 64 chain-block CTAs of a slice drift apart in L2)
+                      ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}
 
 
 def make_data(n=N_OBS, p=P_X, seed=DATA_SEED, block=0):
@@ -399,9 +401,8 @@ def measure(wl, args, env, brief=False, chains_total=None):
                 try:
                     if sh is not None:
                         _, mps = sh.gelman(model, first, rows, free, C, k, rows - first, timings=timings)
-                    else:
-                        xb, s2, ws = model.gelman_partials(first, rows, free, C)
-                        _, mps = model.gelman_finish(rows - first, C, k, xb, s2, ws)
+                    else:       # one GPU: what MCMC(conv_checker = convergence_gelman()) calls - coda's window + statistics + finish in ONE library call
+                        _, mps, _ = model.gelman(free)
                 except fm.FmcmcError as e:          # chol(W) may fail on a very short window: the reference warns and goes on
                     mps = f"unavailable: {e}"
                 model.mark(3)
@@ -716,7 +717,7 @@ def main():
         achieved_tf = flops / (hot_ms * 1e-3) / 1e12
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         pipe_slots = 148 * 2 * sm_clock * 1e6                                   # FP64 warp-instructions / s, whole GPU
-        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (10 if wl.family == "logistic" else 3)
+        fp64_instr = wl.fp64_instr_per_eval if path != 4 else (7 if wl.family == "logistic" else 3)   # round 2: 10, round 1: 12
         pipe_util = evals * fp64_instr / 32.0 / (hot_ms * 1e-3) / pipe_slots
         kname = {2: "tiled_loglik_kernel", 3: "tiled_loglik_mma_kernel", 4: "tiled_loglik_i8_kernel", 1: "mh_resident_kernel"}[path]
         line = {
@@ -804,7 +805,12 @@ def main():
                 "int8_mac_per_launch": macs, "int8_peak_mac_per_s": int8_peak, "tensor_floor_ms": 1e3 * t_tensor,
                 "fp64_slots_per_eval": fp64_instr, "fp64_floor_ms": 1e3 * t_fp64, "floor_ms": 1e3 * (t_tensor + t_fp64),
                 "frac": (t_tensor + t_fp64) / (hot_ms * 1e-3),
-                "note": "floor = int8 MACs / measured int8 peak + FP64 epilogue slots / FP64 pipe rate (time-additive on B200)"}
+                "note": "floor = int8 MACs / measured int8 peak + FP64 epilogue slots / FP64 pipe rate (time-additive on B200).  The floor "
+                        "counts THIS kernel's own slice pairs and FP64 slots, so it falls whenever the kernel sheds work: see floor_round1_ms",
+                # the same launch against ROUND 1's floor (21 slice pairs, 12 FP64 slots per evaluation: 0.97 ms at cfg3), the yardstick
+                # VERDICT r1 set its target on (>= 0.70, i.e. <= 1.4 ms per launch at cfg3)
+                "floor_round1_ms": 1e3 * (evals * 21 * 32 * i8_kb / int8_peak + evals * (12 if wl.family == "logistic" else 3) / 32.0 / pipe_slots),
+                "frac_vs_round1_floor": (evals * 21 * 32 * i8_kb / int8_peak + evals * (12 if wl.family == "logistic" else 3) / 32.0 / pipe_slots) / (hot_ms * 1e-3)}
             # the same launch against a roof that does NOT depend on how this kernel splits its operands: the algorithm's own
             # p_x multiply-adds per eval on the int8 tensor pipe at its measured peak + the algorithm's epilogue flops (6 logistic /
             # 4 Gaussian, transcendentals not counted) at the measured FP64 peak.  Adding slices or instructions cannot raise it.
@@ -830,7 +836,7 @@ def main():
                 # every instruction of the epilogue runs on a 16-lane datapath (FP64, IMAD / IMAD.WIDE, SHF, I2F, LDS): the
                 # scheduler issues one warp instruction per 2 clk whatever the pipe (ncu: issue-active 47 % of cycles with
                 # not-selected warps waiting), so the instruction count, not the FP64 count alone, is what bounds the kernel
-                instr = 17                                                      # 10 FP64 + 2 IMAD + LEA.HI.SX32 + IMAD.WIDE + I2F + LEA + LDS.128
+                instr = 15                                                      # 7 FP64 + 2 IMAD + LEA.HI.SX32 + IMAD.WIDE + I2F + IMAD (address) + 2 LDS.128
                 t_issue = evals * instr / 32.0 * 2.0 / (148 * 4 * sm_clock * 1e6)
                 line["roofline_two_engine"].update({
                     "instr_per_eval": instr, "issue_floor_ms": 1e3 * (t_tensor + t_issue),
