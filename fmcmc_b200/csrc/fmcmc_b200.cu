@@ -87,6 +87,7 @@ struct fmcmc_model {
   int trimmed_to = 0;     // fmcmc_model_trim: the only stepping path whose copy of X is still resident (0 = all)
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
   int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
+  int i8_gsl = 0;         // path 4: observation slices per CTA (0: automatic, up to 4; FMCMC_I8_GSL=1|2|4 overrides; A/B measurements)
   bool head_cta = true;   // few chains + kernel_adapt: one CTA per chain in the head kernel (FMCMC_HEAD_CTA=0: the warp-per-chain head; A/B measurements)
   bool pdl = true;        // programmatic dependent launch between the two kernels of an MH row (FMCMC_PDL=0 disables; A/B measurements)
   int mma_wide = 0;       // DMMA tile-shape variant (mma_shape(); FMCMC_MMA_VARIANT, tuning only)
@@ -265,6 +266,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
   if (const char* v = getenv("FMCMC_PDL")) m->pdl = atoi(v) != 0;
   if (const char* v = getenv("FMCMC_HEAD_CTA")) m->head_cta = atoi(v) != 0;
+  if (const char* v = getenv("FMCMC_I8_GSL")) { const int g = atoi(v); if (g == 1 || g == 2 || g == 4) m->i8_gsl = g; }
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
   if (const char* v = getenv("FMCMC_I8_SLICES")) { if (atoi(v) >= I8_NS_LO && atoi(v) <= I8_NS_LO + 1) m->i8_slices = atoi(v); }
@@ -1062,7 +1064,15 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       tb.partial = m->partial.as<double>();
       tb.gx_total = gx;
     }
-    const dim3 lgrid = path >= 3 ? dim3((unsigned)gx * chain_blocks, 1) : dim3(gx, chain_blocks);
+    // path 4: a CTA walks gsl consecutive slices (flushed one by one: the partial sums, hence every bit, do not depend on gsl) so
+    // that its set-up - launch, tensor-memory allocation, Theta slicing, the table's bulk copy, pipeline fill / drain - is paid
+    // once per gsl slices; the CTA count stays a whole number of waves (gx / gsl * chain_blocks, gsl dividing both)
+    int gsl = 1;
+    if (path == 4 && m->i8_gsl != 1)
+      for (int g = (m->i8_gsl > 0 ? m->i8_gsl : 4); g > 1; g >>= 1)
+        if (gx % g == 0 && chain_blocks % g == 0) { gsl = g; break; }
+    tb.gsl = gsl;
+    const dim3 lgrid = path >= 3 ? dim3((unsigned)(gx / gsl) * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;
     // kernel_adapt factorises in 2 kf^2 doubles of shared memory (A, L), kernel_ram needs 4 kf^2: at k = 32 that is 16 KB per

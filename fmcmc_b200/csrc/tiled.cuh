@@ -50,6 +50,7 @@ struct TiledBuffers {
   double* partial;  // [gx_total][ncols]: this step's (parity) block, all ranks' slices when sharded
   int gx_total;     // slices the head kernel reduces (world * gx when sharded, else gx)
   int gx;           // observation slices (gridDim.x of tiled_loglik)
+  int gsl;          // path 4: consecutive slices walked by one CTA (0 / 1: one; grid = gx / gsl * cb CTAs)
   int cb;           // chain blocks (DMMA kernel: 1-D grid of gx * cb CTAs, chain block fastest)
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
   int tune;         // only read when built with -DFMCMC_I8_TUNE_HOOKS (profiling experiments, tiled_i8.cuh)

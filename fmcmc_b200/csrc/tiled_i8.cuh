@@ -686,7 +686,13 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   // warp-uniform and keeps warp-uniform values - the TMEM addresses of the epilogue's tcgen05.ld's above all - in uniform
   // registers (otherwise: one R2UR per load; a shuffle broadcast does not convince it)
   const int warp_u = (int)__reduce_min_sync(FM_FULL, (unsigned)warp);
-  const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice = (int)(blockIdx.x / (unsigned)tb.cb);
+  // A CTA owns one block of 128 chains and tb.gsl >= 1 consecutive observation slices, which it walks one after the other and
+  // flushes one by one: partial[slice][chain] - hence every bit of the log-posterior - is the same whatever gsl is, but the
+  // per-CTA costs (launch, tensor-memory allocation, Theta slicing, the table's bulk copy, pipeline fill and drain: ~6 % of a
+  // cfg3 launch with one slice per CTA) are paid once per gsl slices.
+  const int gsl = tb.gsl > 0 ? tb.gsl : 1;
+  const int chain_block = (int)(blockIdx.x % (unsigned)tb.cb), slice0 = (int)(blockIdx.x / (unsigned)tb.cb) * gsl;
+  const int slice = slice0;
   const long long ntiles = (mp.n + G::TO - 1) / G::TO;
   const long long first = slice, step = tb.gx;
   const int p_x = mp.p_x;
@@ -870,8 +876,9 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
 
   if (warp_u == W_TMA) {
     // ===== producer: one bulk copy per stage (whole warp in the loop, one elected lane issues) =====
-    long long it = n_early;  // the first stages are already on their way
-    for (long long tile = first + (long long)n_early * step; tile < ntiles; tile += step, it++) {
+    long long it = n_early;  // the first stages (of the first slice) are already on their way
+    for (int sl = 0; sl < gsl; sl++)
+    for (long long tile = first + sl + (sl == 0 ? (long long)n_early * step : 0); tile < ntiles; tile += step, it++) {
       const int s = (int)(it % STAGES);
       const uint32_t ph = (uint32_t)((it / STAGES) & 1);
       mbar_wait_sleep(&empty[s], ph ^ 1u, 256);
@@ -889,7 +896,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     const uint32_t sA_addr = smem_u32(sA);
     uint32_t buf = 0, par = 0;  // accumulator set of the next block and the phase of its barriers (block n: n % NACC, (n / NACC) & 1)
     long long it = 0;
-    for (long long tile = first; tile < ntiles; tile += step, it++) {
+    for (int sl = 0; sl < gsl; sl++)
+    for (long long tile = first + sl; tile < ntiles; tile += step, it++) {
       const int s = (int)(it % STAGES);
       mbar_wait_sleep(&full[s], (uint32_t)((it / STAGES) & 1), 32);
       tc_fence_after();
@@ -943,7 +951,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
     constexpr bool PHASES = I8_PHASE_SPLIT != 0 && FAMILY == FMCMC_FAMILY_GAUSSIAN_LM && KB == 4 && CWG == 16;
     // accumulator set and barrier phase of the next block this warp visits (block n: n % NACC, (n / NACC) & 1)
     uint32_t buf = GRP ? (uint32_t)grp : 0u, par = 0u;
-    for (long long tile = first; tile < ntiles; tile += step, it++) {
+    for (int sl = 0; sl < gsl; sl++) {
+    for (long long tile = first + sl; tile < ntiles; tile += step, it++) {
       const double* ymeta = mp.y + tile * G::TO;  // L1-resident broadcast loads (Gaussian / non-binary logistic only)
       const int valid = (int)min((long long)G::TO, mp.n - tile * G::TO);  // < TO only for the last tile
       // the first block of this stage that belongs to the warp's group (blocks are numbered across stages)
@@ -1093,21 +1102,28 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
       }
       }
     }
+    // ---- this slice is complete: the EW / 4 warps of a lane quarter meet in shared memory (epilogue warps only: the producer
+    // and the MMA warp are already working on the next slice), one fixed-order sum per chain, one partial sum per (slice, chain) ----
     // binary logistic: acc holds sum |t|; sum(|eta| / 2 + g) = (csc / 2) sum |t| + sum g
     red[h * I8_CHAINS + q * 32 + lane] = (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) ? fma(0.5 * csc, acc, acc2) : acc + acc2;
+    asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+    if (warp_u < 4 && col < tb.ncols) {
+      double v = red[tid];
+#pragma unroll
+      for (int hh = 1; hh < EW / 4; hh++) v += red[hh * I8_CHAINS + tid];  // fixed order
+      if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) v = (slice0 + sl == 0 ? lin : 0.0) - v;  // theta . sxy enters once per chain
+      // non-finite parameters never reach the integer path: NaN propagates (the reference's `undefined` abort),
+      // +-Inf / beyond 2^480 gives the rejected-proposal value
+      if (th_nan) v = NAN;
+      else if (th_big) v = (FAMILY == FMCMC_FAMILY_LOGISTIC) ? -INFINITY : INFINITY;
+      tb.partial[(size_t)(slice0 + sl) * tb.ncols + col] = v;
+    }
+    if (sl + 1 < gsl) asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // red is written again at the end of the next slice
+    acc = 0.0;
+    acc2 = 0.0;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid < I8_CHAINS && col < tb.ncols) {
-    double v = red[tid];
-#pragma unroll
-    for (int hh = 1; hh < EW / 4; hh++) v += red[hh * I8_CHAINS + tid];  // fixed order
-    if (FAMILY == FMCMC_FAMILY_LOGISTIC && YBIN) v = (slice == 0 ? lin : 0.0) - v;  // theta . sxy enters once per chain
-    // non-finite parameters never reach the integer path: NaN propagates (the reference's `undefined` abort),
-    // +-Inf / beyond 2^480 gives the rejected-proposal value
-    if (th_nan) v = NAN;
-    else if (th_big) v = (FAMILY == FMCMC_FAMILY_LOGISTIC) ? -INFINITY : INFINITY;
-    tb.partial[(size_t)slice * tb.ncols + col] = v;
-  }
   if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
