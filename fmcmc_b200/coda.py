@@ -61,35 +61,67 @@ class Mcmc:
 
 class McmcList(list):
     _arr = None          # [nchains][niter][nvar] when the chains are views of one array (from_array)
+    _meta = None         # (start, end, thin, varnames) of an array-backed list
+    _lazy = False        # array-backed and the per-chain Mcmc views not built yet (they are built on first element access)
 
     @classmethod
     def from_array(cls, arr, start=1, end=None, thin=1, varnames=None):
         """mcmc.list over one [nchains][niter][nvar] array: every chain is a view, as_array() / select() / append_chains
-        work on the whole block at once (65 536 chains are one array, not 65 536 objects' worth of copies)."""
+        work on the whole block at once (65 536 chains are one array, not 65 536 objects' worth of copies).  The per-chain
+        views themselves are only created when an element is asked for: a bulk loop that never looks at them (the device
+        checker reads the sample store) does not pay 1 024 object constructions per bulk."""
         arr = np.asarray(arr, dtype=np.float64)
         start, thin = int(start), int(thin)
         end = int(end) if end is not None else start + (arr.shape[1] - 1) * thin
         names = list(varnames) if varnames is not None else [f"par{i + 1}" for i in range(arr.shape[2])]
-        self = cls(Mcmc._view(arr[c], start, end, thin, names) for c in range(arr.shape[0]))
-        self._arr = arr
+        self = cls()
+        self._arr, self._meta, self._lazy = arr, (start, end, thin, names), True
         return self
+
+    def _fill(self):
+        if self._lazy:
+            self._lazy = False
+            start, end, thin, names = self._meta
+            list.extend(self, (Mcmc._view(self._arr[c], start, end, thin, names) for c in range(self._arr.shape[0])))
+
+    def __len__(self):
+        return self._arr.shape[0] if self._lazy else list.__len__(self)
+
+    def __getitem__(self, idx):
+        self._fill()
+        return list.__getitem__(self, idx)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __eq__(self, other):
+        self._fill()
+        if isinstance(other, McmcList):
+            other._fill()
+        return list.__eq__(self, other)
+
+    __hash__ = None
 
     def nchain(self):
         return len(self)
 
     def niter(self):
-        return self[0].niter()
+        return self._arr.shape[1] if self._meta is not None else self[0].niter()
 
     def nvar(self):
-        return self[0].nvar()
+        return self._arr.shape[2] if self._meta is not None else self[0].nvar()
 
     @property
     def mcpar(self):
-        return self[0].mcpar
+        return self._meta[:3] if self._meta is not None else self[0].mcpar
 
     @property
     def varnames(self):
-        return self[0].varnames
+        return self._meta[3] if self._meta is not None else self[0].varnames
 
     def as_array(self):
         """[nchains][niter][nvar]"""

@@ -1,0 +1,24 @@
+"""cProfile of the public call fm.MCMC(..., conv_checker=convergence_gelman(11)) at bench.py's default workload (cfg3, 100 MH steps
+in 10 bulks): where the host spends the ~1.3 ms per bulk that the end-to-end figure loses against the device-timed one."""
+import cProfile, io, os, pstats, sys, time, contextlib
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np
+import bench
+import fmcmc_b200 as fm
+
+X, y = bench.make_data()
+fam = fm.ll_logistic(X, y, prior_sd=2.0)
+rng = np.random.default_rng(1000)
+C, k = 1024, 32
+init = rng.normal(0, 0.1, (C, k))
+kern = fm.kernel_adapt()
+with open(os.devnull, "w") as dn, contextlib.redirect_stderr(dn):
+    fm.MCMC(init, fam, 560, nchains=C, kernel=kern, seed=1)            # past the kernel's warm-up; model resident
+    def call():
+        return fm.MCMC(init, fam, 110, nchains=C, kernel=kern, conv_checker=fm.convergence_gelman(freq=11, threshold=0.0), seed=2)
+    call()
+    t0 = time.perf_counter(); call(); t1 = time.perf_counter()
+    pr = cProfile.Profile(); pr.enable(); call(); pr.disable()
+print("wall of one call: %.1f ms" % (1e3 * (t1 - t0)))
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:6000])
