@@ -39,8 +39,8 @@ DATA_SEED = 20260317
 KERNEL_WARMUP = 500
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # capture of this command (profiles/): a profiler figure, so it is a constant here, never measured in the timed run
-TRAFFIC_PER_LAUNCH = {("cfg3", 4): 164.9e6,   # profiles/r02_v13_cfg3_tiled_i8_ncu.txt: 160.5 MB read + 4.4 MB written
-                      ("cfg5", 4): 9.64e9,    # profiles/r02_v11_cfg5_tiled_i8_ncu.txt (32-observation blocks; the 64 chain-block CTAs of a slice drift apart in L2)
+TRAFFIC_PER_LAUNCH = {("cfg3", 4): 168.4e6,   # profiles/r02_v13_cfg3_tiled_i8_ncu.txt: 162.5 MB read + 5.9 MB written
+                      ("cfg5", 4): 9.31e9,    # profiles/r02_v13_cfg5_tiled_i8_ncu.txt: 9.276 GB read + 0.034 GB written (the 64 chain-block CTAs of a slice drift apart in L2)
                       ("cfg3", 3): 278.7e6, ("cfg3", 2): 269.7e6}
 
 
@@ -428,13 +428,16 @@ def measure(wl, args, env, brief=False, chains_total=None):
     step_ms = float(sum(r.device_ms for r in reps))
     hot_l = int(sum(r.hot_launches for r in reps))
     hot_ms = float(sum(r.hot_ms for r in reps)) / hot_l if hot_l else step_ms / K      # path 1: one fused launch per bulk
+    hot_series = [float(r.hot_ms) / r.hot_launches for r in reps if r.hot_launches]    # per call: its timed launches' mean
     launches = int(sum(r.n_launches for r in reps)) + nchk * 6                          # + the 3 statistics + 3 finish kernels of a check
     accept = int(sum(r.n_accept for r in reps)) / (C * K)
     path = int(reps[0].path)
     repeats = []
     for _ in range(0 if brief else 2):                 # run-to-run spread of the same region (reported, not used for `value`)
         barrier()
-        repeats.append(region(K)[0] / K)
+        rr = region(K)
+        repeats.append(rr[0] / K)
+        hot_series += [float(q.hot_ms) / q.hot_launches for q in rr[1] if q.hot_launches]
     # ESS of the timed rows on the DEVICE (fmcmc_store_ess: autocovariances + Geyer's initial positive sequence per chain and
     # parameter over the sample store the region just filled), summed over this rank's chains
     ess_dev = None
@@ -444,7 +447,7 @@ def measure(wl, args, env, brief=False, chains_total=None):
             ess_dev = {"per_param_sum_over_chains": e.sum(axis=0), "truncated": trunc, "rows": int(model.store_rows())}
         except fm.FmcmcError as ex:
             ess_dev = {"error": str(ex)}
-    res = dict(ess_dev=ess_dev, dev_ms=dev_ms, step_ms=step_ms, hot_ms=hot_ms, launches=launches, accept=accept, path=path, t_wall=t_wall,
+    res = dict(hot_series=hot_series, ess_dev=ess_dev, dev_ms=dev_ms, step_ms=step_ms, hot_ms=hot_ms, launches=launches, accept=accept, path=path, t_wall=t_wall,
                mpsrf=mpsrf, checks=nchk, check_ms=chk_ms / max(nchk, 1), check_timings=tm, repeats=repeats,
                t_data=t_data, t_model=t_model, C=C, k=k, K=K, ce=ce, ntot=ntot, fam=fam, host_data=host_data,
                model=model, sampler=sampler)
@@ -739,7 +742,10 @@ def main():
                              "device_ms": dev_ms, "stepping_only_ms": step_ms, "rhat_checks": r["checks"],
                              "rhat_check_ms": r["check_ms"], "rhat_check_breakdown": r["check_timings"] or None,
                              "mpsrf_last_check": r["mpsrf"],
-                             "repeat_ms_per_step": r["repeats"]},
+                             "repeat_ms_per_step": r["repeats"],
+                             "hot_launch_ms_series": [round(v, 4) for v in r["hot_series"][:64]],
+                             "hot_launch_ms_series_note": "the timed launches of the dominant kernel, call after call (timed region first, "
+                                                          "then the two repeats): its run-to-run spread as the chains move"},
             "stepping_only": {"value": total_chain_steps / (step_ms * 1e-3), "ms_per_step": step_ms / K,
                               "note": "the same timed region counting only the stepping kernels' CUDA-event time (what round 1 reported as `value`)"},
             "ess_per_s": (float(r["ess_dev"]["per_param_sum_over_chains"].min()) * cw / (dev_ms * 1e-3)

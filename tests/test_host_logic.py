@@ -114,6 +114,24 @@ def test_append_chains_mcpar():
         append_chains(a, Mcmc(np.zeros((5, 3))))
 
 
+def test_array_backed_mcmc_list_builds_its_views_on_demand():
+    """McmcList.from_array (what every MCMC() call returns): shape, mcpar and names are known without creating one Mcmc per
+    chain; the views appear on first element access, share the array's memory and behave like an ordinary list afterwards."""
+    arr = np.arange(3 * 5 * 2, dtype=np.float64).reshape(3, 5, 2)
+    l = McmcList.from_array(arr, 11, 19, 2, ["a", "b"])
+    assert l._lazy and len(l) == 3 and bool(l) and l.nchain() == 3 and l.niter() == 5 and l.nvar() == 2
+    assert l.mcpar == (11, 19, 2) and l.varnames == ["a", "b"] and l.as_array() is arr and l._lazy
+    sel = l.select([1])
+    assert sel.as_array().shape == (3, 5, 1) and sel.varnames == ["b"] and l._lazy
+    m = l[2]
+    assert not l._lazy and isinstance(m, Mcmc) and m.mcpar == (11, 19, 2) and np.shares_memory(m.data, arr)
+    assert [x.data[0, 0] for x in l] == [0.0, 10.0, 20.0] and list.__len__(l) == 3
+    assert l == McmcList.from_array(arr, 11, 19, 2, ["a", "b"]) or True     # comparison materialises both sides without error
+    ap = append_chains(McmcList.from_array(arr, 1, 5, 1), McmcList.from_array(arr, 1, 5, 1))
+    assert ap.nchain() == 3 and ap.niter() == 10 and ap.mcpar == (1, 10, 1)
+    assert McmcList.from_array(np.empty((0, 4, 2))).nchain() == 0 and not McmcList.from_array(np.empty((0, 4, 2)))
+
+
 def test_coda_window_rule():
     """gelman.diag's autoburnin: window(x, start = end/2 + 1); off-grid starts snap UP."""
     assert window_first_row(1, 200, 1, 200, 200 / 2 + 1) == 100
