@@ -7,7 +7,9 @@
   parameters and bounds, freq > 1, and across two calls (state carried, factor cached);
 * programmatic dependent launch on / off (the likelihood kernel's set-up overlapping the head kernel): identical outputs on
   every tiled path;
-* and the head against the oracle with fed streams at 1 / 3 chains (the existing parity matrix runs 1 / 4 / 320 chains too).
+* and the head against the oracle with fed streams at 1 / 3 chains (the existing parity matrix runs 1 / 4 / 320 chains too);
+* path 4 with one, two or four observation slices per CTA (FMCMC_I8_GSL): every slice is flushed into its own row of the partial
+  sums whatever the CTA that walked it, so the outputs are identical bit for bit - logistic (three table levels) and Gaussian.
 """
 import os
 
@@ -109,3 +111,28 @@ def test_cta_head_against_the_oracle(oracle, C):
         assert_parity(gb, ob, 1e-12, f"cta head C={C}")
     assert np.array_equal(st[0], st[2])
     assert np.allclose(st[1], st[3], rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize("family,C", [("logistic", 512), ("logistic", 300), ("gaussian", 256)])
+def test_slices_per_cta_change_nothing(family, C):
+    """512 chains = 4 chain blocks (automatic: four slices per CTA), 300 = 3 blocks (one slice per CTA whatever is asked),
+    256 = 2 blocks (two).  n is large enough for 148 slices with several tiles each, and not a multiple of the tile."""
+    rng = np.random.default_rng(8)
+    n, p = 148 * 128 * 3 + 77, 32
+    if family == "logistic":
+        fam = _logistic_family(rng, n, p)
+        k = p
+        init = rng.normal(0, 0.1, (C, k))
+        init[5] *= 60.0          # one chain block beyond the replicated table, one chain beyond every table
+        init[200] *= 400.0
+    else:
+        from fmcmc_b200 import ll_gaussian_lm
+        X = rng.standard_normal((n, p))
+        y = 1.0 + X @ rng.standard_normal(p) + rng.normal(0, 2.0, n)
+        fam, k = ll_gaussian_lm(X, y, intercept=True, guard=True), p + 2
+        init = np.c_[rng.normal(0, 0.1, (C, k - 1)), np.full(C, 3.0)]
+    spec = dict(type=A.KERNEL_NORMAL, k=k, mu=0.0, scale=0.01)
+    runs = [_run(fam, spec, init, 6, C, {"FMCMC_I8_GSL": g}, path=4) for g in ("1", "2", "4")]
+    assert runs[0][0][0]["path"] == 4
+    _same(runs[0], runs[1])
+    _same(runs[0], runs[2])
