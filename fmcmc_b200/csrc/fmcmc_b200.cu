@@ -87,6 +87,8 @@ struct fmcmc_model {
   int trimmed_to = 0;     // fmcmc_model_trim: the only stepping path whose copy of X is still resident (0 = all)
   int tiled_default = 3;  // tiled variant picked when p_x <= 32 (FMCMC_TILED_VARIANT=2|3 overrides; tuning only)
   int tiled_many = 4;     // tiled variant for > 128 likelihood columns (FMCMC_TILED_MANY=3|4 overrides; tuning only)
+  int l2_bytes = 0;       // L2 cache size of the device
+  int l2_keep_mb = -1;    // path 3, few chains: MB of X kept L2-resident across rows (-1: a third of L2; FMCMC_L2_KEEP_MB)
   int i8_gsl = 0;         // path 4: observation slices per CTA (0: automatic, up to 4; FMCMC_I8_GSL=1|2|4 overrides; A/B measurements)
   bool head_cta = true;   // few chains + kernel_adapt: one CTA per chain in the head kernel (FMCMC_HEAD_CTA=0: the warp-per-chain head; A/B measurements)
   bool pdl = true;        // programmatic dependent launch between the two kernels of an MH row (FMCMC_PDL=0 disables; A/B measurements)
@@ -189,6 +191,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   MC(cudaEventCreate(&m->ev1));
   MC(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
   MC(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  MC(cudaDeviceGetAttribute(&m->l2_bytes, cudaDevAttrL2CacheSize, device));
   const bool aligned16 = (((uintptr_t)d->X | (uintptr_t)d->y) & 15) == 0;   // TMA bulk copies and vector loads need 16-byte aligned columns
   if (device_ptrs && ld == n && aligned16) {  // borrow
     m->borrowed = true;
@@ -266,6 +269,7 @@ static int model_create_impl(const fmcmc_model_desc* d, int device, bool device_
   if (const char* v = getenv("FMCMC_TILED_MANY")) { if (atoi(v) == 3 || atoi(v) == 4) m->tiled_many = atoi(v); }
   if (const char* v = getenv("FMCMC_PDL")) m->pdl = atoi(v) != 0;
   if (const char* v = getenv("FMCMC_HEAD_CTA")) m->head_cta = atoi(v) != 0;
+  if (const char* v = getenv("FMCMC_L2_KEEP_MB")) m->l2_keep_mb = atoi(v);
   if (const char* v = getenv("FMCMC_I8_GSL")) { const int g = atoi(v); if (g == 1 || g == 2 || g == 4) m->i8_gsl = g; }
   if (const char* v = getenv("FMCMC_MMA_VARIANT")) m->mma_wide = atoi(v);
   if (const char* v = getenv("FMCMC_PATH")) { if (atoi(v) >= 1 && atoi(v) <= 4) m->forced_path = atoi(v); }  // tuning / profiling only
@@ -1072,6 +1076,14 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
       for (int g = (m->i8_gsl > 0 ? m->i8_gsl : 4); g > 1; g >>= 1)
         if (gx % g == 0 && chain_blocks % g == 0) { gsl = g; break; }
     tb.gsl = gsl;
+    // path 3 with one chain block (the few-chain, HBM-bound regime) on data larger than L2: keep a part of the tile-major X
+    // L2-resident from row to row (tiled_mma.cuh); FMCMC_L2_KEEP_MB overrides the size (0 disables; A/B measurements)
+    if (path == 3 && chain_blocks == 1 && !sharded) {
+      const size_t stage_bytes = (msh.PB <= 32 ? MmaGeom<32>::STAGE_DOUBLES : (msh.PB == 64 ? MmaGeom<64>::STAGE_DOUBLES : MmaGeom<128>::STAGE_DOUBLES)) * sizeof(double), total = (size_t)ntiles * stage_bytes;
+      size_t keep_bytes = (size_t)(0.33 * m->l2_bytes);   // B200, n = 1e6, p = 32, 4 chains: 0 / 40 / 60 / 75 / 90 / 110 MB -> 68.7 / 64.7 / 65.1 / 65.3 / 68.1 / 69.8 us per MH step
+      if (m->l2_keep_mb >= 0) keep_bytes = (size_t)m->l2_keep_mb << 20;
+      if (total > (size_t)m->l2_bytes && keep_bytes > 0) tb.l2_keep_tiles = (long long)(keep_bytes / stage_bytes);
+    }
     const dim3 lgrid = path >= 3 ? dim3((unsigned)(gx / gsl) * chain_blocks, 1) : dim3(gx, chain_blocks);
     const int hblocks = (C + TL_HEAD_WARPS - 1) / TL_HEAD_WARPS;
     const bool adaptive = ks->type == FMCMC_KERNEL_ADAPT || ks->type == FMCMC_KERNEL_RAM;

@@ -51,6 +51,8 @@ struct TiledBuffers {
   int gx_total;     // slices the head kernel reduces (world * gx when sharded, else gx)
   int gx;           // observation slices (gridDim.x of tiled_loglik)
   int gsl;          // path 4: consecutive slices walked by one CTA (0 / 1: one; grid = gx / gsl * cb CTAs)
+  long long l2_keep_tiles;  // path 3, one chain block, X larger than L2: tiles [0, l2_keep_tiles) are fetched with the evict_last policy and
+                            // stay L2-resident from MH row to MH row, the rest with evict_first (0: no hints)
   int cb;           // chain blocks (DMMA kernel: 1-D grid of gx * cb CTAs, chain block fastest)
   int ncols;        // C (or 2C for kernel_ram: second half = un-reflected proposals)
   int tune;         // only read when built with -DFMCMC_I8_TUNE_HOOKS (profiling experiments, tiled_i8.cuh)

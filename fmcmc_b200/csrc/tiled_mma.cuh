@@ -118,10 +118,20 @@ tiled_loglik_mma_kernel(ModelParams mp, const double* __restrict__ prop, const d
   }
   __syncthreads();
 
+  // With a handful of chains this kernel is HBM-bound and X (256 MB at n = 1e6, p = 32) does not fit the 126 MB L2: streamed
+  // with the default policy every MH row evicts all of it for the next one.  The first l2_keep_tiles tiles are fetched
+  // evict_last, the others evict_first, so that part of X is served from L2 on every row after the first.
+  const bool l2_hints = tb.l2_keep_tiles > 0;
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (l2_hints && tid == 0) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
   auto issue = [&](long long tile, int s) {  // executed by thread 0 only: one bulk copy per stage (tile-major Xt)
     constexpr uint32_t BYTES = (uint32_t)(STAGE_DOUBLES * sizeof(double));
     mbar_expect_tx(&full[s], BYTES);
-    bulk_g2s(stage0 + (size_t)s * STAGE_DOUBLES, mp.Xt + (size_t)tile * STAGE_DOUBLES, BYTES, &full[s]);
+    if (l2_hints)
+      bulk_g2s_hint(stage0 + (size_t)s * STAGE_DOUBLES, mp.Xt + (size_t)tile * STAGE_DOUBLES, BYTES, &full[s],
+                    tile < tb.l2_keep_tiles ? pol_keep : pol_stream);
+    else
+      bulk_g2s(stage0 + (size_t)s * STAGE_DOUBLES, mp.Xt + (size_t)tile * STAGE_DOUBLES, BYTES, &full[s]);
   };
 
   // ---- pipeline prologue: X does not depend on the head kernel, so the first stages are requested BEFORE waiting for it
