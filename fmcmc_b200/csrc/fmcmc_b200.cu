@@ -683,7 +683,7 @@ static int i8_kblocks(int p_x) { return p_x <= 32 ? 1 : (p_x <= 64 ? 2 : 4); }
 #endif
 // observations per pipeline stage / tile of Xq (the Gaussian family at K = 128 packs 64-observation blocks: tiled_i8.cuh, i8_blk)
 static int i8_tile_rows(int family, int NS, int KB) {
-#define I8_CASE(N, K) if (NS == N && KB == K) return family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::TO : I8Geom<N, K>::TO;
+#define I8_CASE(N, K) if (NS == N && KB == K) return family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::TO : I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_LOGISTIC)>::TO;
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
   return 32;
@@ -698,7 +698,7 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   const int TO = i8_tile_rows(mp.family, NS, KB);
   const long long ntiles = (mp.n + TO - 1) / TO;
   size_t stage_bytes = 0;
-#define I8_CASE(N, K) if (NS == N && KB == K) stage_bytes = gauss ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::STAGE_BYTES : I8Geom<N, K>::STAGE_BYTES;
+#define I8_CASE(N, K) if (NS == N && KB == K) stage_bytes = gauss ? I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM)>::STAGE_BYTES : I8Geom<N, K, i8_blk<N, K>(FMCMC_FAMILY_LOGISTIC)>::STAGE_BYTES;
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE
   if (!stage_bytes) return cudaErrorInvalidValue;
@@ -726,9 +726,9 @@ static cudaError_t ensure_packed_i8(fmcmc_model* m, int NS, int KB) {
   i8_sxy_kernel<<<(unsigned)mp.p_x, 1024, 0, m->stream>>>(mp.X, mp.y, mp.n, mp.ld, sxy);
 #define I8_CASE(N, K)                                                                                                      \
   if (NS == N && KB == K) {                                                                                                \
-    constexpr int BW = i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM);                                                             \
-    if (gauss && BW != 32) pack_i8_kernel<N, K, BW><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq); \
-    else pack_i8_kernel<N, K, 32><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);            \
+    constexpr int BW = i8_blk<N, K>(FMCMC_FAMILY_GAUSSIAN_LM), BL = i8_blk<N, K>(FMCMC_FAMILY_LOGISTIC);                   \
+    if (gauss) pack_i8_kernel<N, K, BW><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);      \
+    else pack_i8_kernel<N, K, BL><<<(unsigned)ntiles, TO, 0, m->stream>>>(mp.X, mp.n, mp.ld, mp.p_x, cexp, xq);            \
   }
   I8_FOR_SHAPES(I8_CASE)
 #undef I8_CASE

@@ -88,15 +88,28 @@
 #ifndef I8_PHASE_SPLIT
 #define I8_PHASE_SPLIT 0
 #endif
+// 48-observation blocks (N = 240, 192, 144, 96, 48: 435 clk per K block and 48 observations, two sets of 240 columns, the 32
+// columns left hold Theta slices 0 .. 3 of the first K block, the others are read from shared memory): build-time experiments,
+// -DI8_BLK_LOGIT_K32=48 / -DI8_BLK_GAUSS_K128=48 (profiles/r02_findings.md, section 19)
+#ifndef I8_BLK_LOGIT_K32
+#define I8_BLK_LOGIT_K32 32
+#endif
+#ifndef I8_BLK_GAUSS_K128
+#define I8_BLK_GAUSS_K128 (I8_WIDE_BLOCKS != 0 ? 64 : 32)
+#endif
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_blk(int family) {
-  return (I8_WIDE_BLOCKS != 0 && family == FMCMC_FAMILY_GAUSSIAN_LM && KB == 4 && NS == 5 && I8_DIGIT_BITS == 8) ? 64 : 32;
+  if (I8_DIGIT_BITS == 8 && NS == 5) {
+    if (family == FMCMC_FAMILY_GAUSSIAN_LM && KB == 4) return I8_BLK_GAUSS_K128;
+    if (family == FMCMC_FAMILY_LOGISTIC && KB == 1) return I8_BLK_LOGIT_K32;
+  }
+  return 32;
 }
 template <int NS, int KB, int BLK_ = 32>
 struct I8Geom {
   static constexpr int DB = I8_DIGIT_BITS;
   static constexpr int BLK = BLK_;                                  // observations per MMA block
-  static constexpr int TO = KB == 1 ? 128 : (KB == 2 ? 64 : BLK);   // observations per pipeline stage
+  static constexpr int TO = KB == 1 ? (BLK == 48 ? 96 : 128) : (KB == 2 ? 64 : BLK);   // observations per pipeline stage
   static constexpr int NBLK = TO / BLK;
   static constexpr int SLAB_BYTES = BLK * 32;                        // one slice x one K block of a block: BLK / 8 row groups x 2 chunks x 128 B
   static constexpr int BLOCK_BYTES = KB * NS * SLAB_BYTES;           // [kb][slice][group][chunk][8 rows][16 B]
@@ -108,13 +121,16 @@ struct I8Geom {
   // its next block (12 % of the warps' time in round 2's profile); with three the MMA warp runs a block ahead - correct
   // (all parity tests), but not faster: while the tensor pipe works the FP64 pipe does not, wherever the warps happen to wait.
   // Wide blocks (BLK = 64): one set.
-  static constexpr int NACC = BLK > 32 ? 1 : ((I8_TRIPLE != 0 && KB == 1 && 3 * ACC_COLS + (NS - 1) * 8 <= 512) ? 3 : 2);
+  static constexpr int NACC = BLK > 48 ? 1 : ((I8_TRIPLE != 0 && KB == 1 && 3 * ACC_COLS + (NS - 1) * 8 <= 512) ? 3 : 2);
   // A operand (Theta slices): 8 columns per (slice, K block) unit.  NACC == 2: as many K blocks as fit beside the two sets
   // live in tensor memory (all slices of those K blocks), the rest in shared memory; NACC == 3: slices 0 .. NS-2 in tensor
   // memory, the last slice (one MMA of N = 32 per block) in shared memory.  An MMA whose A comes from shared memory re-reads 4 KB.
+  // When not even one K block fits with all its slices (48-observation blocks: 32 columns left), slices 0 .. A_TS-1 of the first K
+  // block do.
   static constexpr int A_COL0 = NACC * ACC_COLS;
-  static constexpr int A_TS = NACC == 3 ? NS - 1 : NS;
-  static constexpr int A_TKB = NACC == 3 ? 1 : (((512 - A_COL0) / (NS * 8)) < KB ? ((512 - A_COL0) / (NS * 8)) : KB);
+  static constexpr int A_FULL = (512 - A_COL0) / (NS * 8);          // K blocks that fit with all their slices
+  static constexpr int A_TS = NACC == 3 ? NS - 1 : (A_FULL >= 1 ? NS : ((512 - A_COL0) / 8 < NS ? (512 - A_COL0) / 8 : NS));
+  static constexpr int A_TKB = NACC == 3 ? 1 : (A_FULL >= 1 ? (A_FULL < KB ? A_FULL : KB) : ((512 - A_COL0) >= 8 ? 1 : 0));
   static constexpr int A_SKB = KB - A_TKB;
   static constexpr int A_SMEM_BYTES = (NS * A_SKB + (NS - A_TS) * A_TKB) * 4096;
   __host__ __device__ static constexpr bool a_in_tmem(int i, int kb) { return kb < A_TKB && i < A_TS; }
@@ -139,7 +155,8 @@ __host__ __device__ constexpr int i8_scratch_bytes(int family) {
 }
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_table_level() {
-  return (232448 - i8_smem_fixed<NS, KB>(FM_SP8_ENTRIES * 16)) / I8Geom<NS, KB>::STAGE_BYTES >= 2 ? 2 : 1;
+  constexpr int BL = i8_blk<NS, KB>(FMCMC_FAMILY_LOGISTIC);
+  return (232448 - i8_smem_fixed<NS, KB, BL>(FM_SP8_ENTRIES * 16)) / I8Geom<NS, KB, BL>::STAGE_BYTES >= 2 ? 2 : 1;
 }
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_table_entries() { return i8_table_level<NS, KB>() == 2 ? FM_SP8_ENTRIES : FM_SP4_ENTRIES; }
@@ -151,7 +168,8 @@ __host__ __device__ constexpr int i8_table_entries() { return i8_table_level<NS,
 #endif
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_rep_entries() {
-  const int fit = (232448 - i8_smem_fixed<NS, KB>(0) - 2 * I8Geom<NS, KB>::STAGE_BYTES) / FM_LC6_POINT_BYTES;
+  constexpr int BL = i8_blk<NS, KB>(FMCMC_FAMILY_LOGISTIC);
+  const int fit = (232448 - i8_smem_fixed<NS, KB, BL>(0) - 2 * I8Geom<NS, KB, BL>::STAGE_BYTES) / FM_LC6_POINT_BYTES;
   const int e = fit > FM_LC6_ENTRIES_MAX ? FM_LC6_ENTRIES_MAX : fit;
   return (I8_REP_TABLE != 0 && i8_table_level<NS, KB>() == 2 && e >= 5 * FM_LC6_H + 1) ? e : 0;  // worth it from |eta| <= 5 on
 }
@@ -163,17 +181,17 @@ __host__ __device__ constexpr int i8_table_bytes(int family, bool ybin) {
 // pipeline depth: as many stages as fit beside the Theta slices and the softplus table, at most 6.
 template <int NS, int KB>
 __host__ __device__ constexpr int i8_stages(int family, bool ybin) {
-  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM);   // (only the Gaussian family has wide blocks)
-  const int stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB>::STAGE_BYTES;
-  const int fixed = family == FMCMC_FAMILY_GAUSSIAN_LM ? i8_smem_fixed<NS, KB, B>(0) : i8_smem_fixed<NS, KB>(i8_table_bytes<NS, KB>(family, ybin));
+  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM), BL = i8_blk<NS, KB>(FMCMC_FAMILY_LOGISTIC);
+  const int stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB, BL>::STAGE_BYTES;
+  const int fixed = family == FMCMC_FAMILY_GAUSSIAN_LM ? i8_smem_fixed<NS, KB, B>(0) : i8_smem_fixed<NS, KB, BL>(i8_table_bytes<NS, KB>(family, ybin));
   const int fit = (232448 - fixed - i8_scratch_bytes(family)) / stage;
   return fit > 6 ? 6 : fit;
 }
 template <int NS, int KB>
 __host__ __device__ inline size_t tiled_i8_smem_bytes(int family, bool ybin) {
-  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM);
-  const size_t stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB>::STAGE_BYTES;
-  const size_t asmem = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::A_SMEM_BYTES : I8Geom<NS, KB>::A_SMEM_BYTES;
+  constexpr int B = i8_blk<NS, KB>(FMCMC_FAMILY_GAUSSIAN_LM), BL = i8_blk<NS, KB>(FMCMC_FAMILY_LOGISTIC);
+  const size_t stage = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::STAGE_BYTES : I8Geom<NS, KB, BL>::STAGE_BYTES;
+  const size_t asmem = family == FMCMC_FAMILY_GAUSSIAN_LM ? I8Geom<NS, KB, B>::A_SMEM_BYTES : I8Geom<NS, KB, BL>::A_SMEM_BYTES;
   size_t b = 256 + (size_t)i8_stages<NS, KB>(family, ybin) * stage + asmem +
              (size_t)i8_table_bytes<NS, KB>(family, ybin) + (I8_MAX_EPI_WARPS / 4) * I8_CHAINS * sizeof(double) + i8_scratch_bytes(family);
   return b < 120 * 1024 ? 120 * 1024 : b;  // one CTA per SM: a CTA allocates all 512 TMEM columns
@@ -663,8 +681,8 @@ tiled_loglik_i8_kernel(ModelParams mp, const double* __restrict__ prop, const do
   static_assert(NS >= 2 && NS <= 8, "2..8 slices");
   static_assert(I8_DIGIT_BITS == 7 || (I8_DIGIT_BITS == 8 && NS <= 6), "8-bit digits: at most 6 slices (int64 merge)");
   static_assert(EW == 8 || EW == 16, "2 or 4 epilogue warps per TMEM lane quarter");
-  constexpr int CW = G::BLK / (EW / 4);  // columns (observations) of a block owned by one epilogue warp
-  static_assert(CW % CH == 0, "whole chunks");
+  constexpr int CW = G::BLK / (EW / 4);  // columns (observations) of a block owned by one epilogue warp (grouped epilogue: twice that)
+  static_assert((((I8_GROUPED != 0 && EW == 16 && G::NACC >= 2) ? 2 : 1) * CW) % CH == 0, "whole chunks");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   constexpr int STAGES = i8_stages<NS, KB>(FAMILY, YBIN);
