@@ -240,7 +240,9 @@ typedef struct fmcmc_run_report {
   int32_t path;          /* 1 = chain-resident fused kernel, 2 = observation-tiled (DFMA), 3 = (DMMA), 4 = (tcgen05 int8 slices) */
   int32_t reserved;
   double  hot_ms;        /* summed CUDA-event time of the dominant kernel's launches ... */
-  int64_t hot_launches;  /* ... and how many of them were timed (path 2: tiled_loglik)   */
+  int64_t hot_launches;  /* ... and how many of them were timed: the first and every 16th likelihood launch of a call
+                            (a timed launch is bracketed by event records and therefore does not overlap its set-up with
+                            the preceding head kernel - programmatic dependent launch -, the others do)               */
   int64_t h2d_bytes;     /* bytes this call copied host -> device                        */
   int64_t d2h_bytes;     /* bytes this call copied device -> host                        */
 } fmcmc_run_report;
