@@ -1100,10 +1100,16 @@ extern "C" int fmcmc_run(fmcmc_model* m, const fmcmc_run_spec* run, const fmcmc_
     const bool pdl_ok = m->pdl && !(m->shard_world > 1);
     bool pdl_head = false;
     // few chains, kernel_adapt with the Cholesky draw: a CTA per chain (tiled.cuh, tiled_head_adapt_cta_kernel) - same results bit for bit
+    // (with more chains than SMs the same kernel at 128 threads per chain - 8 chains per CTA - was measured SLOWER than the
+    // warp-per-chain head at 1 024 chains, 58 against 33 us per row: profiles/r02_findings.md, section 20)
     const bool head_cta = m->head_cta && kclass == KC_ADAPT && ks->mvn_method != FMCMC_MVN_EIGEN && ks->bw <= 0 && kf <= 32 && C <= m->sm_count;
+    if (head_cta) {
+      cudaError_t ae = cudaFuncSetAttribute(tiled_head_adapt_cta_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_headc_smem_bytes(1024));
+      if (ae != cudaSuccess) { set_err(err, errlen, "CUDA error %s (tiled_head_adapt_cta attributes)", cudaGetErrorString(ae)); return FMCMC_ECUDA; }
+    }
     auto head_launch = [&](long long row) -> cudaError_t {
       if (head_cta)
-        return launch_chained(tiled_head_adapt_cta_kernel, dim3(C), dim3(TL_HEADC_THREADS), 0, m->stream, pdl_head,
+        return launch_chained(tiled_head_adapt_cta_kernel<1024>, dim3(C), dim3(TL_HEADC_THREADS), tiled_headc_smem_bytes(1024), m->stream, pdl_head,
                               mp, kp, sp, rb, tb, d_initial, row);
 #define HEAD_CASE(K)                                                                                              \
   case K:                                                                                                          \

@@ -316,29 +316,46 @@ tiled_head_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, Ti
   }
 }
 
-// ---- the few-chain head of kernel_adapt: one CTA per chain ---------------------------------------------------------------
+// ---- the block-parallel head of kernel_adapt: TPC threads per chain ---------------------------------------------------------
 // With a handful of chains (the reference's typical usage) the warp-per-chain head above is a single warp walking the
 // covariance recurrence and a 32 x 32 left-looking Cholesky factorisation: ~30 us of dependent instructions per MH row, as long
-// as the HBM-bound likelihood launch next to it.  Here a chain owns a CTA of 1 024 threads, thread (i, j) = (lane, warp) one
-// entry of the k_f x k_f matrices: the recurrence is one multiply-add per thread, and the factorisation runs RIGHT-looking in
-// registers - after column p is final (warp p: square root and divisions), every entry (i, j > p) subtracts L[i][p] L[j][p].
-// Each entry still sees its subtractions in the order p = 0, 1, 2 ... with the same unfused operations, so the factor - hence
-// every draw - is bit-identical to the left-looking loop (chol_lower_warp) and to the oracle; the critical path is 32 steps of
-// (sqrt, divide, multiply, subtract, one barrier) instead of 496 dependent multiply-subtracts.
-// Finishing the previous row (partial sums, accept / reject, output rows) is warp 0's job, exactly as above.
-// Chosen by fmcmc_run for kernel_adapt with the Cholesky draw, bw = 0, k_f <= 32 and at most one CTA per SM of chains.
+// as the HBM-bound likelihood launch next to it.  Here a chain owns TPC threads - a whole CTA of 1 024 with few chains (thread
+// (i, j) = (lane, warp) holds ONE entry of the k_f x k_f matrices), 128 threads = 4 warps with many (8 chains per CTA; lane i of
+// warp w holds the 8 entries (i, w), (i, w + 4) ... (i, w + 28)): the recurrence is one multiply-add per entry, and the
+// factorisation runs RIGHT-looking in registers - after column p is final (its warp: square root and divisions), every entry
+// (i, j > p) subtracts L[i][p] L[j][p].  Each entry still sees its subtractions in the order p = 0, 1, 2 ... with the same
+// unfused operations, so the factor - hence every draw - is bit-identical to the left-looking loop (chol_lower_warp) and to the
+// oracle; the critical path is 32 steps of (sqrt, divide, multiply-subtracts, one named barrier among the chain's threads)
+// instead of 496 dependent multiply-subtracts.  Finishing the previous row (partial sums, accept / reject, output rows) is the
+// job of the chain's first warp, exactly as above.
+// Chosen by fmcmc_run for kernel_adapt with the Cholesky draw, bw = 0, k_f <= 32 and at most one chain per SM (TPC = 1 024).  The
+// 128-thread instantiation is correct (bit-identical in tests/test_gpu_session3.py when enabled) but slower than the
+// warp-per-chain head at 1 024 chains (58 against 33 us per row): not instantiated by the library.
 #define TL_HEADC_THREADS 1024
+__host__ __device__ inline size_t tiled_headc_smem_bytes(int tpc) {   // per chain: L columns [32][33], x / m / mp / z [4][32], stop flag
+  return (size_t)(TL_HEADC_THREADS / tpc) * ((32 * 33 + 4 * 32) * sizeof(double) + 16);
+}
+template <int TPC>
 __global__ void __launch_bounds__(TL_HEADC_THREADS)
 tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuffers rb, TiledBuffers tb,
                             const double* initial, long long row) {
-  __shared__ double s_x[32], s_m[32], s_mp[32], s_z[32];
-  __shared__ double s_L[32][33];   // s_L[p][i] = L[i][p]
-  __shared__ int s_stop;           // != 0: the chain stops here (error recorded, or nothing left to do)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long c = blockIdx.x;
+  constexpr int CPB = TL_HEADC_THREADS / TPC;   // chains per CTA
+  constexpr int W = TPC / 32;                   // warps per chain
+  constexpr int NE = 32 / W;                    // matrix entries per thread: columns w, w + W, ...
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int grp = threadIdx.x / TPC, t = threadIdx.x % TPC, lane = t & 31, warp = t >> 5;
+  double* sbase = reinterpret_cast<double*>(smem_raw) + (size_t)grp * (32 * 33 + 4 * 32 + 2);
+  double (*s_L)[33] = reinterpret_cast<double (*)[33]>(sbase);   // s_L[p][i] = L[i][p]
+  double* s_x = sbase + 32 * 33;
+  double* s_m = s_x + 32;
+  double* s_mp = s_m + 32;
+  double* s_z = s_mp + 32;
+  volatile int* s_stop = reinterpret_cast<volatile int*>(s_z + 32);   // != 0: the chain stops here (error recorded, or nothing left to do)
+  const long long c = (long long)blockIdx.x * CPB + grp;
+  auto chain_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(TPC) : "memory"); };   // the chain's threads only
   pdl_launch_dependents();
   pdl_wait();
-  if (rb.err[0] != 0) return;
+  if (rb.err[0] != 0 || c >= rb.nchains) return;   // (whole chains leave: their barriers are their own)
   const int k = kp.k, kf = kp.kf;
   double* th0 = rb.cur_theta + (size_t)c * k;
   double* th1 = rb.prop + (size_t)c * k;
@@ -357,10 +374,10 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
     }
     return;
   }
-  if (tid == 0) s_stop = 0;
-  __syncthreads();
+  if (t == 0) *s_stop = 0;
+  chain_sync();
 
-  // ---- finish row r = row - 1 (warp 0; same steps as tiled_head_kernel) ----
+  // ---- finish row r = row - 1 (the chain's first warp; same steps as tiled_head_kernel) ----
   if (warp == 0) {
     const long long r = row - 1;
     bool stop = false;
@@ -404,10 +421,11 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
       }
     }
     if (row > rb.T) stop = true;   // the last launch only finishes row T
-    if (stop && lane == 0) s_stop = 1;
+    if (stop && lane == 0) *s_stop = 1;
   }
-  __syncthreads();   // (also publishes warp 0's global writes - theta0, the ans row, colsum - to the CTA)
-  if (s_stop) return;
+  __threadfence_block();
+  chain_sync();   // (also publishes the first warp's global writes - theta0, the ans row, colsum - to the chain's threads)
+  if (*s_stop) return;
 
   // ---- propose row `row`: R/kernel_adapt.R:84-182, the steps of propose_warp<KC_ADAPT> ----
   const long long i = row;
@@ -418,12 +436,12 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
   double* L = rb.work + (size_t)c * rb.worklen;
   int* cflag = rb.chain_flags + c;
   bool dirty = !(*cflag & 2);
-  __syncthreads();   // every thread has read the chain's state words before anyone updates them below
+  chain_sync();   // every thread has read the chain's state words before anyone updates them below
   ChainCtx cx;
   cx.c = c; cx.i = i; cx.theta0 = th0; cx.theta1 = th1; cx.theta1u = th1u; cx.scr = nullptr; cx.f0 = 0.0;
   cx.ans = rb.ans; cx.ans_stride = (long long)rb.nchains * k; cx.mat = nullptr;
   if (!(flags & FMCMC_STATE_INIT)) {  // :87-115
-    for (int e = tid; e < kf * kf; e += TL_HEADC_THREADS) Sigma[e] = ((e % kf) == (e / kf)) ? kp.eps : 0.0;
+    for (int e = t; e < kf * kf; e += TPC) Sigma[e] = ((e % kf) == (e / kf)) ? kp.eps : 0.0;
     flags |= FMCMC_STATE_INIT;
     dirty = true;
   }
@@ -441,14 +459,15 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
       }
       flags |= FMCMC_STATE_HAS_MEAN;
     }
-    const double t = (double)(abs_iter - kp.freq);  // :144
-    if (i - kp.freq < 1 || t == 0.0) {              // the reference indexes row <= 0 / divides by zero here
-      if (tid == 0) set_error(rb.err, FMCMC_EUNSUP, c + 1, row);
+    const double tt = (double)(abs_iter - kp.freq);  // :144
+    if (i - kp.freq < 1 || tt == 0.0) {              // the reference indexes row <= 0 / divides by zero here
+      if (t == 0) set_error(rb.err, FMCMC_EUNSUP, c + 1, row);
       return;
     }
-    __syncthreads();
+    __threadfence_block();
+    chain_sync();
     for (long long jj = 0; jj < kp.freq; jj++) {  // rows (i-freq):(i-1), R/recursive.R:78-110
-      const double tj = t + (double)jj;
+      const double tj = tt + (double)jj;
       if (warp == 0) {
         const double* xr = ans_row(cx, kp, i - kp.freq + jj);
         for (int a = lane; a < kf; a += FM_WARP) {
@@ -459,9 +478,9 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
           s_m[a] = xdiv(xadd(xmul(mpa, tj), xa), tj + 1.0);  // mean_recursive :126
         }
       }
-      __syncthreads();
+      chain_sync();
       const double c1 = xdiv(tj - 1.0, tj), c2 = xdiv(1.0, tj);
-      for (int e = tid; e < kf * kf; e += TL_HEADC_THREADS) {  // cov_recursive :112-118, Sd = 1, eps = 1e-5
+      for (int e = t; e < kf * kf; e += TPC) {  // cov_recursive :112-118, Sd = 1, eps = 1e-5
         const int a = e % kf, b = e / kf;
         double inner = xsub(xmul(tj, xmul(s_mp[a], s_mp[b])), xmul(tj + 1.0, xmul(s_m[a], s_m[b])));
         inner = xadd(inner, xmul(s_x[a], s_x[b]));
@@ -470,37 +489,56 @@ tiled_head_adapt_cta_kernel(ModelParams mp, KParams kp, StreamParams sp, RunBuff
       }
       if (warp == 0)
         for (int a = lane; a < kf; a += FM_WARP) Mean_prev[a] = s_m[a];
-      __syncthreads();
+      __threadfence_block();
+      chain_sync();
     }
     dirty = true;
   }
   abs_iter += 1;  // :170
   if (dirty) {
-    __syncthreads();   // Sigma complete (its entries were written by other threads when k_f < 32)
-    const int ri = lane, cj = warp;
-    const bool active = ri < kf && cj < kf && ri >= cj;
-    double v = active ? Sigma[ri + cj * kf] : 0.0;
-    for (int p = 0; p < kf; p++) {
-      if (warp == p) {  // column p is final: pivot, square root, divisions (chol_lower_warp's second pass)
-        const double s = __shfl_sync(FM_FULL, v, p);
-        if (!(s > 0.0)) {
-          if (lane == 0) s_stop = p + 1;
-        } else {
-          const double ljj = sqrt(s);
-          v = (lane == p) ? ljj : xdiv(v, ljj);
-          if (lane >= p && lane < kf) s_L[p][lane] = v;
-        }
-      }
-      __syncthreads();
-      if (s_stop) break;
-      if (active && cj > p) v = xsub(v, xmul(s_L[p][ri], s_L[p][cj]));
+    __threadfence_block();
+    chain_sync();   // Sigma complete (its entries were written by other threads of the chain)
+    const int ri = lane;
+    double v[NE];
+#pragma unroll
+    for (int q = 0; q < NE; q++) {
+      const int cj = warp + W * q;
+      v[q] = (ri < kf && cj < kf && ri >= cj) ? Sigma[ri + cj * kf] : 0.0;
     }
-    if (s_stop) {  // mvrnorm: "'Sigma' is not positive definite"
-      if (tid == 0) set_error(rb.err, FMCMC_ENOTPD, c + 1, row);
+    for (int p = 0; p < kf; p++) {
+      if (warp == p % W) {  // column p is final: pivot, square root, divisions (chol_lower_warp's second pass)
+#pragma unroll
+        for (int q = 0; q < NE; q++)
+          if (q == p / W) {
+            const double s = __shfl_sync(FM_FULL, v[q], p);
+            if (!(s > 0.0)) {
+              if (lane == 0) *s_stop = p + 1;
+            } else {
+              const double ljj = sqrt(s);
+              v[q] = (lane == p) ? ljj : xdiv(v[q], ljj);
+              if (lane >= p && lane < kf) s_L[p][lane] = v[q];
+            }
+          }
+      }
+      chain_sync();
+      if (*s_stop) break;
+      const double lip = s_L[p][ri < kf ? ri : 0];
+#pragma unroll
+      for (int q = 0; q < NE; q++) {
+        const int cj = warp + W * q;
+        if (ri < kf && cj < kf && ri >= cj && cj > p) v[q] = xsub(v[q], xmul(lip, s_L[p][cj]));
+      }
+    }
+    if (*s_stop) {  // mvrnorm: "'Sigma' is not positive definite"
+      if (t == 0) set_error(rb.err, FMCMC_ENOTPD, c + 1, row);
       return;
     }
-    if (ri < kf && cj < kf) L[ri + cj * kf] = active ? v : 0.0;   // cached for the rows that do not re-adapt
-    if (tid == 0) *cflag |= 2;
+#pragma unroll
+    for (int q = 0; q < NE; q++) {   // cached for the rows that do not re-adapt
+      const int cj = warp + W * q;
+      if (ri < kf && cj < kf) L[ri + cj * kf] = (ri >= cj) ? v[q] : 0.0;
+    }
+    if (t == 0) *cflag |= 2;
   }
   if (warp == 0) {
     for (int a = lane; a < kf; a += FM_WARP) s_z[a] = draw_z(sp, rb, cx, a);
