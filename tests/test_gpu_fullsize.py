@@ -199,6 +199,30 @@ def test_cfg3_full_n_against_the_oracle(oracle, cfg3_data):
     assert 0.02 < acc.mean() < 0.98                 # the comparison saw both accepted and rejected proposals
 
 
+def test_cfg3_full_n_near_the_mode_against_the_oracle(oracle, cfg3_data):
+    """The same at the posterior mode, where the bench's chains end up: |eta| reaches 4.7 and the chains' bound on it 10.4 - the
+    upper part of the bank-group-replicated cubic table (|eta| <= 11.15) is what the hot loop reads - with kernel_adapt adapting
+    on every row (warm-up 3), 192 chains (two chain blocks: two observation slices per CTA) x 24 fed-stream rows = 4 416 oracle
+    chain-steps over 1e6 observations: every decision identical, samples and log-posteriors within 1e-12."""
+    import bench
+    import fmcmc_b200 as fm
+    from gpu_util import assert_parity, run_both
+    X, y = cfg3_data
+    p = X.shape[1]
+    C, T = 192, 24
+    beta = np.random.Generator(np.random.PCG64(bench.DATA_SEED + 7919)).standard_normal(p)   # the generating beta* (bench.make_data)
+    rng = np.random.default_rng(29)
+    init = beta + rng.normal(0, 2e-3, (C, p))
+    spec = dict(type=A.KERNEL_ADAPT, k=p, mu=0.0, warmup=3, freq=1, eps=1e-6)
+    g, o, _ = run_both(oracle, fm.ll_logistic(X, y, prior_sd=2.0), spec, init, T, C, rng=rng)
+    assert g[0]["report"].path == 4
+    assert_parity(g[0], o[0], RTOL, "cfg3 full n, mode, adapt")
+    acc = np.any(g[0]["ans"][:, 1:] != g[0]["ans"][:, :-1], axis=2)
+    assert 0.02 < acc.mean() < 0.98
+    bound = np.linalg.norm(g[0]["ans"][:, -1, :], axis=1) * np.sqrt((X * X).sum(axis=1).max())
+    assert 9.5 < bound.max() < 11.15                 # inside the replicated table, near its end
+
+
 def test_cfg5_shape_against_the_oracle(oracle):
     """BASELINE configs[4]'s geometry (Gaussian, 127 columns + sd: four K blocks, Theta slices split between tensor and
     shared memory, 6 slices) at n = 300 000 against the CPU oracle: decisions identical, samples and log-posteriors 1e-12."""
